@@ -1,0 +1,191 @@
+"""Drop-in for the reference's train/model_helpers.py: sample generation, field evaluation, X-ray line
+integral and the training losses (reference train/model_helpers.py:3-289), with the heavy lifting in
+libnerfca_b200.so.  Function names, argument order and return tuples follow upstream so that
+run_nerf.py / run_composite.py import it unchanged (`from model_helpers import *`).
+
+Differences that are deliberate and invisible to the drivers:
+  * obtain_train_predictions_* never materialise the [B*N,3] point tensor: the kernels form
+    fl32(fl64(o + d z)) in registers from the float64 ray rows (bit-identical positions);
+  * the python chunk loop (get_minibatches*, `chunksize`) is replaced by the kernels' tile loop, so
+    `chunksize` / `batch_size` is accepted and ignored;
+  * the hierarchical fine pass (depth_samples_per_ray_fine > 0) is not built yet.
+"""
+import torch
+
+from nerfca import ops
+
+
+# ---- A3 -------------------------------------------------------------------------------------------------
+
+def randomize_depth(z_vals, device):
+    """Stratified jitter of the shared depth vector; the uniform draw comes from the CPU generator exactly like
+    upstream (:8) so seeded runs see the same samples, the arithmetic runs on the device."""
+    t_rand = torch.rand(z_vals.shape)
+    return ops.jitter_depth(z_vals.to(device), t_rand)
+
+
+# ---- A8: chunk helpers (kept for API parity; the CUDA path does not need them) -----------------------------
+
+def get_minibatches(inputs, chunksize=1024 * 8):
+    return [[inputs[i:i + chunksize]] for i in range(0, inputs.shape[0], chunksize)]
+
+
+def get_minibatches_time(inputs, time_inputs, chunksize=1024 * 8):
+    return [[inputs[i:i + chunksize], time_inputs[i:i + chunksize]] for i in range(0, inputs.shape[0], chunksize)]
+
+
+def get_predictions_static(static_model, flattened_query_points, chunksize):
+    return static_model(flattened_query_points)
+
+
+def get_predictions_composite(static_model, temp_model, flattened_query_points, flattened_time_points, chunksize,
+                              use_nerf_acc=False):
+    if use_nerf_acc:
+        raise NotImplementedError("use_nerf_acc=True is dead code upstream (it concatenates None, model_helpers.py:41-58)")
+    return static_model(flattened_query_points), temp_model.forward_composite(flattened_query_points, flattened_time_points)
+
+
+# ---- A9 -------------------------------------------------------------------------------------------------
+
+def get_activation_func(output_activation):
+    if output_activation == 'softplus':
+        return torch.nn.Softplus()
+    if output_activation == 'clamp':
+        return lambda x: torch.nn.functional.hardtanh(torch.nn.Softplus()(x), min_val=0., max_val=1.)
+    return torch.nn.Sigmoid()
+
+
+def _last_channel(field):
+    return field if field.shape[-1] == 1 else field[..., -1:].contiguous()
+
+
+def _check_scale(scale_value):
+    if scale_value != 1e-2:
+        raise NotImplementedError("the line-integral kernels are built for scale_value = 1e-2 (the only value upstream uses)")
+
+
+def render_volume_density_composite(static_radiance_field, temp_radiance_field, initial_intensities, ray_directions,
+                                    depth_values, output_activation='softplus', scale_value=1e-2):
+    """-> (int_map[B], static_sigma[B,N], temp_sigma[B,N], dists[N]); dtypes follow ray_directions.dtype like upstream."""
+    _check_scale(scale_value)
+    acc64 = ray_directions.dtype == torch.float64
+    return ops.IntegrateFunction.apply(_last_channel(static_radiance_field), _last_channel(temp_radiance_field),
+                                       initial_intensities, depth_values, ops.activation_code(output_activation), acc64)
+
+
+def render_volume_density(radiance_field, initial_intensities, ray_directions, depth_values, output_activation='softplus',
+                          scale_value=1e-2):
+    """-> (int_map[B], sigma[B,N] (unscaled, as upstream), dists[N])."""
+    _check_scale(scale_value)
+    acc64 = ray_directions.dtype == torch.float64
+    return ops.IntegrateFunction.apply(_last_channel(radiance_field), None, initial_intensities, depth_values,
+                                       ops.activation_code(output_activation), acc64)
+
+
+# ---- A4 + A6/A7 + A9: the two step functions the drivers call ----------------------------------------------
+
+def obtain_train_predictions_static(static_model, batch_origins, batch_directions, batch_initial_intensities, depth_values,
+                                    output_activation, batch_size, device):
+    z = randomize_depth(depth_values, device)
+    samples = ops.Samples.from_rays(batch_origins.to(device), batch_directions.to(device), z)
+    raw = static_model.forward_rays(samples).reshape(batch_origins.shape[0], z.shape[0], static_model.num_output_channels)
+    return render_volume_density(raw, batch_initial_intensities, batch_directions, z, output_activation)
+
+
+def obtain_train_predictions_iter(static_model_coarse, temp_model_coarse, static_model_fine, temp_model_fine, batch_origins,
+                                  batch_directions, batch_phases, batch_initial_intensities, depth_values, output_activation,
+                                  batch_size, depth_samples_per_ray_fine, device):
+    if depth_samples_per_ray_fine > 0:
+        raise NotImplementedError("hierarchical fine pass (depth_samples_per_ray_fine > 0) is not built; "
+                                  "the shipped composite.txt sets it to 0")
+    z = randomize_depth(depth_values, device)
+    n_rays, n_depth = batch_origins.shape[0], z.shape[0]
+    # upstream repeats the per-ray phase over the samples (run_composite.py:265); all entries of a row are equal
+    phase_ray = batch_phases.reshape(n_rays, -1)[:, 0]
+    samples = ops.Samples.from_rays(batch_origins.to(device), batch_directions.to(device), z, phase_ray.to(device))
+    shape = (n_rays, n_depth, temp_model_coarse.num_output_channels)
+    raw_s = static_model_coarse.forward_rays(samples).reshape(shape)
+    raw_d = temp_model_coarse.forward_rays(samples).reshape(shape)
+    pix, sig_s, sig_d, dists = render_volume_density_composite(raw_s, raw_d, batch_initial_intensities, batch_directions, z,
+                                                               output_activation)
+    return pix, sig_s, sig_d, dists, None, None, None, None
+
+
+def sample_pdf(bins, weights, N_samples, device):
+    raise NotImplementedError("sample_pdf belongs to the hierarchical fine pass, which is not built (SURVEY 8(f) N3)")
+
+
+# ---- A10: regularisers on the per-sample attenuations -------------------------------------------------------
+# These consume [B,N] sigma tensors returned by the renderers above; written as device tensor expressions so any
+# caller-side combination stays differentiable.  The fused step (nerfca.train_step) evaluates the same terms and
+# their closed-form gradient in one kernel.
+
+def compute_ratio(sigma_s, sigma_d, favor_s_opt=None, sigma_s_max=None, sigma_d_max=None, weight_max=0.05):
+    with torch.no_grad():
+        sigma_s_max, sigma_d_max = sigma_s.max(), sigma_d.max()
+    return sigma_d / (sigma_s + sigma_d + 1e-10), sigma_s_max, sigma_d_max
+
+
+def compute_blendw_loss(blendw, clip_threshold=1e-19, skewness=1):
+    b = (blendw ** skewness).clip(min=clip_threshold, max=1 - clip_threshold)
+    r = (1 - b).clip(min=clip_threshold)
+    return (-(b * b.log() + r * r.log())).mean(dim=-1).mean()
+
+
+def compute_sigma_s_ray_loss(sigma_s, dists, mask_threshold=0.1, clip_threshold=1e-19, use_weighting=False, weighted_pixs=[],
+                             weighted_thresh=0.25):
+    contrib = sigma_s * dists
+    total = contrib.sum(dim=-1, keepdim=True)
+    keep = torch.where(total < mask_threshold, 0., 1.).flatten().int()
+    if use_weighting and len(weighted_pixs) > 0:
+        moving = torch.zeros_like(keep)
+        moving[:weighted_pixs.shape[0]] = (weighted_pixs > 1 + weighted_thresh).int()
+        keep = keep | moving
+    p = contrib / total.clip(min=clip_threshold)
+    entropy = keep * -(p * (p + 1e-10).log()).sum(dim=-1)
+    return entropy.mean(), total.mean()
+
+
+def compute_occl_loss(sigma_s, dists, reg_perc=0.1, use_back=False):
+    travelled = dists.cumsum(dim=0)[None, :].expand(sigma_s.shape[0], -1)
+    length = travelled[-1, -1]
+    near_source = (travelled < reg_perc * length).int()
+    far_side = (travelled > (1 - reg_perc) * length).int() if use_back else torch.ones_like(near_source)
+    return (sigma_s * dists * (near_source | far_side)).sum(dim=-1).mean()
+
+
+def compute_losses(static_sigma, temp_sigma, dists, weighted_pixs, run_args):
+    blendw, sigma_s_max, sigma_d_max = compute_ratio(static_sigma, temp_sigma, run_args.favor_s_opt)
+    favor_s_loss = compute_blendw_loss(blendw, skewness=run_args.skewness_val)
+    s_entropy, s_sum = compute_sigma_s_ray_loss(static_sigma, dists, mask_threshold=run_args.entro_mask_thre)
+    d_entropy, d_sum = compute_sigma_s_ray_loss(temp_sigma, dists, mask_threshold=run_args.entro_mask_thre,
+                                                use_weighting=run_args.entro_use_weighting, weighted_pixs=weighted_pixs,
+                                                weighted_thresh=run_args.entro_weighted_thresh)
+    d_occl = compute_occl_loss(temp_sigma, dists, run_args.occl_reg_perc)
+    s_contrib = static_sigma * dists
+    return (blendw.mean(), sigma_s_max, sigma_d_max, favor_s_loss, s_entropy, s_sum, d_entropy, d_sum, d_occl,
+            s_contrib.sum(dim=-1).sum(), (s_contrib ** 2).sum(dim=-1).sum())
+
+
+# ---- schedules ----------------------------------------------------------------------------------------------
+
+def linear_param_decay(curr_iter, start_weight, end_weight, steps, delay_steps=0):
+    if curr_iter < delay_steps:
+        return 0
+    alpha = min((curr_iter - delay_steps) / steps, 1.0)
+    return (1.0 - alpha) * start_weight + alpha * end_weight
+
+
+def exp_param_decay(curr_iter, start_weight, end_weight, steps, delay_steps=0):
+    if curr_iter < delay_steps:
+        return 0
+    if start_weight == end_weight:
+        return start_weight
+    if curr_iter >= steps:
+        return end_weight
+    return start_weight * (end_weight / start_weight) ** (curr_iter / (steps - 1))
+
+
+class weighted_MSELoss(torch.nn.Module):
+    def forward(self, preds, gts, weights):
+        return ((preds - gts) ** 2) * weights

@@ -1,0 +1,366 @@
+"""GPU parity tests: every call goes through the C ABI (ctypes) into the sm_100a kernels and is compared with
+(a) fixtures produced by the unmodified reference and (b) the CPU oracle on seeded inputs.
+Bit-exact where the reference's arithmetic is integer / fp32-elementwise (rays, depths, sample positions); stated
+tolerances (tests/parity.py) for the MLP-dependent quantities."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import state_dict_from
+from oracle import nerfca_oracle as orc
+import parity
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+PRECISIONS = ["fp32", "bf16"]
+
+GEOS = [
+    {"DSD": 20.0, "DSO": 6.0, "nDetector": [16, 12], "dDetector": [200 * 0.01 / 16, 200 * 0.01 / 12], "offDetector": [0.0, 0.0, 0.0]},
+    {"DSD": 11.98, "DSO": 7.65, "nDetector": [9, 14], "dDetector": [0.0308, 0.0291], "offDetector": [0.013, -0.027, 0.0]},
+    {"DSD": 20.0, "DSO": 6.0, "nDetector": [64, 64], "dDetector": [200 * 0.01 / 64, 200 * 0.01 / 64], "offDetector": [0.0, 0.0, 0.0]},
+]
+VIEWS = [(-30.0, 30.0), (-30.0, -30.0), (60.0, -30.0), (60.0, 30.0), (-5.0, 40.0), (17.3, -12.9)]
+
+
+def ulp_diff(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, dtype=np.float32).view(np.int32).astype(np.int64)
+    a = np.where(a < 0, np.int64(-2147483648) - a, a)
+    b = np.where(b < 0, np.int64(-2147483648) - b, b)
+    return np.abs(a - b)
+
+
+# ---- A2 / A3 / A4: bit-exact ---------------------------------------------------------------------------------
+
+def test_rays_bit_exact(golden):
+    import proj_helpers as ph
+    g = golden("geometry")
+    for gi, geo in enumerate(GEOS):
+        for vi, (th, phi) in enumerate(VIEWS):
+            o, d = ph.get_ray_values_tigre(th, phi, 0, geo, DEV)
+            assert o.dtype == np.float32 and o.shape == (geo["nDetector"][0], geo["nDetector"][1], 3)
+            assert np.array_equal(o, g[f"g{gi}_v{vi}_o"]) and np.array_equal(d, g[f"g{gi}_v{vi}_d"]), (gi, vi)
+
+
+def test_depth_jitter_bit_exact(golden):
+    import model_helpers as mh
+    import proj_helpers as ph
+    from nerfca import ops
+    g = golden("depth")
+    for k in range(3):
+        z = torch.from_numpy(g[f"c{k}_z"]).to(DEV)
+        assert np.array_equal(ops.jitter_depth(z, torch.from_numpy(g[f"c{k}_t"])).cpu().numpy(), g[f"c{k}_zj"])
+        torch.manual_seed(10 + k)     # same CPU generator stream as the reference's randomize_depth
+        assert np.array_equal(mh.randomize_depth(z, DEV).cpu().numpy(), g[f"c{k}_zj"])
+        near, far, n = g[f"c{k}_nf"]
+        torch.manual_seed(10 + k)
+        assert np.array_equal(ph.get_depth_values(float(near), float(far), int(n), DEV).cpu().numpy(), g[f"c{k}_zj"])
+
+
+def test_sample_points_bit_exact(golden):
+    from nerfca import ops
+    # eval path: float32 rays (golden from run_composite.py:351)
+    g = golden("render")
+    o, d, z = (torch.from_numpy(g[k]).to(DEV) for k in ("origins", "dirs", "z"))
+    pts = ops.sample_points(ops.Samples.from_rays(o, d, z))
+    assert np.array_equal(pts.cpu().numpy(), g["points"])
+    # training path: float64 rows of the ray table, strided views like batch_rays[:,0,:] (oracle == reference expression)
+    rays, _, zt = parity.synthetic_batch(777, 129, seed=3)
+    want = orc.sample_points(rays[:, 0, :], rays[:, 1, :], zt).numpy()
+    rd = rays.to(DEV)
+    got = ops.sample_points(ops.Samples.from_rays(rd[:, 0, :], rd[:, 1, :], zt.to(DEV)))
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_sample_points_full_size_properties():
+    """Config-2 size (1024 x 500): bit-exact vs the oracle expression evaluated on the GPU's own host, plus ray-major indexing."""
+    from nerfca import ops
+    rays, _, z = parity.synthetic_batch(1024, 500, seed=11)
+    rd = rays.to(DEV)
+    got = ops.sample_points(ops.Samples.from_rays(rd[:, 0, :], rd[:, 1, :], z.to(DEV))).cpu()
+    want = orc.sample_points(rays[:, 0, :], rays[:, 1, :], z)
+    assert torch.equal(got, want)
+    assert got.shape == (1024 * 500, 3)
+    r, s = 513, 499
+    assert torch.equal(got[r * 500 + s], (rays[r, 0] + rays[r, 1] * z[s].double()).float())
+
+
+# ---- A5: encoding ---------------------------------------------------------------------------------------------
+
+def test_encoding_within_2ulp_of_reference(golden):
+    from model.CPPN import CPPN
+    g = golden("encoding")
+    x = torch.from_numpy(g["x"]).to(DEV)
+
+    def enc(mode, L=12, **kw):
+        m = CPPN(parity.static_definition(DEV, 8, 0, L, mode=mode) | kw).to(DEV)
+        return m
+    m = enc("free_windowed")
+    for tag, it in [("half", 75000), ("early", 1234), ("open", 150000)]:
+        m.update_freq_mask_alpha(it, 150000)
+        got = m.pos_enc(x, 12, "pts").cpu().numpy()
+        want = g[f"free_{tag}_enc"]
+        assert got.shape == want.shape
+        assert np.array_equal(got[:, :3], want[:, :3])
+        assert np.max(np.abs(got - want)) <= 2.4e-7, tag     # 2 ulp at |sin| ~ 1
+    m = enc("nerfies_windowed"); m.update_windowed_alpha(40000, 150000)
+    assert np.max(np.abs(m.pos_enc(x, 12, "pts").cpu().numpy() - g["nerfies_enc"])) <= 2.4e-7
+    m = enc("windowed")
+    assert np.max(np.abs(m.pos_enc(x, 12, "pts").cpu().numpy() - g["plain_enc"])) <= 2.4e-7
+    m = enc("fourier", L=6, fourier_gaussian=torch.from_numpy(g["fourier_g"]), fourier_sigma=1.7)
+    assert np.max(np.abs(m.pos_enc(x, 6, "pts").cpu().numpy() - g["fourier_enc"])) <= 5e-6   # |arg| up to ~60 rad
+    m = enc("none")
+    assert torch.equal(m.pos_enc(x, 0, "pts"), x)
+
+
+# ---- A6 / A7: fields ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_fields_match_reference(golden, precision):
+    g = golden("fields")
+    tol = parity.TOL[precision]
+    x, ph = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["phases"]).to(DEV)
+    for tag, h, ne, L in [("small", 32, 2, 4), ("full", 128, 4, 12)]:
+        if precision == "bf16" and h != 128:
+            continue   # the tcgen05 path is built for hidden == 128 tiles
+        s, t = parity.build_models(state_dict_from(g, f"{tag}_s."), state_dict_from(g, f"{tag}_d."), DEV, precision, h, ne, L,
+                                   mask=g[f"{tag}_mask"])
+        with torch.no_grad():
+            rs, rd = s(x), t.forward_composite(x, ph.int())
+            rd_f = t.forward_composite(x, ph.float())
+        assert rs.shape == (300, 1) and rd.shape == (300, 1)
+        rt, at = (2e-5, 1e-7) if precision == "fp32" else (3e-2, 2e-3)
+        np.testing.assert_allclose(rs.cpu().numpy(), g[f"{tag}_raw_s"], rtol=rt, atol=at)
+        np.testing.assert_allclose(rd.cpu().numpy(), g[f"{tag}_raw_d"], rtol=rt, atol=at)
+        assert torch.equal(rd, rd_f)
+
+
+def test_field_edge_cases():
+    """Empty input, a single point, a ragged count that is not a multiple of any tile, query_time with explicit latents."""
+    sd_s = orc.init_field_state(75, 128, 4, seed=1)
+    sd_d = orc.init_field_state(83, 128, 4, 10, 8, seed=2)
+    mask = np.ones(12, dtype=np.float32)
+    cfg = {"n_freq": 12, "n_hidden": 4, "pos_enc": "free_windowed", "window": torch.ones(12)}
+    for precision in PRECISIONS:
+        s, t = parity.build_models(sd_s, sd_d, DEV, precision, mask=mask)
+        with torch.no_grad():
+            assert s(torch.zeros((0, 3), device=DEV)).shape == (0, 1)
+            for n in (1, 127, 129, 1000):
+                x = (torch.rand(n, 3) * 2 - 1)
+                ph = torch.randint(0, 10, (n,))
+                rt, at = (2e-5, 1e-7) if precision == "fp32" else (3e-2, 2e-3)
+                np.testing.assert_allclose(s(x.to(DEV)).cpu().numpy(), orc.static_field(x, sd_s, cfg).numpy(), rtol=rt, atol=at)
+                np.testing.assert_allclose(t.forward_composite(x.to(DEV), ph.to(DEV)).cpu().numpy(),
+                                           orc.dynamic_field(x, ph, sd_d, cfg).numpy(), rtol=rt, atol=at)
+            lat = sd_d["time_latents"][ph]
+            np.testing.assert_allclose(t.query_time(x.to(DEV), lat.to(DEV)).cpu().numpy(),
+                                       orc.dynamic_field(x, ph, sd_d, cfg).numpy(), rtol=rt, atol=at)
+
+
+# ---- A9: line integral ----------------------------------------------------------------------------------------
+
+def test_integral_matches_reference(golden):
+    import model_helpers as mh
+    g = golden("activations")
+    rs, rd, z, i0 = (torch.from_numpy(g[k]).to(DEV) for k in ("raw_s", "raw_d", "z", "i0"))
+    for act in ["softplus", "clamp", "Softplus"]:
+        for tag, dt in [("f32", torch.float32), ("f64", torch.float64)]:
+            dirs = torch.zeros(6, 3, dtype=dt, device=DEV)
+            pix, ss, sd, dists = mh.render_volume_density_composite(rs, rd, i0, dirs, z, act)
+            assert pix.dtype == dt and dists.dtype == dt and ss.dtype == torch.float32
+            assert np.array_equal(dists.cpu().numpy(), g[f"{act}_{tag}_dists"])
+            np.testing.assert_allclose(ss.cpu().numpy(), g[f"{act}_{tag}_ss"], rtol=3e-6, atol=1e-12)
+            np.testing.assert_allclose(sd.cpu().numpy(), g[f"{act}_{tag}_sd"], rtol=3e-6, atol=1e-12)
+            np.testing.assert_allclose(pix.cpu().numpy(), g[f"{act}_{tag}_pix"], rtol=2e-6)
+            p1, s1, _ = mh.render_volume_density(rs, i0, dirs, z, act)
+            np.testing.assert_allclose(s1.cpu().numpy(), g[f"{act}_{tag}_sig1"], rtol=3e-6, atol=1e-12)
+            np.testing.assert_allclose(p1.cpu().numpy(), g[f"{act}_{tag}_pix1"], rtol=2e-6)
+
+
+def test_integral_autograd_matches_oracle():
+    import model_helpers as mh
+    torch.manual_seed(4)
+    B, N = 7, 33
+    raw_s, raw_d = torch.randn(B, N, 1) * 3, torch.randn(B, N, 1) * 3
+    z = torch.sort(torch.rand(N) * 5 + 3).values
+    i0 = torch.full((B,), parity.I0)
+    gp, gs, gd = torch.randn(B, dtype=torch.float64), torch.randn(B, N), torch.randn(B, N)
+    for act in ["softplus", "clamp", "sigmoid"]:
+        a, b = raw_s.clone().requires_grad_(True), raw_d.clone().requires_grad_(True)
+        pix, ss, sd, _ = orc.integrate_composite(a, b, i0, torch.float64, z, act)
+        ((pix * gp).sum() + (ss * gs).sum() + (sd * gd).sum()).backward()
+        a2, b2 = raw_s.to(DEV).requires_grad_(True), raw_d.to(DEV).requires_grad_(True)
+        pix2, ss2, sd2, _ = mh.render_volume_density_composite(a2, b2, i0.to(DEV), torch.zeros(B, 3, dtype=torch.float64, device=DEV),
+                                                               z.to(DEV), act)
+        ((pix2 * gp.to(DEV)).sum() + (ss2 * gs.to(DEV)).sum() + (sd2 * gd.to(DEV)).sum()).backward()
+        np.testing.assert_allclose(a2.grad.cpu().numpy(), a.grad.numpy(), rtol=2e-5, atol=1e-9)
+        np.testing.assert_allclose(b2.grad.cpu().numpy(), b.grad.numpy(), rtol=2e-5, atol=1e-9)
+        c = raw_s.clone().requires_grad_(True)
+        p1, s1, _ = orc.integrate_single(c, i0, torch.float64, z, act)
+        ((p1 * gp).sum() + (s1 * gs).sum()).backward()
+        c2 = raw_s.to(DEV).requires_grad_(True)
+        p2, s2, _ = mh.render_volume_density(c2, i0.to(DEV), torch.zeros(B, 3, dtype=torch.float64, device=DEV), z.to(DEV), act)
+        ((p2 * gp.to(DEV)).sum() + (s2 * gs.to(DEV)).sum()).backward()
+        np.testing.assert_allclose(c2.grad.cpu().numpy(), c.grad.numpy(), rtol=2e-5, atol=1e-9)
+
+
+# ---- whole training steps against the reference fixtures ------------------------------------------------------------
+
+def _args(hp):
+    return types.SimpleNamespace(favor_s_opt=None, skewness_val=1, entro_mask_thre=hp["entro_mask_thre"],
+                                 entro_use_weighting=hp["entro_use_weighting"], entro_weighted_thresh=hp["entro_weighted_thresh"],
+                                 occl_reg_perc=hp["occl_reg_perc"])
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_composite_step_matches_reference_fixture(golden, precision):
+    """run_composite.py:262-305 through the drop-in functions (autograd path) AND the fused step, vs the reference's outputs."""
+    import model_helpers as mh
+    from nerfca import ops
+    g = golden("composite_step")
+    tol = parity.TOL[precision]
+    hp, it = orc.COMPOSITE_HP, int(g["iter"])
+    rays, phases = torch.from_numpy(g["rays"]).to(DEV), torch.from_numpy(g["phases"]).to(DEV)
+    B, N = rays.shape[0], g["z0"].shape[0]
+    i0 = torch.from_numpy(g["i0"]).to(DEV)
+    fw, ew, ow, lw = g["weights"]
+    want_gs = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("gs.")}
+    want_gd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("gd.")}
+
+    # (1) drop-in autograd path
+    s, t = parity.build_models(state_dict_from(g, "s."), state_dict_from(g, "d."), DEV, precision, mask=g["mask"])
+    torch.manual_seed(77)
+    pix, ss, sd, dists, *rest = mh.obtain_train_predictions_iter(s, t, None, None, rays[:, 0, :], rays[:, 1, :], phases[:, None].repeat(1, N),
+                                                                i0, torch.from_numpy(g["z0"]).to(DEV), "softplus", 32768, 0, DEV)
+    assert rest == [None] * 4 and pix.dtype == torch.float64 and dists.dtype == torch.float64
+    assert np.array_equal(dists.cpu().numpy(), g["dists"])
+    np.testing.assert_allclose(pix.detach().cpu().numpy(), g["pix"], rtol=tol["pix_rtol"], atol=tol["pix_atol"])
+    np.testing.assert_allclose(ss.detach().cpu().numpy(), g["sigma_s"], rtol=tol["sig_rtol"], atol=tol["sig_atol"])
+    np.testing.assert_allclose(sd.detach().cpu().numpy(), g["sigma_d"], rtol=tol["sig_rtol"], atol=tol["sig_atol"])
+    pixel = mh.weighted_MSELoss()(pix, rays[:, 2, 0], rays[:, 3, 0]).mean()
+    terms = mh.compute_losses(ss, sd, dists, rays[:, 3, 0], _args(hp))
+    loss = pixel + fw * terms[3] + ew * terms[6] + ow * terms[8] + lw * terms[10] + lw * terms[9]
+    loss.backward()
+    lt = 1e-4 if precision == "fp32" else 2e-2
+    assert abs(float(loss) - float(g["loss"])) <= lt * abs(float(g["loss"]))
+    np.testing.assert_allclose(np.array([float(v) for v in terms]), g["terms"], rtol=(1e-4 if precision == "fp32" else 5e-2))
+    parity.compare_grads({k: p.grad for k, p in s.named_parameters()}, want_gs, tol, "static.")
+    parity.compare_grads({k: p.grad for k, p in t.named_parameters()}, want_gd, tol, "dynamic.")
+
+    # (2) fused step
+    s2, t2 = parity.build_models(state_dict_from(g, "s."), state_dict_from(g, "d."), DEV, precision, mask=g["mask"])
+    z = ops.jitter_depth(torch.from_numpy(g["z0"]).to(DEV), torch.from_numpy(g["t_rand"]))
+    lc = ops.LossConfig(fw, ew, ow, lw, hp["entro_mask_thre"], hp["entro_weighted_thresh"], hp["entro_use_weighting"], B)
+    tv, pix2 = ops.train_step_composite(s2, t2, rays, phases, i0, z, "softplus", lc)
+    np.testing.assert_allclose(pix2.cpu().numpy(), g["pix"], rtol=tol["pix_rtol"], atol=tol["pix_atol"])
+    assert abs(float(ops.loss_from_terms(tv, lc, B, N)) - float(g["loss"])) <= lt * abs(float(g["loss"]))
+    tv = tv.cpu().numpy()
+    rt = 1e-4 if precision == "fp32" else 5e-2
+    got_terms = [tv[1] / (B * N), tv[2], tv[3], tv[4] / (B * N), tv[5] / B, tv[6] / B, tv[7] / B, tv[8] / B, tv[9] / B, tv[10], tv[11]]
+    np.testing.assert_allclose(got_terms, g["terms"], rtol=rt)
+    np.testing.assert_allclose(tv[0] / B, float(g["pixel_loss"]), rtol=rt)
+    parity.compare_grads({k: p.grad for k, p in s2.named_parameters()}, want_gs, tol, "fused static.")
+    parity.compare_grads({k: p.grad for k, p in t2.named_parameters()}, want_gd, tol, "fused dynamic.")
+
+
+def test_static_step_matches_reference_fixture(golden):
+    """run_nerf.py:205-230 (small 64-wide net: fp32 path) -- drop-in autograd path and the fused static step."""
+    import model_helpers as mh
+    from nerfca import ops
+    g = golden("static_step")
+    tol = parity.TOL["fp32"]
+    rays, i0 = torch.from_numpy(g["rays"]).to(DEV), torch.from_numpy(g["i0"]).to(DEV)
+    want = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("gs.")}
+    s, _ = parity.build_models(state_dict_from(g, "s."), None, DEV, "fp32", 64, 3, 8, mask=g["mask"])
+    torch.manual_seed(78)
+    pix, sig, dists = mh.obtain_train_predictions_static(s, rays[:, 0, :], rays[:, 1, :], i0, torch.from_numpy(g["z0"]).to(DEV),
+                                                         "softplus", 256, DEV)
+    assert np.array_equal(dists.cpu().numpy(), g["dists"])
+    np.testing.assert_allclose(pix.detach().cpu().numpy(), g["pix"], rtol=tol["pix_rtol"])
+    np.testing.assert_allclose(sig.detach().cpu().numpy(), g["sigma"], rtol=tol["sig_rtol"])
+    occl = mh.compute_occl_loss(sig, dists)
+    loss = mh.weighted_MSELoss()(pix, rays[:, 2, 0], rays[:, 3, 0]).mean() + 1e-4 * occl
+    loss.backward()
+    assert float(occl) == pytest.approx(float(g["occl"]), rel=1e-5) and float(loss) == pytest.approx(float(g["loss"]), rel=1e-5)
+    parity.compare_grads({k: p.grad for k, p in s.named_parameters()}, want, tol)
+    s2, _ = parity.build_models(state_dict_from(g, "s."), None, DEV, "fp32", 64, 3, 8, mask=g["mask"])
+    z = ops.jitter_depth(torch.from_numpy(g["z0"]).to(DEV), torch.from_numpy(g["t_rand"]))
+    tv, pix2 = ops.train_step_static(s2, rays, i0, z, "softplus", 1e-4)
+    np.testing.assert_allclose(pix2.cpu().numpy(), g["pix"], rtol=tol["pix_rtol"])
+    lc = ops.LossConfig(occl_weight=1e-4)
+    assert float(ops.loss_from_terms(tv, lc, rays.shape[0], 33, static_only=True)) == pytest.approx(float(g["loss"]), rel=1e-5)
+    parity.compare_grads({k: p.grad for k, p in s2.named_parameters()}, want, tol, "fused ")
+
+
+def test_render_path_matches_reference_fixture(golden):
+    """Eval path run_composite.py:346-361,407-413: float32 rays, float phases, three images."""
+    import model_helpers as mh
+    import proj_helpers as ph
+    from nerfca import ops
+    g = golden("render")
+    s, t = parity.build_models(state_dict_from(g, "s."), state_dict_from(g, "d."), DEV, "fp32", 64, 2, 10, mask=np.ones(10, dtype=np.float32))
+    s.eval(); t.eval()
+    o, d = ph.ray_values_tigre_device(60.0, 30.0, 0, GEOS[0], DEV)
+    z = torch.from_numpy(g["z"]).to(DEV)
+    n = z.shape[0]
+    with torch.no_grad():
+        # (1) the reference's own sequence of calls
+        q = (o.reshape(-1, 3)[..., None, :] + d.reshape(-1, 3)[..., None, :] * z[..., :, None]).reshape((-1, 3)).float()
+        assert np.array_equal(q.cpu().numpy(), g["points"])
+        bp = torch.full((q.shape[0],), float(g["phase"]), device=DEV)
+        rs, rd = mh.get_predictions_composite(s, t, q, bp, 4096)
+        i0 = torch.full((o.shape[0] * o.shape[1],), parity.I0, device=DEV)
+        pix, ss, sd, dists = mh.render_volume_density_composite(rs.reshape(-1, n, 1), rd.reshape(-1, n, 1), i0, d.reshape(-1, 3), z, "softplus")
+        assert pix.dtype == torch.float32 and np.array_equal(dists.cpu().numpy(), g["dists"])
+        np.testing.assert_allclose(pix.cpu().numpy(), g["pix"], rtol=2e-5)
+        np.testing.assert_allclose(ss.cpu().numpy(), g["sigma_s"], rtol=1e-4)
+        np.testing.assert_allclose(sd.cpu().numpy(), g["sigma_d"], rtol=1e-4)
+        # (2) the fused frame renderer (points formed in-kernel)
+        p, p_s, p_d = ops.render_frame(s, t, o, d, z, int(g["phase"]), parity.I0, rays_per_pass=50)
+        np.testing.assert_allclose(p.cpu().numpy(), g["pix"], rtol=2e-5)
+        np.testing.assert_allclose(p_s.cpu().numpy(), g["pix_static"], rtol=2e-5)
+        np.testing.assert_allclose(p_d.cpu().numpy(), g["pix_dynamic"], rtol=2e-5)
+
+
+# ---- seeded oracle comparisons at larger sizes + size-independent properties ---------------------------------------
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("fused", [True, False])
+def test_composite_step_vs_oracle(precision, fused):
+    res = parity.run_composite_step_parity(n_rays=96, n_depth=77, precision=precision, seed=5, fused=fused)
+    assert res["grad_cos_min"] >= parity.TOL[precision]["grad_cos"]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_full_size_step_properties(precision):
+    """Config-2 batch (1024 rays x 500 samples): determinism of the forward, and ray-shard additivity of the gradients
+    (the multi-GPU contract: sum of shard gradients with the global 1/B == single-device gradients)."""
+    from nerfca import ops
+    n_rays, n_depth, it = 1024, 500, 50000
+    sd_s = orc.init_field_state(75, 128, 4, seed=1)
+    sd_d = orc.init_field_state(83, 128, 4, 10, 8, seed=2)
+    mask, _ = orc.freq_mask(12, it, 150000, 1)
+    rays, phases, z = parity.synthetic_batch(n_rays, n_depth, seed=9)
+    rays, phases, z = rays.to(DEV), phases.to(DEV), z.to(DEV)
+    i0 = torch.full((n_rays,), parity.I0, device=DEV)
+    w = orc.schedule_weights(it, orc.COMPOSITE_HP)
+    lc = ops.LossConfig(w["favor_s"], w["dyn_entro"], w["occl"], w["l1"], 1e-4, 0.03, True, n_rays)
+
+    def run(sl):
+        s, t = parity.build_models(sd_s, sd_d, DEV, precision, mask=mask)
+        tv, pix = ops.train_step_composite(s, t, rays[sl], phases[sl], i0[sl], z, "softplus", lc)
+        return tv, pix, [p.grad.clone() for p in list(s.parameters()) + list(t.parameters())]
+    tv, pix, gr = run(slice(0, n_rays))
+    tv_b, pix_b, _ = run(slice(0, n_rays))
+    assert torch.equal(pix, pix_b)                        # forward is deterministic
+    assert torch.isfinite(pix).all() and all(torch.isfinite(x).all() for x in gr)
+    tv1, pix1, g1 = run(slice(0, 384))
+    tv2, pix2, g2 = run(slice(384, n_rays))
+    assert torch.equal(torch.cat([pix1, pix2]), pix)      # a ray's pixel does not depend on its batch neighbours
+    both = tv1 + tv2
+    both[2:4] = torch.maximum(tv1[2:4], tv2[2:4])
+    np.testing.assert_allclose(both.cpu().numpy(), tv.cpu().numpy(), rtol=1e-9)
+    for a, b, c in zip(g1, g2, gr):
+        assert parity.rel_l2((a + b).cpu().numpy(), c.cpu().numpy()) <= 2e-3   # fp32 atomics: order-dependent rounding only
