@@ -259,11 +259,12 @@ size_t tc_stash_bytes(const nerfca_field_t& f, long long P) {
   return (size_t)((P + TILE_M - 1) / TILE_M) * d.tile_stash_bytes;
 }
 
+// backward workspace: [params block][dZ hand-off between layer-group passes: n_tiles * 32 KB]
 size_t tc_workspace_bytes(const nerfca_field_t& f, long long P, int backward) {
   const TcDims d = tc_dims(f);
-  (void)P;
-  if (!backward) return tc_param_bytes(d);
-  return tc_param_bytes(d);
+  size_t n = (tc_param_bytes(d) + 255) & ~(size_t)255;
+  if (backward) n += (size_t)((P + TILE_M - 1) / TILE_M) * 32768;
+  return n;
 }
 
 static int sm_count() {
@@ -300,10 +301,341 @@ int tc_field_forward(const nerfca_field_t& f, const nerfca_samples_t& s, float* 
   return NERFCA_OK;
 }
 
-int tc_field_backward(const nerfca_field_t&, const nerfca_samples_t&, const float*, const void*, void*,
-                      const nerfca_field_grads_t&, cudaStream_t) {
-  set_error("tcgen05 backward not built yet");
-  return NERFCA_E_UNSUPPORTED;
+// ---- backward kernel -----------------------------------------------------------------------------------------------
+// One launch handles a group of at most two consecutive layers (hi, hi-1) for a stream of tiles; the weight-gradient
+// accumulators of those layers stay in TMEM for the CTA's whole lifetime and are flushed once with atomics.
+//   per tile and per layer l of the group (top first):
+//     dgrad   accD[128 x 128]   = dZ_l (K-major A)        x W_l  (MN-major B)      -> epilogue: * 1[H_{l-1} > 0] -> dZ_{l-1}
+//     wgrad   accW_l[out x in] += dZ_l^T (MN-major A)     x H_{l-1} (MN-major B)       (H_{-1} = encoded input X0)
+//     bgrad   accB_l[out x 16] += dZ_l^T (MN-major A)     x side tile (column 2 == 1)
+//   top group only: dZ_{L-1} = d_raw * w_out * 1[H_{L-1} > 0] on the CUDA cores, and
+//     wout    accO[feat x 16]  += H_{L-1}^T (MN-major A)  x side tile (columns 0,1 = bf16 hi / lo split of d_raw)
+//   bottom layer of a Temporal field: latent dgrad accD[128 x 16/32] = dZ_0 x W_0[:, latent columns] -> scatter by phase.
+// Groups hand dZ over through global memory in tile-canonical layout (bulk-copied back into smem by the next launch).
+struct BwdArgs {
+  SampleSrc src;
+  const uint8_t* params;     // packed weights + fp32 block (w_out at fp32 offset n_relu*128)
+  const uint8_t* stash;
+  uint8_t* handoff;          // [n_tiles][32768]
+  const float* d_raw;
+  float* g_w[2];             // fp32 gradient of weight[l_hi], weight[l_hi-1]
+  float* g_b[2];             // may be null
+  float* g_wout; float* g_bout; float* g_lat;
+  long long n_tiles;
+  int kpad0, n_relu, in_dim, enc_dim, n_latent, n_phases;
+  int l_hi, n_layers;        // layers l_hi, l_hi-1 (n_layers in {1,2})
+  int from_raw;              // l_hi == n_relu-1
+  uint32_t w_bytes, tile_stash_bytes;
+};
+
+constexpr int BW_COL_D = 0, BW_COL_W0 = 128, BW_COL_W1 = 256, BW_COL_B0 = 384, BW_COL_B1 = 400, BW_COL_O = 416;
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_backward_kernel(BwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool has_lat = a.n_latent > 0;
+  const int l_lo = a.l_hi - a.n_layers + 1;
+  // smem map: [W(l_hi)][W(l_hi-1)] (32 KB each; layer 0: kpad0*256)  [P][Q][hbuf0][hbuf1][side 4 KB][w_out 512 B][lat acc][bars]
+  uint32_t w_off[2], w_len[2];
+  uint32_t cur = 0;
+  for (int j = 0; j < 2; ++j) {
+    const int l = a.l_hi - j;
+    const bool need = j < a.n_layers && (l > 0 || has_lat);
+    w_off[j] = cur;
+    w_len[j] = need ? (l == 0 ? (uint32_t)a.kpad0 * 256u : 32768u) : 0u;
+    cur += w_len[j];
+  }
+  uint8_t* s_w = smem;
+  uint8_t* s_dz = smem + cur;            // P = s_dz, Q = s_dz + 32768
+  uint8_t* s_h = s_dz + 2 * 32768;       // hbuf0, hbuf1
+  uint8_t* s_side = s_h + 2 * 32768;
+  float* s_wout = reinterpret_cast<float*>(s_side + 4096);
+  float* s_lat = s_wout + 128;
+  const int n_lat_acc = (has_lat && l_lo == 0) ? a.n_phases * a.n_latent : 0;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_lat + ((n_lat_acc + 3) & ~3));
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 6);
+  const uint32_t bar_w = smem_u32(s_bar), bar_load = bar_w + 8, bar_dz = bar_w + 16, bar_d = bar_w + 24, bar_done = bar_w + 32,
+                 bar_free = bar_w + 40;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_init(bar_w, 1); mbar_init(bar_load, 1); mbar_init(bar_dz, 256); mbar_init(bar_d, 1); mbar_init(bar_done, 1);
+      mbar_init(bar_free, 256);
+      mbar_init_fence();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(s_tmem), 512);
+  }
+  for (int i = threadIdx.x; i < 128; i += blockDim.x)
+    s_wout[i] = __ldg(reinterpret_cast<const float*>(a.params + a.w_bytes) + a.n_relu * 128 + i);
+  for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x) s_lat[i] = 0.f;
+  for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_side)[i] = make_uint4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const long long n_my = (a.n_tiles > (long long)blockIdx.x) ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int lat_c0 = a.enc_dim / 8;                                        // first chunk holding latent columns
+  const int lat_n = ((a.enc_dim % 8 + a.n_latent + 15) / 16) * 16;         // MMA N covering them
+
+  if (warp == 8) {
+    if (lane == 0) {
+      // ---- resident weights of the group
+      uint32_t wtot = w_len[0] + w_len[1];
+      if (wtot) {
+        mbar_expect_tx(bar_w, wtot);
+        for (int j = 0; j < 2; ++j) {
+          if (!w_len[j]) continue;
+          const int l = a.l_hi - j;
+          const uint8_t* src = a.params + (l == 0 ? 0 : (size_t)a.kpad0 * 256 + (size_t)(l - 1) * 32768);
+          bulk_g2s(smem_u32(s_w + w_off[j]), src, w_len[j], bar_w);
+        }
+        mbar_wait(bar_w, 0);
+      }
+      uint32_t ph_dz = 0, ph_done = 0, ph_free = 0, ph_load_c = 0;
+      for (long long i = 0; i < n_my; ++i) {
+        const long long tile = blockIdx.x + i * gridDim.x;
+        const uint8_t* st_tile = a.stash + (size_t)tile * a.tile_stash_bytes;
+        if (i > 0) {   // every MMA and every epilogue read of the previous tile's buffers has finished
+          mbar_wait(bar_done, ph_done); ph_done ^= 1;
+          mbar_wait(bar_free, ph_free); ph_free ^= 1;
+        }
+        // ---- tile loads
+        uint32_t bytes = 32768;
+        for (int j = 0; j < a.n_layers; ++j) bytes += (a.l_hi - j > 0) ? 32768u : (uint32_t)a.kpad0 * 256u;
+        mbar_expect_tx(bar_load, bytes);
+        if (a.from_raw) bulk_g2s(smem_u32(s_dz + 32768), st_tile + (size_t)a.kpad0 * 256 + (size_t)a.l_hi * 32768, 32768, bar_load);
+        else            bulk_g2s(smem_u32(s_dz), a.handoff + (size_t)tile * 32768, 32768, bar_load);
+        for (int j = 0; j < a.n_layers; ++j) {
+          const int l = a.l_hi - j;
+          if (l > 0) bulk_g2s(smem_u32(s_h + j * 32768), st_tile + (size_t)a.kpad0 * 256 + (size_t)(l - 1) * 32768, 32768, bar_load);
+          else       bulk_g2s(smem_u32(s_h + j * 32768), st_tile, (uint32_t)a.kpad0 * 256u, bar_load);
+        }
+        mbar_wait(bar_load, ph_load_c); ph_load_c ^= 1;   // the issuing thread observes the bulk copies itself as well
+        const uint32_t acc_first = (i > 0) ? 1u : 0u;
+        for (int j = 0; j < a.n_layers; ++j) {
+          const int l = a.l_hi - j;
+          const uint32_t dz = smem_u32(s_dz + (j & 1) * 32768), other = smem_u32(s_dz + ((j & 1) ^ 1) * 32768);
+          const uint32_t hb = smem_u32(s_h + j * 32768), side = smem_u32(s_side), wl = smem_u32(s_w + w_off[j]);
+          mbar_wait(bar_dz, ph_dz); ph_dz ^= 1;    // dZ_l (and the side tile) are in shared memory
+          tc_fence_after();
+          if (j == 0 && a.from_raw)
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss(tmem + BW_COL_O, desc_mnmajor(other, kk), desc_mnmajor(side, kk), instr_desc(128, 16, 1, 1), acc_first | (kk > 0));
+          if (l > 0) {
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss(tmem + BW_COL_D, desc_kmajor(dz, kk), desc_mnmajor(wl, kk), instr_desc(128, 128, 0, 1), kk > 0);
+            umma_commit(bar_d);
+          } else if (has_lat) {
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss(tmem + BW_COL_D, desc_kmajor(dz, kk), desc_mnmajor(wl + lat_c0 * CHUNK_BYTES, kk), instr_desc(128, lat_n, 0, 1), kk > 0);
+            umma_commit(bar_d);
+          }
+          const int n_in = (l > 0) ? 128 : a.kpad0;
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ss(tmem + (j == 0 ? BW_COL_W0 : BW_COL_W1), desc_mnmajor(dz, kk), desc_mnmajor(hb, kk), instr_desc(128, n_in, 1, 1),
+                    acc_first | (kk > 0));
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ss(tmem + (j == 0 ? BW_COL_B0 : BW_COL_B1), desc_mnmajor(dz, kk), desc_mnmajor(side, kk), instr_desc(128, 16, 1, 1),
+                    acc_first | (kk > 0));
+        }
+        umma_commit(bar_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= 8 epilogue warps: thread = (row, column half) =================
+    const int row = (warp & 3) * 32 + lane, ch = warp >> 2;
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t ph_load = 0, ph_d = 0;
+    for (long long i = 0; i < n_my; ++i) {
+      const long long tile = blockIdx.x + i * gridDim.x;
+      const long long p = tile * TILE_M + row;
+      const bool valid = p < a.src.n_points;
+      mbar_wait(bar_load, ph_load); ph_load ^= 1;
+      float g = 0.f;
+      if (a.from_raw) {
+        // dZ_top = d_raw * w_out * 1[H_top > 0]   (H_top sits in Q)
+        g = valid ? __ldg(a.d_raw + p) : 0.f;
+        const uint8_t* hq = s_dz + 32768;
+        for (int c = ch * 8; c < ch * 8 + 8; ++c) {
+          const uint4 hv = *reinterpret_cast<const uint4*>(hq + c * CHUNK_BYTES + row * 16);
+          const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lo = (hw[e] & 0x7FFFu) ? g * s_wout[c * 8 + 2 * e] : 0.f;         // bf16 h > 0  <=>  magnitude bits set (h >= 0)
+            const float hi = (hw[e] & 0x7FFF0000u) ? g * s_wout[c * 8 + 2 * e + 1] : 0.f;
+            o[e] = pack_bf16x2(lo, hi);
+          }
+          *reinterpret_cast<uint4*>(s_dz + c * CHUNK_BYTES + row * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        if (ch == 0 && a.g_bout) {
+          float sum = g;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (lane == 0) atomicAdd(a.g_bout, sum);
+        }
+      }
+      if (ch == 0) {   // side tile row: [d_hi, d_lo, 1, 0, ...]
+        const __nv_bfloat16 dh = __float2bfloat16_rn(g);
+        const __nv_bfloat16 dl = __float2bfloat16_rn(g - __bfloat162float(dh));
+        const uint32_t w0 = (uint32_t)__bfloat16_as_ushort(dh) | ((uint32_t)__bfloat16_as_ushort(dl) << 16);
+        *reinterpret_cast<uint4*>(s_side + row * 16) = make_uint4(w0, 0x00003F80u, 0u, 0u);   // 0x3F80 = bf16(1.0)
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_dz);
+
+      for (int j = 0; j < a.n_layers; ++j) {
+        const int l = a.l_hi - j;
+        if (!(l > 0 || has_lat)) continue;
+        mbar_wait(bar_d, ph_d); ph_d ^= 1;
+        tc_fence_after();
+        if (l > 0) {
+          const uint8_t* hprev = s_h + j * 32768;
+          uint8_t* out_s = s_dz + ((j & 1) ^ 1) * 32768;
+          const bool to_smem = (j + 1 < a.n_layers);
+          uint8_t* out_g = a.handoff + (size_t)tile * 32768;
+#pragma unroll 1
+          for (int cb = 0; cb < 2; ++cb) {
+            uint32_t v[32];
+            tmem_ld32(t_lane + BW_COL_D + ch * 64 + cb * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int c = ch * 8 + cb * 4 + q4;
+              const uint4 hv = *reinterpret_cast<const uint4*>(hprev + c * CHUNK_BYTES + row * 16);
+              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float lo = (hw[e] & 0x7FFFu) ? __uint_as_float(v[q4 * 8 + 2 * e]) : 0.f;
+                const float hi = (hw[e] & 0x7FFF0000u) ? __uint_as_float(v[q4 * 8 + 2 * e + 1]) : 0.f;
+                o[e] = pack_bf16x2(lo, hi);
+              }
+              const uint4 q = make_uint4(o[0], o[1], o[2], o[3]);
+              if (to_smem) *reinterpret_cast<uint4*>(out_s + c * CHUNK_BYTES + row * 16) = q;
+              else         *reinterpret_cast<uint4*>(out_g + c * CHUNK_BYTES + row * 16) = q;
+            }
+          }
+          tc_fence_before();
+          if (to_smem) {
+            fence_proxy_async();
+            mbar_arrive(bar_dz);
+          }
+        } else {
+          // latent gradient: columns [enc_dim, enc_dim + T) of dX0 live at accD columns enc_dim - 8*lat_c0 + t
+          if (ch == 0) {
+            uint32_t v[16];
+            const int phase = valid ? load_phase(a.src, p) : -1;
+            for (int c0 = 0; c0 < lat_n; c0 += 16) {
+              tmem_ld16(t_lane + BW_COL_D + c0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int t = c0 + e - (a.enc_dim - 8 * lat_c0);
+                if (t >= 0 && t < a.n_latent && phase >= 0 && phase < a.n_phases)
+                  atomicAdd(&s_lat[phase * a.n_latent + t], __uint_as_float(v[e]));
+              }
+            }
+          }
+          tc_fence_before();
+        }
+      }
+      mbar_arrive(bar_free);
+    }
+    // ---- all tiles issued: wait for the last MMAs, then flush the TMEM-resident accumulators
+    if (n_my > 0) {
+      mbar_wait(bar_done, (uint32_t)((n_my - 1) & 1));
+      tc_fence_after();
+      for (int j = 0; j < a.n_layers; ++j) {
+        const int l = a.l_hi - j;
+        const int n_in = (l > 0) ? 128 : a.kpad0, k_in = (l > 0) ? 128 : a.in_dim;
+        float* gw = a.g_w[j];
+        for (int c0 = ch * 64; c0 < n_in && c0 < ch * 64 + 64; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_lane + (j == 0 ? BW_COL_W0 : BW_COL_W1) + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (c0 + e < k_in) atomicAdd(gw + (size_t)row * k_in + c0 + e, __uint_as_float(v[e]));
+        }
+        if (ch == 0) {
+          uint32_t v[16];
+          tmem_ld16(t_lane + (j == 0 ? BW_COL_B0 : BW_COL_B1), v);
+          tmem_ld_wait();
+          if (a.g_b[j]) atomicAdd(a.g_b[j] + row, __uint_as_float(v[2]));
+        }
+      }
+      if (a.from_raw && ch == 1) {
+        uint32_t v[16];
+        tmem_ld16(t_lane + BW_COL_O, v);
+        tmem_ld_wait();
+        atomicAdd(a.g_wout + row, __uint_as_float(v[0]) + __uint_as_float(v[1]));
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (a.g_lat)
+    for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x)
+      if (s_lat[i] != 0.f) atomicAdd(a.g_lat + i, s_lat[i]);
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+static size_t bwd_smem_bytes(const nerfca_field_t& f, const TcDims& d, int l_hi, int n_layers) {
+  size_t w = 0;
+  for (int j = 0; j < n_layers; ++j) {
+    const int l = l_hi - j;
+    if (l > 0) w += 32768;
+    else if (f.n_latent > 0) w += (size_t)d.kpad0 * 256;
+  }
+  const int l_lo = l_hi - n_layers + 1;
+  const int n_lat_acc = (f.n_latent > 0 && l_lo == 0) ? f.n_phases * f.n_latent : 0;
+  return w + 4 * 32768 + 4096 + 128 * sizeof(float) + (size_t)((n_lat_acc + 3) & ~3) * sizeof(float) + 8 * sizeof(uint64_t);
+}
+
+int tc_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, const float* d_raw, const void* stash, void* workspace,
+                      const nerfca_field_grads_t& gr, cudaStream_t st) {
+  const TcDims d = tc_dims(f);
+  NERFCA_REQUIRE(f.n_latent == 0 || (size_t)f.n_phases * f.n_latent * sizeof(float) <= 16 * 1024, NERFCA_E_UNSUPPORTED,
+                 "tcgen05 backward: latent table too large for the shared-memory accumulator (use precision fp32)");
+  NERFCA_REQUIRE(f.n_latent == 0 || (enc_dim_of(f) % 8 + f.n_latent + 15) / 16 * 16 + enc_dim_of(f) / 8 * 8 <= d.kpad0,
+                 NERFCA_E_UNSUPPORTED, "tcgen05 backward: latent columns do not fit the padded first layer");
+  int rc = pack_params(f, d, workspace, st);   // same packing as the forward (weights may have changed since)
+  if (rc) return rc;
+  BwdArgs a;
+  a.src = make_src(s);
+  a.params = (const uint8_t*)workspace;
+  a.stash = (const uint8_t*)stash;
+  a.handoff = (uint8_t*)workspace + ((tc_param_bytes(d) + 255) & ~(size_t)255);
+  a.d_raw = d_raw;
+  a.g_wout = gr.weight[d.n_relu]; a.g_bout = gr.bias[d.n_relu]; a.g_lat = gr.latents;
+  a.n_tiles = (s.n_points + TILE_M - 1) / TILE_M;
+  a.kpad0 = d.kpad0; a.n_relu = d.n_relu; a.in_dim = d.in_dim; a.enc_dim = enc_dim_of(f); a.n_latent = f.n_latent;
+  a.n_phases = f.n_phases;
+  a.w_bytes = (uint32_t)d.w_bytes; a.tile_stash_bytes = (uint32_t)d.tile_stash_bytes;
+  const long long grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
+  size_t max_smem = 0;
+  for (int l_hi = d.n_relu - 1; l_hi >= 0; l_hi -= 2) {
+    const size_t sm = bwd_smem_bytes(f, d, l_hi, l_hi >= 1 ? 2 : 1);
+    max_smem = sm > max_smem ? sm : max_smem;
+  }
+  NERFCA_REQUIRE(max_smem <= 227 * 1024, NERFCA_E_UNSUPPORTED, "field does not fit the backward kernel's shared memory");
+  NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  for (int l_hi = d.n_relu - 1; l_hi >= 0; l_hi -= 2) {
+    a.l_hi = l_hi;
+    a.n_layers = l_hi >= 1 ? 2 : 1;
+    a.from_raw = (l_hi == d.n_relu - 1);
+    for (int j = 0; j < 2; ++j) {
+      const int l = l_hi - j;
+      a.g_w[j] = (j < a.n_layers) ? gr.weight[l] : nullptr;
+      a.g_b[j] = (j < a.n_layers) ? gr.bias[l] : nullptr;
+    }
+    tc_backward_kernel<<<(unsigned)grid, TC_THREADS, bwd_smem_bytes(f, d, l_hi, a.n_layers), st>>>(a);
+    NERFCA_LAUNCH_OK();
+  }
+  return NERFCA_OK;
 }
 
 }  // namespace nerfca
