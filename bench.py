@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- NeRF-CA composite training throughput (rays/s, forward + losses + backward + Adam) on B200.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W [--impl reference]
+  N > 1 is launched with torch.distributed.run, one rank per GPU (NCCL); rays are sharded across ranks
+  (weak scaling: every rank runs the config's 1024-ray batch), the only collective is the gradient all-reduce.
+
+One JSON line is printed by rank 0.  `value` = rays/s with the ray batches already resident in HBM; `e2e` = the same
+step driven through the public host API with pinned HOST buffers (H2D of the batch rows + D2H of the loss terms in
+the timed region); `roofline` = the dominant kernel against the measured bf16 tensor peak; `cpu_baseline` = the CPU
+oracle port (oracle/nerfca_oracle.py, CPU torch, all host threads) timed on a bounded sample of the same workload.
+
+`--impl reference` times the reference's CPU algorithm (the oracle port -- the reference is pure Python/PyTorch and
+/root/reference does not exist on the GPU box) on the box's host cores for the same metric / config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "nerf-ca_b200")
+for _p in (ROOT, PKG, os.path.join(PKG, "train"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# ---- workload: BASELINE.json configs[1] = train/composite.txt ------------------------------------------------------
+N_RAYS = 1024          # composite.txt:40  rays per step (per GPU: weak scaling)
+N_DEPTH = 500          # composite.txt:25
+N_FREQ, HIDDEN, N_EARLY, N_LATENT, N_PHASES = 12, 128, 4, 8, 10
+DET = 200              # 200 x 200 detector, 4 views x 10 cardiac phases = 1.6 M rays
+VIEWS = [(-30.0, 30.0), (-30.0, -30.0), (60.0, -30.0), (60.0, 30.0)]
+GEO = {"DSD": 20.0, "DSO": 6.0, "nDetector": [DET, DET], "dDetector": [200 * 0.01 / DET] * 2, "offDetector": [0.0, 0.0, 0.0]}
+NEAR, FAR = 3.2, 8.8
+I0 = float(np.log(8.670397))
+ITER = 50000           # schedule point: all regularisers active, 5 of 12 bands masked by the frequency window
+FLOP_PER_SAMPLE = 870912      # fwd + bwd, 1 MAC = 2 FLOP, unpadded K, no recompute credit
+FLOP_PER_SAMPLE_FWD = 303104
+LR, LR_END_FACTOR, LR_DECAY_STEPS = 1e-3, 0.01, 150000   # composite.txt:33-35
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_burst": p["bf16_tflops"], "bf16_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "hbm": p["hbm_gbs"], "source": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+# ---- synthetic phantom: a chain of Gaussian blobs (closed-form line integrals) ---------------------------------------
+
+def phantom_blobs(phase: int):
+    """Background blob + a branching 'vessel' of small blobs whose centreline moves with the cardiac phase."""
+    rng = np.random.default_rng(0)
+    t = np.linspace(0, 1, 24)
+    wob = 0.09 * np.sin(2 * np.pi * (phase / N_PHASES) + 3 * t)
+    c1 = np.stack([-0.5 + 1.0 * t + wob, 0.35 * np.sin(3 * t) + wob, -0.4 + 0.8 * t], 1)
+    c2 = np.stack([0.1 + 0.5 * t, -0.2 - 0.5 * t + wob, 0.1 + 0.3 * t - wob], 1)
+    centres = np.concatenate([np.zeros((1, 3)), c1, c2[4:]], 0)
+    sig = np.concatenate([[0.8], np.full(len(c1) + len(c2) - 4, 0.045)])
+    amp = np.concatenate([[0.02], 0.05 + 0.1 * rng.random(len(sig) - 1)])
+    return centres, sig, amp
+
+
+def project_blobs(o: torch.Tensor, d: torch.Tensor, phase: int) -> torch.Tensor:
+    """log-intensity pixel  log I0 - sum_blobs A s sqrt(2 pi) / |d| exp(-dist^2 / 2 s^2)  (float64, on o's device)."""
+    c, s, a = phantom_blobs(phase)
+    c = torch.as_tensor(c, dtype=torch.float64, device=o.device)
+    s = torch.as_tensor(s, dtype=torch.float64, device=o.device)
+    a = torch.as_tensor(a, dtype=torch.float64, device=o.device)
+    o, d = o.double(), d.double()
+    dn = d.norm(dim=-1, keepdim=True)
+    u = d / dn
+    oc = c[None, :, :] - o[:, None, :]
+    along = (oc * u[:, None, :]).sum(-1)
+    dist2 = (oc * oc).sum(-1) - along * along
+    integ = (a * s * np.sqrt(2 * np.pi))[None, :] * torch.exp(-dist2 / (2 * s * s)[None, :])
+    return I0 - integ.sum(-1)
+
+
+def build_ray_table(device):
+    """rays_train [R,4,3] float64 (origin, direction, pixel x3, weight x3) + phases_train [R] int64 in the reference's
+    layout (train/data_helpers.py:141-165), ray id = frame * W * H + i * H + j.  Built on `device`."""
+    import proj_helpers as ph
+    rows, phases = [], []
+    for (theta, phi) in VIEWS:
+        o, d = ph.ray_values_tigre_device(theta, phi, 0, GEO, device)
+        o, d = o.reshape(-1, 3), d.reshape(-1, 3)
+        pix = torch.stack([project_blobs(o, d, p) for p in range(N_PHASES)], 0)          # [phases, W*H]
+        var = pix.var(dim=0)
+        wmap = 1.0 + var / var.max().clamp_min(1e-30)                                     # [1,2] temporal-variance weights
+        for p in range(N_PHASES):
+            r = torch.empty((o.shape[0], 4, 3), dtype=torch.float64, device=device)
+            r[:, 0], r[:, 1] = o.double(), d.double()
+            r[:, 2], r[:, 3] = pix[p][:, None], wmap[:, None]
+            rows.append(r)
+            phases.append(torch.full((o.shape[0],), p, dtype=torch.int64, device=device))
+    return torch.cat(rows, 0), torch.cat(phases, 0)
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---- CPU arm: the oracle port of the reference step ------------------------------------------------------------------------
+
+def cpu_reference_step_fn(n_rays: int, seed: int = 0):
+    """Returns (step, n_rays): one reference training step (obtain_train_predictions_iter + wMSE + compute_losses +
+    backward + Adam, train/run_composite.py:283-308) on CPU torch through the oracle port."""
+    from oracle import nerfca_oracle as orc
+    import parity          # tests/parity.py (a foreign `tests` package may shadow `from tests import ...` on the box)
+    torch.set_num_threads(os.cpu_count() or 1)
+    enc = 3 + 6 * N_FREQ
+    sd_s = {k: v.requires_grad_(True) for k, v in orc.init_field_state(enc, HIDDEN, N_EARLY, seed=1).items()}
+    sd_d = {k: v.requires_grad_(True) for k, v in orc.init_field_state(enc + N_LATENT, HIDDEN, N_EARLY, N_PHASES, N_LATENT, seed=2).items()}
+    mask, _ = orc.freq_mask(N_FREQ, ITER, 150000, 1)
+    cfg = {"n_freq": N_FREQ, "n_hidden": N_EARLY, "pos_enc": "free_windowed", "window": mask}
+    opt = torch.optim.Adam(list(sd_s.values()) + list(sd_d.values()), lr=LR)
+    i0 = torch.full((n_rays,), I0, dtype=torch.float32)
+    state = {"k": 0}
+
+    def step():
+        rays, phases, z = parity.synthetic_batch(n_rays, N_DEPTH, seed + state["k"], N_PHASES, NEAR, FAR)
+        state["k"] += 1
+        loss, _ = orc.composite_step_loss(sd_s, sd_d, cfg, cfg, rays[:, 0, :], rays[:, 1, :], phases, i0, z, rays[:, 2, 0], rays[:, 3, 0],
+                                          orc.COMPOSITE_HP, ITER)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step
+
+
+def time_cpu_arm(n_rays: int, steps: int, warmup: int):
+    step = cpu_reference_step_fn(n_rays)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return n_rays * steps / dt, dt / steps
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample: rays per step sized from a 16-ray probe so that (steps + warmup) steps take about <= 150 s
+    probe_rate, _ = time_cpu_arm(16, 1, 1)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n = int(min(N_RAYS, max(16, 2 ** int(np.floor(np.log2(max(16.0, probe_rate * budget)))))))
+    rate, sec = time_cpu_arm(n, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "training rays/sec (fwd+bwd)", "value": rate, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(extra={"cpu_sample_rays_per_step": n}),
+            "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} rays x {N_DEPTH} samples per step, {args.steps} steps, oracle port of the reference step "
+                                       f"(CPU torch {torch.__version__}, {cores} threads)"},
+            "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(extra=None):
+    c = {"workload": "NeRF-CA composite training step, train/composite.txt: static CPPN + dynamic Temporal, "
+                     "1024 rays x 500 samples per step per GPU, 12 bands, 2 x [in->128, 4 x 128->128, 128->1], "
+                     "200x200 detector x 4 views x 10 phases synthetic blob phantom",
+         "rays_per_step_per_gpu": N_RAYS, "samples_per_ray": N_DEPTH, "hidden": HIDDEN, "n_freq": N_FREQ,
+         "step": "zero_grad + fields fwd + line integral + 11 loss terms + closed-form dL/draw + fields bwd (wgrad/dgrad/latent) "
+                 "+ grad all-reduce (N>1) + Adam",
+         "l2": "per-step working set (activation stash, ~1.5 GB) exceeds the 126 MB L2 and every step uses a distinct ray batch; no explicit flush"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---- GPU arm ------------------------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("NERFCA_PRECISION", "bf16"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    from nerfca import trainer as tr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"WORLD_SIZE {world} != --gpus {args.gpus}"
+
+    torch.manual_seed(0)
+    np.random.seed(0)
+    trainer = tr.CompositeTrainer.from_config(device=dev, precision=args.precision, n_freq=N_FREQ, hidden=HIDDEN, n_early=N_EARLY,
+                                              n_latent=N_LATENT, n_phases=N_PHASES, lr=LR, lr_end_factor=LR_END_FACTOR,
+                                              lr_decay_steps=LR_DECAY_STEPS, i0=I0, near=NEAR, far=FAR, n_depth=N_DEPTH,
+                                              world_size=world, process_group=dist)
+    trainer.set_iteration(ITER)
+    rays_tab, phases_tab = build_ray_table(dev)
+    R = rays_tab.shape[0]
+
+    n_total = args.steps + args.warmup
+    # same host RNG stream on every rank; each rank takes its contiguous slice of the global batch
+    ids_all = np.random.randint(0, R, size=(n_total, world * N_RAYS))[:, rank * N_RAYS:(rank + 1) * N_RAYS]
+    ids_dev = torch.from_numpy(ids_all).to(dev)
+    gen = torch.Generator().manual_seed(1234)
+    t_rand = torch.rand((n_total, N_DEPTH), generator=gen)
+
+    # ---------------- value: batches resident in HBM ----------------
+    batches = [(rays_tab[ids_dev[k]].contiguous(), phases_tab[ids_dev[k]].to(torch.int32).contiguous(), trainer.jitter(t_rand[k]))
+               for k in range(n_total)]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        trainer.step_device(*batches[k])
+    clocks = ClockSampler(local)
+    launches0 = trainer.launch_count
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.warmup, n_total):
+        trainer.step_device(*batches[k])
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    launches = trainer.launch_count - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * N_RAYS * args.steps / (ms * 1e-3)
+    last_terms = trainer.last_terms.clone()
+
+    # ---------------- per-kernel timing (second pass, events inside the library on the launch stream) ----------------
+    kt = trainer.kernel_times(lambda k: trainer.step_device(*batches[args.warmup + (k % args.steps)]), min(args.steps, 20))
+
+    # ---------------- e2e: pinned host batches, H2D + D2H inside the timed region ----------------
+    rays_host = [rays_tab[ids_dev[k]].cpu().pin_memory() for k in range(n_total)]
+    phases_host = [phases_tab[ids_dev[k]].cpu().pin_memory() for k in range(n_total)]
+    trand_host = [t_rand[k].pin_memory() for k in range(n_total)]
+    h2d = rays_host[0].numel() * 8 + phases_host[0].numel() * 8 + trand_host[0].numel() * 4
+    for k in range(args.warmup):
+        trainer.step_host(rays_host[k], phases_host[k], trand_host[k])
+    barrier()
+    e0.record()
+    losses = []
+    for k in range(args.warmup, n_total):
+        losses.append(trainer.step_host(rays_host[k], phases_host[k], trand_host[k]))
+    e1.record()
+    barrier()
+    ms2 = e0.elapsed_time(e1)
+    t = torch.tensor([ms2], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_RAYS * args.steps / (float(t.item()) * 1e-3)
+    d2h = trainer.d2h_bytes_per_step
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    dom = max(kt, key=lambda k: kt[k]["ms_per_step"]) if kt else None
+    roof = None
+    if dom:
+        d = kt[dom]
+        # algorithmic FLOPs of the family per step / launches of that family per step
+        fam_flop = {"field_forward": FLOP_PER_SAMPLE_FWD, "field_backward": FLOP_PER_SAMPLE - FLOP_PER_SAMPLE_FWD}.get(dom, 0) * N_RAYS * N_DEPTH
+        d["flop_per_launch"] = fam_flop / d["launches_per_step"]
+        achieved = d["flop_per_launch"] / (d["ms_per_launch"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
+                "ms_per_launch": d["ms_per_launch"], "launches_per_step": d["launches_per_step"],
+                "share_of_step": d["ms_per_step"] / ms_per_step,
+                "whole_step_frac": (N_RAYS * N_DEPTH * FLOP_PER_SAMPLE / (ms_per_step * 1e-3) / 1e12) / pk["bf16_sustained"],
+                "kernels": {k: {"ms_per_step": v["ms_per_step"], "launches_per_step": v["launches_per_step"]} for k, v in kt.items()}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_cpu = 128
+        rate, sec = time_cpu_arm(n_cpu, 3, 1)
+        cpu = {"value": rate, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"{n_cpu} rays x {N_DEPTH} samples per step, 3 timed steps after 1 warm-up, oracle port of the reference "
+                         f"training step on CPU torch ({sec:.2f} s/step)"}
+
+    line = {"metric": "training rays/sec (fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config({"parallelism": f"rays sharded x{world}, grads all-reduced (NCCL)" if world > 1 else "single GPU",
+                                       "loss_last_step": float(trainer.loss_from(last_terms))}),
+            "clocks": clk, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "loss_last_step": losses[-1] if losses else None},
+            "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -201,6 +201,65 @@ NERFCA_API int nerfca_composite_loss(const float* raw_s, const float* raw_d, con
                           int32_t activation, const nerfca_loss_cfg_t* cfg, double* pix_out, double* terms_out,
                           float* d_raw_s, float* d_raw_d, void* stream);
 
+/* One whole training step of train/run_composite.py:283-305 (minus the optimizer) as ONE call: both fields forward over the
+ * same ray-generated sample set (a single launch on the tcgen05 path), nerfca_composite_loss, both fields backward.
+ * dynamic_field == NULL selects the static run of train/run_nerf.py:205-233.  Scratch is caller-allocated:
+ * raw_* / d_raw_* float32 [P]; stash / workspace of nerfca_step_stash_bytes / nerfca_step_workspace_bytes bytes.
+ * Parameter gradients are accumulated (+=); pix_out float64 [n_rays]; terms_out float64 [NERFCA_N_LOSS_TERMS] (+=).   */
+typedef struct nerfca_step_t {
+  const nerfca_field_t* static_field;
+  const nerfca_field_t* dynamic_field;
+  const nerfca_field_grads_t* static_grads;
+  const nerfca_field_grads_t* dynamic_grads;
+  const nerfca_samples_t* samples;
+  int32_t precision;
+  int32_t activation;
+  const float* i0;              /* device [n_rays]                                                       */
+  const double* gt;             /* device, element r at gt[r * gw_stride]                                 */
+  const double* wpix;
+  int32_t gw_stride;
+  int32_t reserved;
+  const nerfca_loss_cfg_t* loss;
+  float* raw_s; float* raw_d; float* d_raw_s; float* d_raw_d;
+  void* stash; void* workspace;
+  double* pix_out; double* terms_out;
+} nerfca_step_t;
+NERFCA_API size_t nerfca_step_stash_bytes(const nerfca_step_t* step);
+NERFCA_API size_t nerfca_step_workspace_bytes(const nerfca_step_t* step);
+NERFCA_API int nerfca_train_step(const nerfca_step_t* step, void* stream);
+
+/* No-grad evaluation of both fields over one sample set in a single launch (the render path of
+ * train/run_composite.py:346-361): raw_s / raw_d float32 [P]; dynamic_field / raw_d may be NULL.
+ * workspace: nerfca_step_workspace_bytes of a step descriptor with the same fields / samples / precision.          */
+NERFCA_API int nerfca_fields_forward(const nerfca_field_t* static_field, const nerfca_field_t* dynamic_field,
+                          const nerfca_samples_t* samples, int32_t precision, float* raw_s, float* raw_d, void* workspace,
+                          void* stream);
+
+/* N2  torch.optim.Adam + LinearLR of train/run_composite.py:209-215,305-308 over ONE flat fp32 parameter buffer
+ * (params / grads / exp_avg / exp_avg_sq device [n]).  The step counter lives on the device (step_dev, int64,
+ * incremented by the call) so the whole training step can be captured in a CUDA graph.  Update of step t = *step_dev+1:
+ *   lr_t = lr * (1 + (lr_end_factor - 1) * min(t - 1, lr_decay_steps) / lr_decay_steps)      (LinearLR, start_factor 1)
+ *   m = lerp(m, g, 1 - beta1);  v = beta2 v + (1 - beta2) g g;  p -= lr_t / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)
+ * grads are multiplied by grad_scale first (1 on one GPU) and, if zero_grads != 0, cleared afterwards so the next
+ * step's kernels can accumulate without a separate memset.                                             */
+typedef struct nerfca_adam_cfg_t {
+  double lr, beta1, beta2, eps;
+  double lr_end_factor;          /* 1.0 = constant learning rate */
+  int64_t lr_decay_steps;
+} nerfca_adam_cfg_t;
+NERFCA_API int nerfca_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step_dev,
+                     const nerfca_adam_cfg_t* cfg, float grad_scale, int32_t zero_grads, void* stream);
+
+/* Launch accounting and per-kernel device timing (used by bench.py for `gpu_launches` and the roofline line).
+ * nerfca_launch_count: kernels launched by this library since load.  nerfca_profile_enable(1) starts recording a
+ * CUDA-event pair around every kernel family launch on its own stream (reset first); nerfca_profile_enable(0) stops.
+ * nerfca_profile_read synchronises the recorded events and returns total milliseconds and launch count of a family. */
+enum { NERFCA_K_RAYS = 0, NERFCA_K_PACK = 1, NERFCA_K_FIELD_FWD = 2, NERFCA_K_LOSS = 3, NERFCA_K_FIELD_BWD = 4,
+       NERFCA_K_ADAM = 5, NERFCA_K_COUNT = 6 };
+NERFCA_API int64_t nerfca_launch_count(void);
+NERFCA_API int nerfca_profile_enable(int32_t on);
+NERFCA_API int nerfca_profile_read(int32_t kind, double* ms_total, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

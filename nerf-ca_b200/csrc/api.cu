@@ -1,10 +1,43 @@
 // C-ABI plumbing: error state, argument validation and precision dispatch of the field entry points.
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace nerfca {
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+
+// ---- launch accounting / profiling ----------------------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfRec { int kind; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;            // recorded pairs
+static std::vector<ProfRec> g_prof_pool;       // reusable event pairs
+
+ProfScope::ProfScope(int kind, cudaStream_t st) : kind_(kind), st_(st), rec_(nullptr) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec* r = new ProfRec;
+  if (!g_prof_pool.empty()) { *r = g_prof_pool.back(); g_prof_pool.pop_back(); }
+  else { cudaEventCreate(&r->e0); cudaEventCreate(&r->e1); }
+  r->kind = kind;
+  cudaEventRecord(r->e0, st);
+  rec_ = r;
+}
+ProfScope::~ProfScope() {
+  if (!rec_) return;
+  ProfRec* r = static_cast<ProfRec*>(rec_);
+  cudaEventRecord(r->e1, st_);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(*r);
+  delete r;
+}
 
 int validate_field(const nerfca_field_t* f) {
   NERFCA_REQUIRE(f != nullptr, NERFCA_E_ARG, "field is null");
@@ -52,6 +85,14 @@ int tc_field_forward(const nerfca_field_t& f, const nerfca_samples_t& s, float* 
                      cudaStream_t st);
 int tc_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, const float* d_raw, const void* stash,
                       void* workspace, const nerfca_field_grads_t& gr, cudaStream_t st);
+size_t tc_stash_bytes_n(int n_nets, long long P);
+size_t tc_workspace_bytes_n(const nerfca_field_t* const* f, int n_nets, long long P, int backward);
+int tc_fields_forward(const nerfca_field_t* const* f, int n_nets, const nerfca_samples_t& s, float* const* raw_out, void* stash,
+                      void* workspace, int pack, cudaStream_t st);
+int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_samples_t& s, const float* const* d_raw,
+                       const void* stash, void* workspace, int pack, const nerfca_field_grads_t* const* gr, cudaStream_t st);
+
+static size_t up256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 }  // namespace nerfca
 
@@ -59,6 +100,36 @@ using namespace nerfca;
 
 extern "C" const char* nerfca_last_error(void) { return g_last_error.c_str(); }
 extern "C" int nerfca_abi_version(void) { return NERFCA_ABI_VERSION; }
+
+extern "C" int64_t nerfca_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int nerfca_profile_enable(int32_t on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (on) {
+    for (auto& r : g_prof) g_prof_pool.push_back(r);
+    g_prof.clear();
+  }
+  g_prof_on = on != 0;
+  return NERFCA_OK;
+}
+
+extern "C" int nerfca_profile_read(int32_t kind, double* ms_total, int64_t* launches) {
+  NERFCA_REQUIRE(kind >= 0 && kind < NERFCA_K_COUNT && ms_total && launches, NERFCA_E_ARG, "bad kind / null pointer");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms = 0;
+  long long n = 0;
+  for (auto& r : g_prof) {
+    if (r.kind != kind) continue;
+    NERFCA_CUDA_OK(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    NERFCA_CUDA_OK(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms += t;
+    ++n;
+  }
+  *ms_total = ms;
+  *launches = n;
+  return NERFCA_OK;
+}
 
 extern "C" size_t nerfca_field_stash_bytes(const nerfca_field_t* field, int64_t n_points, int32_t precision) {
   if (!field || n_points <= 0) return 0;
@@ -89,6 +160,7 @@ extern "C" int nerfca_field_forward(const nerfca_field_t* field, const nerfca_sa
     if (rc) return rc;
     return tc_field_forward(*field, *samples, raw_out, stash, workspace, (cudaStream_t)stream);
   }
+  ProfScope prof(NERFCA_K_FIELD_FWD, (cudaStream_t)stream);
   return simt_field_forward(*field, *samples, raw_out, stash, workspace, (cudaStream_t)stream);
 }
 
@@ -111,5 +183,110 @@ extern "C" int nerfca_field_backward(const nerfca_field_t* field, const nerfca_s
     if (rc) return rc;
     return tc_field_backward(*field, *samples, d_raw, stash, workspace, *grads, (cudaStream_t)stream);
   }
+  ProfScope prof(NERFCA_K_FIELD_BWD, (cudaStream_t)stream);
   return simt_field_backward(*field, *samples, d_raw, stash, workspace, *grads, (cudaStream_t)stream);
+}
+
+// ---- whole-step entry points ------------------------------------------------------------------------------------------
+static int validate_step(const nerfca_step_t* s, bool training) {
+  NERFCA_REQUIRE(s != nullptr, NERFCA_E_ARG, "step is null");
+  int rc = validate_field(s->static_field);
+  if (rc) return rc;
+  if (s->dynamic_field) {
+    rc = validate_field(s->dynamic_field);
+    if (rc) return rc;
+  }
+  rc = validate_samples(s->samples, s->dynamic_field && s->dynamic_field->n_latent > 0);
+  if (rc) return rc;
+  NERFCA_REQUIRE(s->precision == NERFCA_PREC_FP32 || s->precision == NERFCA_PREC_BF16, NERFCA_E_ARG, "bad precision");
+  if (training) {
+    NERFCA_REQUIRE(!s->samples->points && s->samples->n_rays > 0, NERFCA_E_ARG, "a training step needs ray-generated samples");
+    NERFCA_REQUIRE(s->static_grads && (!s->dynamic_field || s->dynamic_grads), NERFCA_E_ARG, "gradient descriptors missing");
+  }
+  if (s->precision == NERFCA_PREC_BF16) {
+    rc = tc_supported(*s->static_field);
+    if (rc) return rc;
+    if (s->dynamic_field) rc = tc_supported(*s->dynamic_field);
+  }
+  return rc;
+}
+
+extern "C" size_t nerfca_step_stash_bytes(const nerfca_step_t* s) {
+  if (!s || !s->static_field || !s->samples || s->samples->n_points <= 0) return 0;
+  const long long P = s->samples->n_points;
+  if (s->precision == NERFCA_PREC_BF16) return tc_stash_bytes_n(s->dynamic_field ? 2 : 1, P);
+  size_t n = up256(simt_stash_bytes(*s->static_field, P));
+  if (s->dynamic_field) n += up256(simt_stash_bytes(*s->dynamic_field, P));
+  return n;
+}
+
+extern "C" size_t nerfca_step_workspace_bytes(const nerfca_step_t* s) {
+  if (!s || !s->static_field || !s->samples || s->samples->n_points <= 0) return 0;
+  const long long P = s->samples->n_points;
+  if (s->precision == NERFCA_PREC_BF16) {
+    const nerfca_field_t* f[2] = {s->static_field, s->dynamic_field};
+    return tc_workspace_bytes_n(f, s->dynamic_field ? 2 : 1, P, 1);
+  }
+  size_t n = simt_workspace_bytes(*s->static_field, P, 1);
+  if (s->dynamic_field) {
+    const size_t m = simt_workspace_bytes(*s->dynamic_field, P, 1);
+    n = m > n ? m : n;
+  }
+  return n;
+}
+
+extern "C" int nerfca_fields_forward(const nerfca_field_t* fs, const nerfca_field_t* fd, const nerfca_samples_t* samples,
+                                     int32_t precision, float* raw_s, float* raw_d, void* workspace, void* stream) {
+  nerfca_step_t st = {};
+  st.static_field = fs; st.dynamic_field = fd; st.samples = samples; st.precision = precision;
+  int rc = validate_step(&st, false);
+  if (rc) return rc;
+  if (samples->n_points == 0) return NERFCA_OK;
+  NERFCA_REQUIRE(raw_s && (!fd || raw_d), NERFCA_E_ARG, "output pointer is null");
+  NERFCA_REQUIRE(workspace || nerfca_step_workspace_bytes(&st) == 0, NERFCA_E_WORKSPACE, "workspace is null");
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (precision == NERFCA_PREC_BF16) {
+    const nerfca_field_t* f[2] = {fs, fd};
+    float* outs[2] = {raw_s, raw_d};
+    return tc_fields_forward(f, fd ? 2 : 1, *samples, outs, nullptr, workspace, 1, cs);
+  }
+  ProfScope prof(NERFCA_K_FIELD_FWD, cs);
+  rc = simt_field_forward(*fs, *samples, raw_s, nullptr, workspace, cs);
+  if (rc || !fd) return rc;
+  return simt_field_forward(*fd, *samples, raw_d, nullptr, workspace, cs);
+}
+
+extern "C" int nerfca_train_step(const nerfca_step_t* s, void* stream) {
+  int rc = validate_step(s, true);
+  if (rc) return rc;
+  const nerfca_samples_t& smp = *s->samples;
+  if (smp.n_points == 0) return NERFCA_OK;
+  const bool dyn = s->dynamic_field != nullptr;
+  NERFCA_REQUIRE(s->raw_s && s->d_raw_s && (!dyn || (s->raw_d && s->d_raw_d)), NERFCA_E_ARG, "scratch pointer is null");
+  NERFCA_REQUIRE(s->stash && s->workspace, NERFCA_E_WORKSPACE, "stash / workspace is null");
+  NERFCA_REQUIRE(s->i0 && s->gt && s->wpix && s->loss && s->pix_out && s->terms_out, NERFCA_E_ARG, "null pointer");
+  cudaStream_t cs = (cudaStream_t)stream;
+  const nerfca_field_t* f[2] = {s->static_field, s->dynamic_field};
+  const nerfca_field_grads_t* g[2] = {s->static_grads, s->dynamic_grads};
+  float* raws[2] = {s->raw_s, s->raw_d};
+  const float* draws[2] = {s->d_raw_s, s->d_raw_d};
+  const int n = dyn ? 2 : 1;
+  const long long P = smp.n_points;
+  uint8_t* stash_d = (uint8_t*)s->stash + (s->precision == NERFCA_PREC_BF16 ? 0 : up256(simt_stash_bytes(*s->static_field, P)));
+  if (s->precision == NERFCA_PREC_BF16) {
+    rc = tc_fields_forward(f, n, smp, raws, s->stash, s->workspace, 1, cs);
+  } else {
+    ProfScope prof(NERFCA_K_FIELD_FWD, cs);
+    rc = simt_field_forward(*f[0], smp, raws[0], s->stash, s->workspace, cs);
+    if (!rc && dyn) rc = simt_field_forward(*f[1], smp, raws[1], stash_d, s->workspace, cs);
+  }
+  if (rc) return rc;
+  rc = nerfca_composite_loss(s->raw_s, dyn ? s->raw_d : nullptr, smp.depth, s->i0, s->gt, s->wpix, s->gw_stride, smp.n_rays, smp.n_depth,
+                             s->activation, s->loss, s->pix_out, s->terms_out, s->d_raw_s, dyn ? s->d_raw_d : nullptr, stream);
+  if (rc) return rc;
+  if (s->precision == NERFCA_PREC_BF16) return tc_fields_backward(f, n, smp, draws, s->stash, s->workspace, 0, g, cs);
+  ProfScope prof(NERFCA_K_FIELD_BWD, cs);
+  rc = simt_field_backward(*f[0], smp, draws[0], s->stash, s->workspace, *g[0], cs);
+  if (!rc && dyn) rc = simt_field_backward(*f[1], smp, draws[1], stash_d, s->workspace, *g[1], cs);
+  return rc;
 }

@@ -31,12 +31,25 @@ void set_error(const std::string& msg);
 
 #define NERFCA_LAUNCH_OK()                                                                       \
   do {                                                                                           \
+    ::nerfca::note_launch();                                                                     \
     cudaError_t e__ = cudaGetLastError();                                                        \
     if (e__ != cudaSuccess) {                                                                    \
       ::nerfca::set_error(std::string(__func__) + ": kernel launch -> " + cudaGetErrorString(e__)); \
       return NERFCA_E_CUDA;                                                                      \
     }                                                                                            \
   } while (0)
+
+// ---- launch accounting + optional per-kernel device timing (api.cu) -----------------------------------------
+void note_launch();
+// Brackets the launches issued inside its lifetime with two CUDA events on the launching stream when profiling is
+// enabled (nerfca_profile_enable); a no-op otherwise.  kind = NERFCA_K_* of include/nerfca.h.
+struct ProfScope {
+  ProfScope(int kind, cudaStream_t st);
+  ~ProfScope();
+  int kind_;
+  cudaStream_t st_;
+  void* rec_;
+};
 
 inline int enc_dim_of(const nerfca_field_t& f) {
   if (f.enc_mode == NERFCA_ENC_NONE || f.n_freq <= 0) return 3;

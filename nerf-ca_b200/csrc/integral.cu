@@ -274,6 +274,7 @@ extern "C" int nerfca_composite_loss(const float* raw_s, const float* raw_d, con
   c.mask_thre = cfg->entro_mask_thre; c.w_thresh = cfg->entro_weighted_thresh; c.use_weighting = cfg->entro_use_weighting;
   c.b_global = cfg->n_rays_global;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(NERFCA_K_LOSS, st);
   if (!raw_d) {
     static_loss_kernel<<<div_up((long long)n_rays * 32, 128), 128, 0, st>>>(raw_s, depth, i0, gt, wpix, gw_stride, n_rays,
                                                                             n_depth, activation, c, pix_out, terms_out, d_raw_s);

@@ -1,18 +1,27 @@
-// bf16 tensor-core path of the two coordinate MLPs on tcgen05 / TMEM (sm_100a).
+// bf16 tensor-core path of the two coordinate MLPs on tcgen05 / TMEM (sm_100a): forward + two-pass backward.
 //
-// Forward (A5-A7): one persistent CTA per SM evaluates ONE field for a stream of 128-sample tiles.
-//   * all layer weights (bf16, tile-canonical K-major) stay resident in shared memory for the CTA's lifetime
-//     (loaded once with 1-D bulk async copies), biases / output weights in fp32;
-//   * warp 8 lane 0 issues tcgen05.mma (M=128 samples, N=128 features, K=16 per instruction), accumulating each
-//     layer's [128 x 128] fp32 pre-activation in TMEM;
-//   * two epilogue warpgroups (warps 0-3 and 4-7) each own one of two in-flight tiles ("slots"): they build the
-//     layer-0 input (sample point + positional encoding, in registers), and after every layer read the accumulator
-//     with tcgen05.ld, add bias, ReLU, round to bf16 and write the next layer's A operand back to shared memory;
-//     the last layer's 128 -> 1 projection is a per-thread dot product (thread == sample row), so no MMA with N = 1;
-//   * the two slots ping-pong: while one tile's epilogue runs on the CUDA cores the other tile's layer runs on the
-//     tensor core.  mbarriers: act_full[slot] (128 epilogue arrivals) -> MMA, acc_full[slot] (tcgen05.commit) -> epilogue.
-//   * training: every layer's bf16 input/activation tile is also written to the stash in tile-canonical layout so
-//     the backward kernels can bulk-copy it straight back into shared memory as a UMMA operand.
+// Shapes: hidden = 128, 4 hidden layers (5 ReLU layers L0..L4 + the 128 -> 1 output layer), first-layer input padded to
+// kpad0 (multiple of 16, with one extra constant-1 column that carries the layer-0 bias).  One tile = 128 consecutive
+// samples (= UMMA M = TMEM lanes).  All kernels are persistent: grid = #SMs, CTA b serves net (b % n_nets) and walks
+// the tiles  worker, worker + n_workers, ...   Both fields (static CPPN, dynamic Temporal) run in the SAME launch.
+//
+// What lives where
+//   shared memory : the bf16 weights the kernel needs (tile-canonical K-major bytes, read K-major by the forward GEMMs
+//                   and MN-major by the dgrad GEMMs), activation / gradient tiles of the tiles in flight
+//   TMEM          : fp32 accumulators; in the backward kernels the weight-gradient accumulators stay resident for the
+//                   CTA's whole lifetime and are flushed once with vector reductions
+//   HBM           : per tile and net only H0 and H2 (bf16, 32 KB each) are stashed by the forward; the backward
+//                   recomputes H1 (from H0), H3, H4 (from H2) and the encoded input X0 on chip, and hands dZ2 from the
+//                   top pass to the bottom pass.  192 KB per tile and net in total (vs 496 KB for stashing everything).
+//
+// Kernels
+//   tc_forward_kernel   X0 -> H0 .. H4 -> raw.   16 epilogue warps (2 tiles in flight x (row quadrant, column half)),
+//                       1 MMA warp, 1 stash-store warp.  Hidden-layer biases are preloaded into the accumulator with
+//                       tcgen05.st, ReLU is fused into the bf16 conversion, the 128 -> 1 layer is an N = 16 MMA against
+//                       a (hi, lo) bf16 split of the output weights.
+//   tc_bwd_top_kernel   layers 4, 3 (+ output layer): loads H2, recomputes H3, Z4; dZ4 = d_raw * w_out * 1[Z4 > 0];
+//                       wgrad / bias-grad / w_out-grad accumulate in TMEM; writes dZ2 to the hand-off buffer.
+//   tc_bwd_bot_kernel   layers 2, 1, 0: loads dZ2, H0, recomputes H1 and X0; latent gradients by phase.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -20,251 +29,227 @@ namespace nerfca {
 
 using namespace tc;
 
-constexpr int TC_H = 128;            // hidden width the tensor-core kernels are built for
-constexpr int TC_THREADS = 288;      // 2 epilogue warpgroups + 1 MMA / control warp
-constexpr int TC_MAX_RELU_LAYERS = 5;
+constexpr int TC_H = 128;
+constexpr uint32_t TILE_BYTES = 32768;           // one [128 x 128] bf16 tile
+constexpr int TC_N_RELU = 5;
+constexpr int STASH_TILES = 2;                   // H0 and H2
+constexpr int FWD_THREADS = 18 * 32;             // 16 epilogue warps + MMA warp + store warp
+constexpr int BWD_THREADS = 11 * 32;             // 8 epilogue warps + MMA warp + load warp + store warp
+constexpr int FAST_FREQ = 12;                    // band count the register-resident encoder is specialised for
 
-struct TcDims {
-  int in_dim, kpad0, n_relu;         // n_relu = n_hidden + 1 layers that end in ReLU
-  size_t w_bytes;                    // packed bf16 weights of the ReLU layers
-  size_t x0_bytes;                   // one tile of layer-0 input  (kpad0 * 256)
-  size_t tile_stash_bytes;           // x0 + n_relu activation tiles
+// ---- packed parameter block of one net (device memory, also the leading part of the forward kernel's shared memory) --
+//   [W0: kpad0 * 256][W1..W4: 4 x 32768][w_out tile: 4096][fp32: bias[5][128], w_out[128], b_out, pad]
+struct NetDims {
+  int in_dim, enc_dim, kpad0;
+  uint32_t w0_bytes, w_bytes, wout_off, f32_off, pack_bytes;
 };
-static TcDims tc_dims(const nerfca_field_t& f) {
-  TcDims d;
+__host__ __device__ inline uint32_t f32_block_floats() { return TC_N_RELU * 128 + 128 + 32; }
+static NetDims net_dims(const nerfca_field_t& f) {
+  NetDims d;
   d.in_dim = in_dim_of(f);
-  d.kpad0 = (d.in_dim + 15) / 16 * 16;
-  d.n_relu = f.n_hidden + 1;
-  d.w_bytes = (size_t)d.kpad0 * 256 + (size_t)f.n_hidden * 32768;
-  d.x0_bytes = (size_t)d.kpad0 * 256;
-  d.tile_stash_bytes = d.x0_bytes + (size_t)d.n_relu * 32768;
+  d.enc_dim = enc_dim_of(f);
+  d.kpad0 = (d.in_dim + 1 + 15) / 16 * 16;
+  d.w0_bytes = (uint32_t)d.kpad0 * 256u;
+  d.w_bytes = d.w0_bytes + 4u * TILE_BYTES;
+  d.wout_off = d.w_bytes;
+  d.f32_off = d.wout_off + 4096u;
+  d.pack_bytes = d.f32_off + f32_block_floats() * 4u;
   return d;
 }
-// workspace: [packed weights][bias: n_relu * 128 f32][w_out: 128 f32][b_out: 4 f32]
-static size_t tc_param_bytes(const TcDims& d) { return d.w_bytes + ((size_t)d.n_relu * 128 + 128 + 4) * sizeof(float); }
 
 int tc_supported(const nerfca_field_t& f) {
   NERFCA_REQUIRE(f.hidden == TC_H, NERFCA_E_UNSUPPORTED, "the tcgen05 path is built for hidden == 128 (use precision fp32)");
-  NERFCA_REQUIRE(f.n_hidden + 1 <= TC_MAX_RELU_LAYERS, NERFCA_E_UNSUPPORTED, "tcgen05 path: at most 4 hidden layers fit in shared memory");
-  NERFCA_REQUIRE(in_dim_of(f) <= 128, NERFCA_E_UNSUPPORTED, "tcgen05 path: first-layer input wider than 128");
+  NERFCA_REQUIRE(f.n_hidden == TC_N_RELU - 1, NERFCA_E_UNSUPPORTED, "the tcgen05 path is built for 4 hidden layers (use precision fp32)");
+  NERFCA_REQUIRE(in_dim_of(f) + 1 <= 96, NERFCA_E_UNSUPPORTED, "tcgen05 path: first-layer input wider than 95 (use precision fp32)");
+  NERFCA_REQUIRE(f.n_latent <= 16, NERFCA_E_UNSUPPORTED, "tcgen05 path: more than 16 latent dims (use precision fp32)");
   return NERFCA_OK;
 }
 
-// ---- parameter packing: fp32 nn.Linear tensors -> bf16 tile-canonical + fp32 bias block ------------------------
-struct PackArgs {
+// ---- parameter packing ---------------------------------------------------------------------------------------------
+struct PackNet {
   const float* w[NERFCA_MAX_LAYERS];
   const float* b[NERFCA_MAX_LAYERS];
-  int in_dim, kpad0, n_relu;
+  uint8_t* out;
+  int in_dim, kpad0;
+  uint32_t wout_off, f32_off;
 };
-__global__ void pack_params_kernel(PackArgs a, uint8_t* __restrict__ out, size_t w_bytes) {
-  const int total_w = a.kpad0 * 128 + (a.n_relu - 1) * 128 * 128;
+struct PackArgs { PackNet net[2]; };
+
+__global__ void pack_params_kernel(PackArgs pa) {
+  const PackNet& a = pa.net[blockIdx.y];
+  const int n_w0 = a.kpad0 * 128;
+  const int total_w = n_w0 + 4 * 128 * 128;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid < total_w) {
     int l, e;
-    if (tid < a.kpad0 * 128) { l = 0; e = tid; }
-    else { l = 1 + (tid - a.kpad0 * 128) / (128 * 128); e = (tid - a.kpad0 * 128) % (128 * 128); }
+    if (tid < n_w0) { l = 0; e = tid; }
+    else { l = 1 + (tid - n_w0) / (128 * 128); e = (tid - n_w0) % (128 * 128); }
     const int K = (l == 0) ? a.in_dim : 128;
-    // e enumerates the packed layout: chunk-major, then output row n, then position in chunk
+    // e enumerates the packed layout: chunk-major, then output row n, then position in the chunk
     const int chunk = e / (128 * 8), n = (e / 8) % 128, kk = e % 8;
     const int k = chunk * 8 + kk;
-    const float v = (k < K) ? __ldg(a.w[l] + (size_t)n * K + k) : 0.f;
-    const size_t base = (l == 0) ? 0 : (size_t)a.kpad0 * 256 + (size_t)(l - 1) * 32768;
-    reinterpret_cast<__nv_bfloat16*>(out + base)[e] = __float2bfloat16_rn(v);
+    float v = 0.f;
+    if (k < K) v = __ldg(a.w[l] + (size_t)n * K + k);
+    else if (l == 0 && k == K) v = a.b[0] ? __ldg(a.b[0] + n) : 0.f;   // bias column of layer 0
+    const size_t base = (l == 0) ? 0 : (size_t)a.kpad0 * 256 + (size_t)(l - 1) * TILE_BYTES;
+    reinterpret_cast<__nv_bfloat16*>(a.out + base)[e] = __float2bfloat16_rn(v);
   }
-  float* fb = reinterpret_cast<float*>(out + w_bytes);
-  const int nb = a.n_relu * 128 + 128 + 4;
+  if (tid < 16 * 128) {   // output-weight tile [16 n x 128 k], chunk stride 256 B: n = 0 -> hi, n = 1 -> lo, rest 0
+    const int chunk = tid / 128, n = (tid / 8) % 16, kk = tid % 8;
+    const int k = chunk * 8 + kk;
+    const float w = __ldg(a.w[TC_N_RELU] + k);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (n == 0) v = hi;
+    else if (n == 1) v = __float2bfloat16_rn(w - __bfloat162float(hi));
+    reinterpret_cast<__nv_bfloat16*>(a.out + a.wout_off)[tid] = v;
+  }
+  float* fb = reinterpret_cast<float*>(a.out + a.f32_off);
+  const int nb = (int)f32_block_floats();
   if (tid < nb) {
     float v = 0.f;
-    if (tid < a.n_relu * 128) { const int l = tid / 128; v = a.b[l] ? __ldg(a.b[l] + tid % 128) : 0.f; }
-    else if (tid < a.n_relu * 128 + 128) v = __ldg(a.w[a.n_relu] + (tid - a.n_relu * 128));
-    else if (tid == a.n_relu * 128 + 128) v = a.b[a.n_relu] ? __ldg(a.b[a.n_relu]) : 0.f;
+    if (tid < TC_N_RELU * 128) { const int l = tid / 128; v = a.b[l] ? __ldg(a.b[l] + tid % 128) : 0.f; }
+    else if (tid < TC_N_RELU * 128 + 128) v = __ldg(a.w[TC_N_RELU] + (tid - TC_N_RELU * 128));
+    else if (tid == TC_N_RELU * 128 + 128) v = a.b[TC_N_RELU] ? __ldg(a.b[TC_N_RELU]) : 0.f;
     fb[tid] = v;
   }
 }
 
-static int pack_params(const nerfca_field_t& f, const TcDims& d, void* dst, cudaStream_t st) {
-  PackArgs a;
-  for (int l = 0; l < NERFCA_MAX_LAYERS; ++l) { a.w[l] = f.weight[l]; a.b[l] = f.bias[l]; }
-  a.in_dim = d.in_dim; a.kpad0 = d.kpad0; a.n_relu = d.n_relu;
-  const int total = d.kpad0 * 128 + f.n_hidden * 128 * 128;
-  pack_params_kernel<<<div_up(total, 256), 256, 0, st>>>(a, (uint8_t*)dst, d.w_bytes);
+// packed blocks of the nets sit back to back in `dst`, each rounded up to 256 B
+static size_t pack_stride(const NetDims& d) { return ((size_t)d.pack_bytes + 255) & ~(size_t)255; }
+
+static int pack_params(const nerfca_field_t* const* f, int n_nets, void* dst, cudaStream_t st) {
+  PackArgs pa;
+  size_t off = 0;
+  int max_total = 0;
+  for (int i = 0; i < n_nets; ++i) {
+    const NetDims d = net_dims(*f[i]);
+    PackNet& a = pa.net[i];
+    for (int l = 0; l < NERFCA_MAX_LAYERS; ++l) { a.w[l] = f[i]->weight[l]; a.b[l] = f[i]->bias[l]; }
+    a.out = (uint8_t*)dst + off;
+    a.in_dim = d.in_dim; a.kpad0 = d.kpad0; a.wout_off = d.wout_off; a.f32_off = d.f32_off;
+    off += pack_stride(d);
+    const int total = d.kpad0 * 128 + 4 * 128 * 128;
+    max_total = total > max_total ? total : max_total;
+  }
+  ProfScope prof(NERFCA_K_PACK, st);
+  pack_params_kernel<<<dim3(div_up(max_total, 256), n_nets), 256, 0, st>>>(pa);
   NERFCA_LAUNCH_OK();
   return NERFCA_OK;
 }
 
-// ---- forward kernel ---------------------------------------------------------------------------------------------
-struct FwdArgs {
-  SampleSrc src;
+// ---- first-layer input tile X0 (bf16, tile-canonical) ------------------------------------------------------------
+// Each tile row is built by the two threads (column halves ch = 0 / 1) that own it.  Fast path (BANDS, 12 bands):
+// the sines / cosines of bands 0-5 and 6-11 come from one accurate sincosf per coordinate (at band 0 resp. band 6)
+// followed by double-angle steps, everything in registers, 16-byte stores.  The result differs from the fp32 reference
+// expression by < 1e-5 absolute (the reference's own "+ fl32(pi/2)" argument rounding is 2.4e-4 at band 11), far
+// below the bf16 rounding applied to the tile.  Other encodings take the generic per-feature path.
+struct X0Desc {
   EncDesc enc;
-  const uint8_t* params;   // packed weights + fp32 block
-  float* raw_out;
-  uint8_t* stash;          // or null
-  long long n_tiles;
-  int kpad0, n_relu;
-  uint32_t w_bytes, tile_stash_bytes;
+  int kpad0;
+  int fast;   // BANDS with n_freq == FAST_FREQ
 };
 
-// dynamic smem map (bytes):  [weights][act slot 0: 32768][act slot 1: 32768][fp32 block][barriers / tmem ptr]
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_forward_kernel(FwdArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* s_w = smem;
-  uint8_t* s_act = s_w + a.w_bytes;
-  float* s_f = reinterpret_cast<float*>(s_act + 2 * 32768);
-  const int n_f = a.n_relu * 128 + 128 + 4;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_f + ((n_f + 3) & ~3));
-  // s_bar[0] weights, [1..2] act_full, [3..4] acc_full, then the TMEM base pointer
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 5);
-  const uint32_t bar_w = smem_u32(s_bar), bar_act0 = smem_u32(s_bar + 1), bar_acc0 = smem_u32(s_bar + 3);
+__device__ __forceinline__ void put_bf16(uint8_t* tile, int row, int f, float v) {
+  *reinterpret_cast<__nv_bfloat16*>(tile + (f >> 3) * CHUNK_BYTES + row * 16 + (f & 7) * 2) = __float2bfloat16_rn(v);
+}
+__device__ __forceinline__ void put_chunk(uint8_t* tile, int row, int c, const float* v) {
+  *reinterpret_cast<uint4*>(tile + c * CHUNK_BYTES + row * 16) =
+      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
 
-  if (warp == 8) {
-    if (lane == 0) {
-      mbar_init(bar_w, 1);
-      mbar_init(bar_act0, 128); mbar_init(bar_act0 + 8, 128);
-      mbar_init(bar_acc0, 1); mbar_init(bar_acc0 + 8, 1);
-      mbar_init_fence();
-    }
-    __syncwarp();
-    tmem_alloc(smem_u32(s_tmem), 256);
-  }
-  for (int i = threadIdx.x; i < n_f; i += blockDim.x) s_f[i] = __ldg(reinterpret_cast<const float*>(a.params + a.w_bytes) + i);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *s_tmem;
-
-  const long long n_my = (a.n_tiles > (long long)blockIdx.x) ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const float* s_wout = s_f + a.n_relu * 128;
-  const float b_out = s_f[a.n_relu * 128 + 128];
-
-  if (warp == 8) {
-    // ================= control warp: weight load + MMA issue =================
-    if (lane == 0) {
-      mbar_expect_tx(bar_w, a.w_bytes);
-      for (uint32_t off = 0; off < a.w_bytes; off += 32768) {
-        const uint32_t n = (a.w_bytes - off < 32768u) ? a.w_bytes - off : 32768u;
-        bulk_g2s(smem_u32(s_w + off), a.params + off, n, bar_w);
-      }
-      mbar_wait(bar_w, 0);
-      constexpr uint32_t idesc = instr_desc(128, 128, 0, 0);
-      uint32_t ph_act[2] = {0, 0};
-      for (long long i0 = 0; i0 < n_my; i0 += 2) {
-        const int nslots = (n_my - i0 >= 2) ? 2 : 1;
-        for (int l = 0; l < a.n_relu; ++l) {
-          const int ksteps = (l == 0 ? a.kpad0 : 128) / 16;
-          const uint32_t wl = smem_u32(s_w) + (l == 0 ? 0u : (uint32_t)a.kpad0 * 256u + (uint32_t)(l - 1) * 32768u);
-          for (int s = 0; s < nslots; ++s) {
-            mbar_wait(bar_act0 + 8 * s, ph_act[s]);
-            ph_act[s] ^= 1;
-            tc_fence_after();
-            const uint32_t act = smem_u32(s_act + s * 32768);
-            for (int kk = 0; kk < ksteps; ++kk)
-              umma_ss(tmem + s * 128, desc_kmajor(act, kk), desc_kmajor(wl, kk), idesc, kk > 0);
-            umma_commit(bar_acc0 + 8 * s);
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // ================= epilogue warpgroups =================
-    const int g = warp >> 2;                       // slot owned by this warpgroup
-    const int row = (warp & 3) * 32 + lane;        // tile row == TMEM lane
-    uint8_t* act = s_act + g * 32768;
-    const uint32_t t_acc = tmem + g * 128 + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t ph_acc = 0;
-    for (long long i = g; i < n_my; i += 2) {
-      const long long tile = blockIdx.x + i * gridDim.x;
-      const long long p = tile * TILE_M + row;     // local sample index
-      const bool valid = p < a.src.n_points;
-      uint8_t* st_tile = a.stash ? a.stash + (size_t)tile * a.tile_stash_bytes : nullptr;
-      // ---- layer-0 input: point + encoding (+ latent) -> bf16 row of the A tile
-      {
-        float x = 0.f, y = 0.f, z = 0.f;
-        int phase = 0;
-        if (valid) {
-          load_point(a.src, p, x, y, z);
-          if (a.enc.n_latent > 0) phase = load_phase(a.src, p);
-          if (phase < 0 || phase >= a.enc.n_phases) phase = 0;
-        }
-        for (int c = 0; c < a.kpad0 / 8; ++c) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int f = c * 8 + e;
-            v[e] = (valid && f < a.enc.in_dim) ? enc_feature(a.enc, f, x, y, z, phase) : 0.f;
-          }
-          const uint4 q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          *reinterpret_cast<uint4*>(act + c * CHUNK_BYTES + row * 16) = q;
-          if (st_tile) *reinterpret_cast<uint4*>(st_tile + c * CHUNK_BYTES + row * 16) = q;
-        }
-      }
-      fence_proxy_async();
-      mbar_arrive(bar_act0 + 8 * g);
-
-      for (int l = 0; l < a.n_relu; ++l) {
-        mbar_wait(bar_acc0 + 8 * g, ph_acc);
-        ph_acc ^= 1;
-        tc_fence_after();
-        const bool last = (l == a.n_relu - 1);
-        const float* bias = s_f + l * 128;
-        uint8_t* st_l = st_tile ? st_tile + (size_t)a.kpad0 * 256 + (size_t)l * 32768 : nullptr;
-        float dot = 0.f;
-#pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
-          uint32_t v[32];
-          tmem_ld32(t_acc + cb * 32, v);
-          tmem_ld_wait();
-          float h[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) h[j] = fmaxf(__uint_as_float(v[j]) + bias[cb * 32 + j], 0.f);
-          if (last) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dot = fmaf(h[j], s_wout[cb * 32 + j], dot);
-          }
-          if (!last || st_l) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const uint4 q = make_uint4(pack_bf16x2(h[q4 * 8 + 0], h[q4 * 8 + 1]), pack_bf16x2(h[q4 * 8 + 2], h[q4 * 8 + 3]),
-                                         pack_bf16x2(h[q4 * 8 + 4], h[q4 * 8 + 5]), pack_bf16x2(h[q4 * 8 + 6], h[q4 * 8 + 7]));
-              const int off = (cb * 4 + q4) * CHUNK_BYTES + row * 16;
-              if (!last) *reinterpret_cast<uint4*>(act + off) = q;
-              if (st_l) *reinterpret_cast<uint4*>(st_l + off) = q;
-            }
-          }
-        }
-        tc_fence_before();
-        if (!last) {
-          fence_proxy_async();
-          mbar_arrive(bar_act0 + 8 * g);
-        } else if (valid) {
-          a.raw_out[p] = dot + b_out;
-        }
-      }
+__device__ __forceinline__ void build_x0_row(const X0Desc& xd, const SampleSrc& src, long long p, bool valid, uint8_t* tile, int row,
+                                             int ch) {
+  float x = 0.f, y = 0.f, z = 0.f;
+  int phase = 0;
+  const EncDesc& e = xd.enc;
+  if (valid) {
+    load_point(src, p, x, y, z);
+    if (e.n_latent > 0) {
+      phase = load_phase(src, p);
+      if (phase < 0 || phase >= e.n_phases) phase = 0;
     }
   }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 256);
+  const float live = valid ? 1.f : 0.f;
+  if (xd.fast) {
+    constexpr int HB = FAST_FREQ / 2;            // bands per half
+    constexpr int SPLIT = 40;                    // features [0, 40) belong to ch 0 (5 chunks), the rest to ch 1
+    const float scale = ch ? (float)(1 << HB) : 1.f;
+    float s[3], c[3];
+    sincosf(x * scale, &s[0], &c[0]);
+    sincosf(y * scale, &s[1], &c[1]);
+    sincosf(z * scale, &s[2], &c[2]);
+    // features are produced in index order and leave in 16-byte chunks as soon as 8 of them exist; `cnt` is a
+    // compile-time constant at every use once the loops are unrolled, so `buf` stays in registers
+    float buf[8];
+    int cnt = 0;
+    const int n_chunks = xd.kpad0 / 8;
+    const int c_base = ch ? SPLIT / 8 : 0;
+#define NERFCA_PUSH(val)                                                                  \
+    do {                                                                                    \
+      buf[cnt & 7] = (val);                                                                 \
+      ++cnt;                                                                                \
+      if ((cnt & 7) == 0 && c_base + (cnt >> 3) - 1 < n_chunks) put_chunk(tile, row, c_base + (cnt >> 3) - 1, buf); \
+    } while (0)
+    if (ch == 0) {
+      NERFCA_PUSH(x); NERFCA_PUSH(y); NERFCA_PUSH(z);
+#pragma unroll
+      for (int b = 0; b < HB; ++b) {
+        const float w = (e.band_weight ? __ldg(e.band_weight + b) : 1.f) * live;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) NERFCA_PUSH(w * s[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) NERFCA_PUSH(w * c[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float t = 2.f * s[k] * c[k];
+          c[k] = fmaf(-2.f * s[k], s[k], 1.f);
+          s[k] = t;
+        }
+      }
+      NERFCA_PUSH((e.band_weight ? __ldg(e.band_weight + HB) : 1.f) * live * s[0]);   // feature 39 = sin(2^6 x) closes chunk 4
+    } else {
+#pragma unroll
+      for (int b = 0; b < HB; ++b) {
+        const float w = (e.band_weight ? __ldg(e.band_weight + HB + b) : 1.f) * live;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (b > 0 || k > 0) NERFCA_PUSH(w * s[k]);                                   // feature 39 belongs to ch 0
+#pragma unroll
+        for (int k = 0; k < 3; ++k) NERFCA_PUSH(w * c[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float t = 2.f * s[k] * c[k];
+          c[k] = fmaf(-2.f * s[k], s[k], 1.f);
+          s[k] = t;
+        }
+      }
+      // latents, the constant-1 column (layer-0 bias / bias gradient), zero padding up to kpad0 (<= 96)
+#pragma unroll
+      for (int t = 0; t < 96 - (3 + 6 * FAST_FREQ); ++t) {
+        float val = 0.f;
+        if (t < e.n_latent) val = live * __ldg(e.latents + (size_t)phase * e.n_latent + t);
+        else if (t == e.n_latent) val = live;
+        NERFCA_PUSH(val);
+      }
+    }
+#undef NERFCA_PUSH
+    return;
+  }
+  // generic encodings: ch 0 writes features [0, kpad0/2), ch 1 the rest
+  const int f_lo = ch ? xd.kpad0 / 2 : 0, f_hi = ch ? xd.kpad0 : xd.kpad0 / 2;
+  for (int f = f_lo; f < f_hi; ++f) {
+    float val = 0.f;
+    if (valid) val = (f < e.in_dim) ? enc_feature(e, f, x, y, z, phase) : (f == e.in_dim ? 1.f : 0.f);
+    put_bf16(tile, row, f, val);
+  }
 }
 
-static size_t fwd_smem_bytes(const TcDims& d) {
-  const int n_f = d.n_relu * 128 + 128 + 4;
-  return d.w_bytes + 2 * 32768 + (size_t)((n_f + 3) & ~3) * sizeof(float) + 8 * sizeof(uint64_t);
-}
-
-size_t tc_stash_bytes(const nerfca_field_t& f, long long P) {
-  const TcDims d = tc_dims(f);
-  return (size_t)((P + TILE_M - 1) / TILE_M) * d.tile_stash_bytes;
-}
-
-// backward workspace: [params block][dZ hand-off between layer-group passes: n_tiles * 32 KB]
-size_t tc_workspace_bytes(const nerfca_field_t& f, long long P, int backward) {
-  const TcDims d = tc_dims(f);
-  size_t n = (tc_param_bytes(d) + 255) & ~(size_t)255;
-  if (backward) n += (size_t)((P + TILE_M - 1) / TILE_M) * 32768;
-  return n;
+// ---- accumulator (this thread's lane, 64 columns) -> registers ---------------------------------------------------
+__device__ __forceinline__ void ld_acc64(uint32_t taddr, uint32_t (&a)[32], uint32_t (&b)[32]) {
+  tmem_ld32(taddr, a);
+  tmem_ld32(taddr + 32, b);
+  tmem_ld_wait();
 }
 
 static int sm_count() {
@@ -278,203 +263,462 @@ static int sm_count() {
   return n;
 }
 
-int tc_field_forward(const nerfca_field_t& f, const nerfca_samples_t& s, float* raw_out, void* stash, void* workspace,
-                     cudaStream_t st) {
-  const TcDims d = tc_dims(f);
-  int rc = pack_params(f, d, workspace, st);
-  if (rc) return rc;
-  FwdArgs a;
-  a.src = make_src(s);
-  a.enc = make_enc(f);
-  a.params = (const uint8_t*)workspace;
-  a.raw_out = raw_out;
-  a.stash = (uint8_t*)stash;
-  a.n_tiles = (s.n_points + TILE_M - 1) / TILE_M;
-  a.kpad0 = d.kpad0; a.n_relu = d.n_relu;
-  a.w_bytes = (uint32_t)d.w_bytes; a.tile_stash_bytes = (uint32_t)d.tile_stash_bytes;
-  const size_t smem = fwd_smem_bytes(d);
-  NERFCA_REQUIRE(smem <= 227 * 1024, NERFCA_E_UNSUPPORTED, "field does not fit the forward kernel's shared memory");
-  NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
-  tc_forward_kernel<<<(unsigned)grid, TC_THREADS, smem, st>>>(a);
-  NERFCA_LAUNCH_OK();
-  return NERFCA_OK;
-}
-
-// ---- backward kernel -----------------------------------------------------------------------------------------------
-// One launch handles a group of at most two consecutive layers (hi, hi-1) for a stream of tiles; the weight-gradient
-// accumulators of those layers stay in TMEM for the CTA's whole lifetime and are flushed once with atomics.
-//   per tile and per layer l of the group (top first):
-//     dgrad   accD[128 x 128]   = dZ_l (K-major A)        x W_l  (MN-major B)      -> epilogue: * 1[H_{l-1} > 0] -> dZ_{l-1}
-//     wgrad   accW_l[out x in] += dZ_l^T (MN-major A)     x H_{l-1} (MN-major B)       (H_{-1} = encoded input X0)
-//     bgrad   accB_l[out x 16] += dZ_l^T (MN-major A)     x side tile (column 2 == 1)
-//   top group only: dZ_{L-1} = d_raw * w_out * 1[H_{L-1} > 0] on the CUDA cores, and
-//     wout    accO[feat x 16]  += H_{L-1}^T (MN-major A)  x side tile (columns 0,1 = bf16 hi / lo split of d_raw)
-//   bottom layer of a Temporal field: latent dgrad accD[128 x 16/32] = dZ_0 x W_0[:, latent columns] -> scatter by phase.
-// Groups hand dZ over through global memory in tile-canonical layout (bulk-copied back into smem by the next launch).
-struct BwdArgs {
+// =====================================================================================================================
+// forward
+// =====================================================================================================================
+struct FwdNet {
+  const uint8_t* pack;
+  float* raw_out;
+  uint8_t* stash;          // [n_tiles][STASH_TILES][TILE_BYTES] or null
+  X0Desc x0;
+  uint32_t w0_bytes, wout_off, f32_off, pack_bytes;
+};
+struct FwdArgs {
   SampleSrc src;
-  const uint8_t* params;     // packed weights + fp32 block (w_out at fp32 offset n_relu*128)
-  const uint8_t* stash;
-  uint8_t* handoff;          // [n_tiles][32768]
-  const float* d_raw;
-  float* g_w[2];             // fp32 gradient of weight[l_hi], weight[l_hi-1]
-  float* g_b[2];             // may be null
-  float* g_wout; float* g_bout; float* g_lat;
+  FwdNet net[2];
+  int n_nets;
   long long n_tiles;
-  int kpad0, n_relu, in_dim, enc_dim, n_latent, n_phases;
-  int l_hi, n_layers;        // layers l_hi, l_hi-1 (n_layers in {1,2})
-  int from_raw;              // l_hi == n_relu-1
-  uint32_t w_bytes, tile_stash_bytes;
 };
 
-constexpr int BW_COL_D = 0, BW_COL_W0 = 128, BW_COL_W1 = 256, BW_COL_B0 = 384, BW_COL_B1 = 400, BW_COL_O = 416;
+constexpr uint32_t FWD_ACC_COL = 0, FWD_OUT_COL = 256;   // slot s: acc at s * 128, output-layer accumulator at 256 + s * 16
 
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_backward_kernel(BwdArgs a) {
+// smem: [packed block][act slot 0][act slot 1][barriers]
+__global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool has_lat = a.n_latent > 0;
-  const int l_lo = a.l_hi - a.n_layers + 1;
-  // smem map: [W(l_hi)][W(l_hi-1)] (32 KB each; layer 0: kpad0*256)  [P][Q][hbuf0][hbuf1][side 4 KB][w_out 512 B][lat acc][bars]
-  uint32_t w_off[2], w_len[2];
-  uint32_t cur = 0;
-  for (int j = 0; j < 2; ++j) {
-    const int l = a.l_hi - j;
-    const bool need = j < a.n_layers && (l > 0 || has_lat);
-    w_off[j] = cur;
-    w_len[j] = need ? (l == 0 ? (uint32_t)a.kpad0 * 256u : 32768u) : 0u;
-    cur += w_len[j];
-  }
-  uint8_t* s_w = smem;
-  uint8_t* s_dz = smem + cur;            // P = s_dz, Q = s_dz + 32768
-  uint8_t* s_h = s_dz + 2 * 32768;       // hbuf0, hbuf1
-  uint8_t* s_side = s_h + 2 * 32768;
-  float* s_wout = reinterpret_cast<float*>(s_side + 4096);
-  float* s_lat = s_wout + 128;
-  const int n_lat_acc = (has_lat && l_lo == 0) ? a.n_phases * a.n_latent : 0;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_lat + ((n_lat_acc + 3) & ~3));
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 6);
-  const uint32_t bar_w = smem_u32(s_bar), bar_load = bar_w + 8, bar_dz = bar_w + 16, bar_d = bar_w + 24, bar_done = bar_w + 32,
-                 bar_free = bar_w + 40;
+  const int net_id = blockIdx.x % a.n_nets;
+  const FwdNet& nt = a.net[net_id];
+  const long long worker = blockIdx.x / a.n_nets, n_workers = gridDim.x / a.n_nets;
+  const uint32_t pack_pad = (nt.pack_bytes + 127u) & ~127u;
+  uint8_t* s_pack = smem;
+  uint8_t* s_act = smem + pack_pad;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_act + 2 * TILE_BYTES);
+  // barriers: [0] weights, [1,2] act_full, [3,4] acc_full, [5,6] stash_ready, [7,8] stash_free
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 9);
+  const float* s_f = reinterpret_cast<const float*>(s_pack + nt.f32_off);
+  const uint32_t bar_w = smem_u32(s_bar), bar_act0 = bar_w + 8, bar_acc0 = bar_w + 24, bar_sr0 = bar_w + 40, bar_sf0 = bar_w + 56;
 
-  if (warp == 8) {
+  if (warp == 16) {
     if (lane == 0) {
-      mbar_init(bar_w, 1); mbar_init(bar_load, 1); mbar_init(bar_dz, 256); mbar_init(bar_d, 1); mbar_init(bar_done, 1);
-      mbar_init(bar_free, 256);
+      mbar_init(bar_w, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(bar_act0 + 8 * s, 256);
+        mbar_init(bar_acc0 + 8 * s, 1);
+        mbar_init(bar_sr0 + 8 * s, 256);
+        mbar_init(bar_sf0 + 8 * s, 1);
+      }
       mbar_init_fence();
     }
     __syncwarp();
     tmem_alloc(smem_u32(s_tmem), 512);
   }
-  for (int i = threadIdx.x; i < 128; i += blockDim.x)
-    s_wout[i] = __ldg(reinterpret_cast<const float*>(a.params + a.w_bytes) + a.n_relu * 128 + i);
-  for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x) s_lat[i] = 0.f;
-  for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_side)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
-  const long long n_my = (a.n_tiles > (long long)blockIdx.x) ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int lat_c0 = a.enc_dim / 8;                                        // first chunk holding latent columns
-  const int lat_n = ((a.enc_dim % 8 + a.n_latent + 15) / 16) * 16;         // MMA N covering them
+  const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
+  const bool stash_on = nt.stash != nullptr;
+
+  if (warp == 16) {
+    // ================= MMA warp =================
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, nt.pack_bytes);
+      for (uint32_t off = 0; off < nt.pack_bytes; off += 32768u) {
+        const uint32_t n = (nt.pack_bytes - off < 32768u) ? nt.pack_bytes - off : 32768u;
+        bulk_g2s(smem_u32(s_pack + off), nt.pack + off, n, bar_w);
+      }
+      mbar_wait(bar_w, 0);
+      constexpr uint32_t idesc = instr_desc(128, 128, 0, 0);
+      constexpr uint32_t idesc_out = instr_desc(128, 16, 0, 0);
+      const int k0steps = nt.x0.kpad0 / 16;
+      const uint32_t w_base = smem_u32(s_pack), wout = smem_u32(s_pack + nt.wout_off);
+      uint32_t ph_act[2] = {0, 0};
+      for (long long i0 = 0; i0 < n_my; i0 += 2) {
+        const int nslots = (n_my - i0 >= 2) ? 2 : 1;
+        for (int l = 0; l <= TC_N_RELU; ++l) {
+          for (int s = 0; s < nslots; ++s) {
+            mbar_wait(bar_act0 + 8 * s, ph_act[s]);
+            ph_act[s] ^= 1;
+            tc_fence_after();
+            const uint32_t act = smem_u32(s_act + s * TILE_BYTES);
+            if (l == 0) {
+              for (int kk = 0; kk < k0steps; ++kk)
+                umma_ss(tmem + FWD_ACC_COL + s * 128, desc_kmajor(act, kk), desc_kmajor(w_base, kk), idesc, kk > 0);
+            } else if (l < TC_N_RELU) {
+              const uint32_t wl = w_base + nt.w0_bytes + (uint32_t)(l - 1) * TILE_BYTES;
+              for (int kk = 0; kk < 8; ++kk)   // accumulator already holds the bias (tcgen05.st by the epilogue)
+                umma_ss(tmem + FWD_ACC_COL + s * 128, desc_kmajor(act, kk), desc_kmajor(wl, kk), idesc, 1);
+            } else {
+              for (int kk = 0; kk < 8; ++kk)
+                umma_ss(tmem + FWD_OUT_COL + s * 16, desc_kmajor(act, kk), desc_kmajor_rows(wout, kk, 256), idesc_out, kk > 0);
+            }
+            umma_commit(bar_acc0 + 8 * s);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 17) {
+    // ================= stash store warp: H0 and H2 of every tile, straight from the activation buffer =================
+    if (stash_on && lane == 0) {
+      uint32_t ph[2] = {0, 0};
+      for (long long i0 = 0; i0 < n_my; i0 += 2) {
+        const int nslots = (n_my - i0 >= 2) ? 2 : 1;
+        for (int j = 0; j < STASH_TILES; ++j) {
+          for (int s = 0; s < nslots; ++s) {
+            const long long tile = worker + (i0 + s) * n_workers;
+            mbar_wait(bar_sr0 + 8 * s, ph[s]);
+            ph[s] ^= 1;
+            bulk_s2g(nt.stash + ((size_t)tile * STASH_TILES + j) * TILE_BYTES, smem_u32(s_act + s * TILE_BYTES), TILE_BYTES);
+            bulk_commit();
+            bulk_wait_read_all();
+            mbar_arrive(bar_sf0 + 8 * s);
+          }
+        }
+      }
+      bulk_wait_all();
+    }
+    __syncwarp();
+  } else {
+    // ================= 16 epilogue warps: slot = warp / 8, column half ch, TMEM lane quadrant q =================
+    const int slot = warp >> 3, ch = (warp >> 2) & 1, q = warp & 3;
+    const int row = q * 32 + lane;
+    uint8_t* act = s_act + slot * TILE_BYTES;
+    const uint32_t t_acc = tmem + FWD_ACC_COL + slot * 128 + ch * 64 + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_out = tmem + FWD_OUT_COL + slot * 16 + ((uint32_t)(q * 32) << 16);
+    const uint32_t bar_act = bar_act0 + 8 * slot, bar_acc = bar_acc0 + 8 * slot, bar_sr = bar_sr0 + 8 * slot, bar_sf = bar_sf0 + 8 * slot;
+    uint32_t ph_acc = 0, ph_sf = 0;
+    bool store_pending = false;
+    bool w_seen = false;
+    float b_out = 0.f;
+    for (long long i = slot; i < n_my; i += 2) {
+      const long long tile = worker + i * n_workers;
+      const long long p = tile * TILE_M + row;
+      const bool valid = p < a.src.n_points;
+      build_x0_row(nt.x0, a.src, p, valid, act, row, ch);
+      fence_proxy_async();
+      mbar_arrive(bar_act);
+      if (!w_seen) {             // biases / b_out below come from the packed block in shared memory
+        mbar_wait(bar_w, 0);
+        w_seen = true;
+        b_out = s_f[TC_N_RELU * 128 + 128];
+      }
+
+      for (int l = 0; l < TC_N_RELU; ++l) {
+        mbar_wait(bar_acc, ph_acc);
+        ph_acc ^= 1;
+        tc_fence_after();
+        uint32_t va[32], vb[32];
+        ld_acc64(t_acc, va, vb);
+        if (l + 1 < TC_N_RELU) {   // preload the next layer's bias into the accumulator columns just read
+          const float4* bn = reinterpret_cast<const float4*>(s_f + (l + 1) * 128 + ch * 64);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {   // 8 columns at a time keeps the register peak at the 64 accumulator values + 8
+            const float4 t0 = bn[2 * j], t1 = bn[2 * j + 1];
+            tmem_st8(t_acc + 8 * j, __float_as_uint(t0.x), __float_as_uint(t0.y), __float_as_uint(t0.z), __float_as_uint(t0.w),
+                     __float_as_uint(t1.x), __float_as_uint(t1.y), __float_as_uint(t1.z), __float_as_uint(t1.w));
+          }
+        }
+        if (store_pending) {       // the previous contents of this buffer are still being copied to the stash
+          mbar_wait(bar_sf, ph_sf);
+          ph_sf ^= 1;
+          store_pending = false;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 q0 = make_uint4(pack_relu_bf16x2(__uint_as_float(va[8 * j]), __uint_as_float(va[8 * j + 1])),
+                                      pack_relu_bf16x2(__uint_as_float(va[8 * j + 2]), __uint_as_float(va[8 * j + 3])),
+                                      pack_relu_bf16x2(__uint_as_float(va[8 * j + 4]), __uint_as_float(va[8 * j + 5])),
+                                      pack_relu_bf16x2(__uint_as_float(va[8 * j + 6]), __uint_as_float(va[8 * j + 7])));
+          *reinterpret_cast<uint4*>(act + (ch * 8 + j) * CHUNK_BYTES + row * 16) = q0;
+          const uint4 q1 = make_uint4(pack_relu_bf16x2(__uint_as_float(vb[8 * j]), __uint_as_float(vb[8 * j + 1])),
+                                      pack_relu_bf16x2(__uint_as_float(vb[8 * j + 2]), __uint_as_float(vb[8 * j + 3])),
+                                      pack_relu_bf16x2(__uint_as_float(vb[8 * j + 4]), __uint_as_float(vb[8 * j + 5])),
+                                      pack_relu_bf16x2(__uint_as_float(vb[8 * j + 6]), __uint_as_float(vb[8 * j + 7])));
+          *reinterpret_cast<uint4*>(act + (ch * 8 + 4 + j) * CHUNK_BYTES + row * 16) = q1;
+        }
+        if (l + 1 < TC_N_RELU) tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(bar_act);
+        if (stash_on && (l == 0 || l == 2)) {
+          mbar_arrive(bar_sr);
+          store_pending = true;
+        }
+      }
+      // output layer: raw = H4 . (w_hi + w_lo) + b_out
+      mbar_wait(bar_acc, ph_acc);
+      ph_acc ^= 1;
+      tc_fence_after();
+      if (ch == 0) {
+        uint32_t o[2];
+        tmem_ld2(t_out, o);
+        tmem_ld_wait();
+        if (valid) nt.raw_out[p] = (__uint_as_float(o[0]) + __uint_as_float(o[1])) + b_out;
+      }
+      tc_fence_before();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem, 512);
+}
+
+// =====================================================================================================================
+// backward, shared pieces
+// =====================================================================================================================
+// dZ = acc * 1[h > 0] for this thread's 64 columns: h comes from the bf16 activation tile in shared memory, the result
+// goes to `out` (tile-canonical bf16).
+__device__ __forceinline__ void masked_grad_store(const uint32_t (&va)[32], const uint32_t (&vb)[32], const uint8_t* h_tile, uint8_t* out,
+                                                  int row, int ch) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = ch * 8 + half * 4 + j;
+      const uint4 hv = *reinterpret_cast<const uint4*>(h_tile + c * CHUNK_BYTES + row * 16);
+      const uint32_t* v = half ? vb : va;
+      uint4 o;
+      o.x = mul_bf16x2(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])), relu_mask_bf16x2(hv.x));
+      o.y = mul_bf16x2(pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])), relu_mask_bf16x2(hv.y));
+      o.z = mul_bf16x2(pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])), relu_mask_bf16x2(hv.z));
+      o.w = mul_bf16x2(pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])), relu_mask_bf16x2(hv.w));
+      *reinterpret_cast<uint4*>(out + c * CHUNK_BYTES + row * 16) = o;
+    }
+  }
+}
+// H = relu(acc + bias) for this thread's 64 columns -> bf16 tile
+__device__ __forceinline__ void relu_bias_store(const uint32_t (&va)[32], const uint32_t (&vb)[32], const float* bias, uint8_t* out,
+                                                int row, int ch) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = ch * 8 + half * 4 + j;
+      const uint32_t* v = half ? vb : va;
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + c * 8), b1 = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
+      uint4 o;
+      o.x = pack_relu_bf16x2(__uint_as_float(v[8 * j]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y);
+      o.y = pack_relu_bf16x2(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w);
+      o.z = pack_relu_bf16x2(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y);
+      o.w = pack_relu_bf16x2(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w);
+      *reinterpret_cast<uint4*>(out + c * CHUNK_BYTES + row * 16) = o;
+    }
+  }
+}
+
+// vector reduction into global memory (4 consecutive floats, 16-byte aligned)
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// flush a TMEM-resident [128 out x n_cols] weight-gradient accumulator: thread = (row, column half)
+__device__ __forceinline__ void flush_wgrad(uint32_t t_lane, uint32_t col0, float* gw, int row, int ch, int n_cols, int k_in) {
+  const bool vec_ok = (k_in & 3) == 0 && (reinterpret_cast<uintptr_t>(gw) & 15) == 0;
+  for (int c0 = ch * 64; c0 < n_cols && c0 < ch * 64 + 64; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(t_lane + col0 + c0, v);
+    tmem_ld_wait();
+    float* dst = gw + (size_t)row * k_in + c0;
+    if (vec_ok && c0 + 16 <= k_in) {
+#pragma unroll
+      for (int e = 0; e < 16; e += 4)
+        red_add_v4(dst + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (c0 + e < k_in) atomicAdd(dst + e, __uint_as_float(v[e]));
+    }
+  }
+}
+
+struct BwdNet {
+  const uint8_t* pack;
+  const uint8_t* stash;
+  uint8_t* handoff;          // [n_tiles][TILE_BYTES]  dZ2
+  const float* d_raw;
+  float* g_w[NERFCA_MAX_LAYERS];
+  float* g_b[NERFCA_MAX_LAYERS];   // may be null
+  float* g_lat;
+  X0Desc x0;
+  uint32_t w0_bytes, f32_off;
+  int in_dim, enc_dim, n_latent, n_phases;
+};
+struct BwdArgs {
+  SampleSrc src;
+  BwdNet net[2];
+  int n_nets;
+  long long n_tiles;
+};
+
+// =====================================================================================================================
+// backward, top pass: output layer, layers 4 and 3
+// =====================================================================================================================
+constexpr uint32_t TOP_ACC = 0, TOP_WG4 = 128, TOP_WG3 = 256, TOP_BG4 = 384, TOP_BG3 = 400, TOP_ACCO = 416;
+
+// smem: [W3][W4][bufH 0][bufH 1][R][S][side 4 KB][fp32: bias3, bias4, w_out (384 floats)][g_bout acc][barriers]
+__global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int net_id = blockIdx.x % a.n_nets;
+  const BwdNet& nt = a.net[net_id];
+  const long long worker = blockIdx.x / a.n_nets, n_workers = gridDim.x / a.n_nets;
+  uint8_t* s_w3 = smem;
+  uint8_t* s_w4 = smem + TILE_BYTES;
+  uint8_t* s_bufh = smem + 2 * TILE_BYTES;           // two buffers: H2 / H3 swap roles every tile
+  uint8_t* s_r = smem + 4 * TILE_BYTES;
+  uint8_t* s_s = smem + 5 * TILE_BYTES;
+  uint8_t* s_side = smem + 6 * TILE_BYTES;
+  float* s_f = reinterpret_cast<float*>(s_side + 4096);   // bias3[128], bias4[128], w_out[128]
+  float* s_gbout = s_f + 384;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_gbout + 4);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 10);
+  const uint32_t bar_w = smem_u32(s_bar), bar_ld = bar_w + 8, bar_acc = bar_w + 16, bar_e = bar_w + 24, bar_h3dead = bar_w + 32,
+                 bar_out = bar_w + 40, bar_stfree = bar_w + 48, bar_accfree = bar_w + 56, bar_done = bar_w + 64;
 
   if (warp == 8) {
     if (lane == 0) {
-      // ---- resident weights of the group
-      uint32_t wtot = w_len[0] + w_len[1];
-      if (wtot) {
-        mbar_expect_tx(bar_w, wtot);
-        for (int j = 0; j < 2; ++j) {
-          if (!w_len[j]) continue;
-          const int l = a.l_hi - j;
-          const uint8_t* src = a.params + (l == 0 ? 0 : (size_t)a.kpad0 * 256 + (size_t)(l - 1) * 32768);
-          bulk_g2s(smem_u32(s_w + w_off[j]), src, w_len[j], bar_w);
-        }
-        mbar_wait(bar_w, 0);
-      }
-      uint32_t ph_dz = 0, ph_done = 0, ph_free = 0, ph_load_c = 0;
+      mbar_init(bar_w, 1); mbar_init(bar_ld, 1); mbar_init(bar_acc, 1); mbar_init(bar_e, 256); mbar_init(bar_h3dead, 1);
+      mbar_init(bar_out, 256); mbar_init(bar_stfree, 1); mbar_init(bar_accfree, 256); mbar_init(bar_done, 1);
+      mbar_init_fence();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(s_tmem), 512);
+  }
+  {
+    const float* fb = reinterpret_cast<const float*>(nt.pack + nt.f32_off);
+    for (int i = threadIdx.x; i < 384; i += blockDim.x) {
+      const int which = i >> 7;   // 0: bias3, 1: bias4, 2: w_out
+      s_f[i] = __ldg(fb + (which == 0 ? 3 * 128 : (which == 1 ? 4 * 128 : 5 * 128)) + (i & 127));
+    }
+    for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_side)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) s_gbout[0] = 0.f;
+  }
+  tc_fence_before();
+  fence_proxy_async();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
+
+  if (warp == 8) {
+    // ================= MMA warp =================
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, 2 * TILE_BYTES);
+      bulk_g2s(smem_u32(s_w3), nt.pack + nt.w0_bytes + 2 * (size_t)TILE_BYTES, TILE_BYTES, bar_w);
+      bulk_g2s(smem_u32(s_w4), nt.pack + nt.w0_bytes + 3 * (size_t)TILE_BYTES, TILE_BYTES, bar_w);
+      mbar_wait(bar_w, 0);
+      const uint32_t w3 = smem_u32(s_w3), w4 = smem_u32(s_w4), side = smem_u32(s_side), R = smem_u32(s_r), S = smem_u32(s_s);
+      constexpr uint32_t id_fwd = instr_desc(128, 128, 0, 0), id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1),
+                         id_side = instr_desc(128, 16, 1, 1);
+      uint32_t ph_ld = 0, ph_e = 0, ph_accfree = 0;
       for (long long i = 0; i < n_my; ++i) {
-        const long long tile = blockIdx.x + i * gridDim.x;
-        const uint8_t* st_tile = a.stash + (size_t)tile * a.tile_stash_bytes;
-        if (i > 0) {   // every MMA and every epilogue read of the previous tile's buffers has finished
-          mbar_wait(bar_done, ph_done); ph_done ^= 1;
-          mbar_wait(bar_free, ph_free); ph_free ^= 1;
-        }
-        // ---- tile loads
-        uint32_t bytes = 32768;
-        for (int j = 0; j < a.n_layers; ++j) bytes += (a.l_hi - j > 0) ? 32768u : (uint32_t)a.kpad0 * 256u;
-        mbar_expect_tx(bar_load, bytes);
-        if (a.from_raw) bulk_g2s(smem_u32(s_dz + 32768), st_tile + (size_t)a.kpad0 * 256 + (size_t)a.l_hi * 32768, 32768, bar_load);
-        else            bulk_g2s(smem_u32(s_dz), a.handoff + (size_t)tile * 32768, 32768, bar_load);
-        for (int j = 0; j < a.n_layers; ++j) {
-          const int l = a.l_hi - j;
-          if (l > 0) bulk_g2s(smem_u32(s_h + j * 32768), st_tile + (size_t)a.kpad0 * 256 + (size_t)(l - 1) * 32768, 32768, bar_load);
-          else       bulk_g2s(smem_u32(s_h + j * 32768), st_tile, (uint32_t)a.kpad0 * 256u, bar_load);
-        }
-        mbar_wait(bar_load, ph_load_c); ph_load_c ^= 1;   // the issuing thread observes the bulk copies itself as well
-        const uint32_t acc_first = (i > 0) ? 1u : 0u;
-        for (int j = 0; j < a.n_layers; ++j) {
-          const int l = a.l_hi - j;
-          const uint32_t dz = smem_u32(s_dz + (j & 1) * 32768), other = smem_u32(s_dz + ((j & 1) ^ 1) * 32768);
-          const uint32_t hb = smem_u32(s_h + j * 32768), side = smem_u32(s_side), wl = smem_u32(s_w + w_off[j]);
-          mbar_wait(bar_dz, ph_dz); ph_dz ^= 1;    // dZ_l (and the side tile) are in shared memory
-          tc_fence_after();
-          if (j == 0 && a.from_raw)
-            for (int kk = 0; kk < 8; ++kk)
-              umma_ss(tmem + BW_COL_O, desc_mnmajor(other, kk), desc_mnmajor(side, kk), instr_desc(128, 16, 1, 1), acc_first | (kk > 0));
-          if (l > 0) {
-            for (int kk = 0; kk < 8; ++kk)
-              umma_ss(tmem + BW_COL_D, desc_kmajor(dz, kk), desc_mnmajor(wl, kk), instr_desc(128, 128, 0, 1), kk > 0);
-            umma_commit(bar_d);
-          } else if (has_lat) {
-            for (int kk = 0; kk < 8; ++kk)
-              umma_ss(tmem + BW_COL_D, desc_kmajor(dz, kk), desc_mnmajor(wl + lat_c0 * CHUNK_BYTES, kk), instr_desc(128, lat_n, 0, 1), kk > 0);
-            umma_commit(bar_d);
-          }
-          const int n_in = (l > 0) ? 128 : a.kpad0;
-          for (int kk = 0; kk < 8; ++kk)
-            umma_ss(tmem + (j == 0 ? BW_COL_W0 : BW_COL_W1), desc_mnmajor(dz, kk), desc_mnmajor(hb, kk), instr_desc(128, n_in, 1, 1),
-                    acc_first | (kk > 0));
-          for (int kk = 0; kk < 8; ++kk)
-            umma_ss(tmem + (j == 0 ? BW_COL_B0 : BW_COL_B1), desc_mnmajor(dz, kk), desc_mnmajor(side, kk), instr_desc(128, 16, 1, 1),
-                    acc_first | (kk > 0));
-        }
-        umma_commit(bar_done);
+        const uint32_t h2 = smem_u32(s_bufh + (i & 1) * TILE_BYTES), h3 = smem_u32(s_bufh + ((i & 1) ^ 1) * TILE_BYTES);
+        const uint32_t first = (i > 0) ? 1u : 0u;
+        // Z3 = H2 W3^T
+        mbar_wait(bar_ld, ph_ld); ph_ld ^= 1;
+        if (i > 0) { mbar_wait(bar_accfree, ph_accfree); ph_accfree ^= 1; }
+        tc_fence_after();
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_ACC, desc_kmajor(h2, kk), desc_kmajor(w3, kk), id_fwd, kk > 0);
+        umma_commit(bar_acc);
+        // Z4 = H3 W4^T
+        mbar_wait(bar_e, ph_e); ph_e ^= 1;
+        tc_fence_after();
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_ACC, desc_kmajor(h3, kk), desc_kmajor(w4, kk), id_fwd, kk > 0);
+        umma_commit(bar_acc);
+        // output-weight grad, dgrad 4, wgrad 4, bias grad 4      (R = dZ4, S = H4)
+        mbar_wait(bar_e, ph_e); ph_e ^= 1;
+        tc_fence_after();
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_ACCO, desc_mnmajor(S, kk), desc_mnmajor(side, kk), id_side, first | (kk > 0));
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_ACC, desc_kmajor(R, kk), desc_mnmajor(w4, kk), id_dgrad, kk > 0);
+        umma_commit(bar_acc);
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_WG4, desc_mnmajor(R, kk), desc_mnmajor(h3, kk), id_wgrad, first | (kk > 0));
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_BG4, desc_mnmajor(R, kk), desc_mnmajor(side, kk), id_side, first | (kk > 0));
+        // dgrad 3, wgrad 3, bias grad 3                           (S = dZ3)
+        mbar_wait(bar_e, ph_e); ph_e ^= 1;
+        tc_fence_after();
+        umma_commit(bar_h3dead);   // wgrad 4 done and the epilogue has read H3's ReLU pattern: the loader may reuse the buffer
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_ACC, desc_kmajor(S, kk), desc_mnmajor(w3, kk), id_dgrad, kk > 0);
+        umma_commit(bar_acc);
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_WG3, desc_mnmajor(S, kk), desc_mnmajor(h2, kk), id_wgrad, first | (kk > 0));
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_BG3, desc_mnmajor(S, kk), desc_mnmajor(side, kk), id_side, first | (kk > 0));
       }
+      umma_commit(bar_done);
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ================= load warp: H2 of tile i + 1 goes into the buffer H3 of tile i vacates =================
+    if (lane == 0) {
+      uint32_t ph_dead = 0;
+      for (long long i = 0; i < n_my; ++i) {
+        const long long tile = worker + i * n_workers;
+        if (i > 0) { mbar_wait(bar_h3dead, ph_dead); ph_dead ^= 1; }
+        mbar_expect_tx(bar_ld, TILE_BYTES);
+        bulk_g2s(smem_u32(s_bufh + (i & 1) * TILE_BYTES), nt.stash + ((size_t)tile * STASH_TILES + 1) * TILE_BYTES, TILE_BYTES, bar_ld);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    // ================= store warp: dZ2 -> hand-off buffer =================
+    if (lane == 0) {
+      uint32_t ph_out = 0;
+      for (long long i = 0; i < n_my; ++i) {
+        const long long tile = worker + i * n_workers;
+        mbar_wait(bar_out, ph_out); ph_out ^= 1;
+        bulk_s2g(nt.handoff + (size_t)tile * TILE_BYTES, smem_u32(s_r), TILE_BYTES);
+        bulk_commit();
+        bulk_wait_read_all();
+        mbar_arrive(bar_stfree);
+      }
+      bulk_wait_all();
     }
     __syncwarp();
   } else {
     // ================= 8 epilogue warps: thread = (row, column half) =================
-    const int row = (warp & 3) * 32 + lane, ch = warp >> 2;
-    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t ph_load = 0, ph_d = 0;
+    const int q = warp & 3, ch = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_acc = t_lane + TOP_ACC + ch * 64;
+    const float* bias3 = s_f, *bias4 = s_f + 128, *wout = s_f + 256;
+    uint32_t ph_acc = 0, ph_stfree = 0;
+    float gb_sum = 0.f;
     for (long long i = 0; i < n_my; ++i) {
-      const long long tile = blockIdx.x + i * gridDim.x;
+      const long long tile = worker + i * n_workers;
       const long long p = tile * TILE_M + row;
       const bool valid = p < a.src.n_points;
-      mbar_wait(bar_load, ph_load); ph_load ^= 1;
-      float g = 0.f;
-      if (a.from_raw) {
-        // dZ_top = d_raw * w_out * 1[H_top > 0]   (H_top sits in Q)
-        g = valid ? __ldg(a.d_raw + p) : 0.f;
-        const uint8_t* hq = s_dz + 32768;
-        for (int c = ch * 8; c < ch * 8 + 8; ++c) {
-          const uint4 hv = *reinterpret_cast<const uint4*>(hq + c * CHUNK_BYTES + row * 16);
-          const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-          uint32_t o[4];
+      uint8_t* h2 = s_bufh + (i & 1) * TILE_BYTES;
+      uint8_t* h3 = s_bufh + ((i & 1) ^ 1) * TILE_BYTES;
+      const float g = valid ? __ldg(nt.d_raw + p) : 0.f;
+      uint32_t va[32], vb[32];
+      // ---- H3 = relu(Z3 + b3)
+      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+      tc_fence_after();
+      ld_acc64(t_acc, va, vb);
+      relu_bias_store(va, vb, bias3, h3, row, ch);
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(bar_e);
+      // ---- Z4 -> H4 (S) and dZ4 = d_raw * w_out * 1[Z4 > 0] (R)
+      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+      tc_fence_after();
+      ld_acc64(t_acc, va, vb);
+      if (i > 0) { mbar_wait(bar_stfree, ph_stfree); ph_stfree ^= 1; }   // previous dZ2 has left R
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float lo = (hw[e] & 0x7FFFu) ? g * s_wout[c * 8 + 2 * e] : 0.f;         // bf16 h > 0  <=>  magnitude bits set (h >= 0)
-            const float hi = (hw[e] & 0x7FFF0000u) ? g * s_wout[c * 8 + 2 * e + 1] : 0.f;
-            o[e] = pack_bf16x2(lo, hi);
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = ch * 8 + half * 4 + j;
+          const uint32_t* v = half ? vb : va;
+          float zz[8], dz[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            zz[e] = __uint_as_float(v[8 * j + e]) + bias4[c * 8 + e];
+            dz[e] = zz[e] > 0.f ? g * wout[c * 8 + e] : 0.f;
           }
-          *reinterpret_cast<uint4*>(s_dz + c * CHUNK_BYTES + row * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-        if (ch == 0 && a.g_bout) {
-          float sum = g;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (lane == 0) atomicAdd(a.g_bout, sum);
+          *reinterpret_cast<uint4*>(s_s + c * CHUNK_BYTES + row * 16) =
+              make_uint4(pack_relu_bf16x2(zz[0], zz[1]), pack_relu_bf16x2(zz[2], zz[3]), pack_relu_bf16x2(zz[4], zz[5]), pack_relu_bf16x2(zz[6], zz[7]));
+          *reinterpret_cast<uint4*>(s_r + c * CHUNK_BYTES + row * 16) =
+              make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]), pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7]));
         }
       }
       if (ch == 0) {   // side tile row: [d_hi, d_lo, 1, 0, ...]
@@ -482,160 +726,453 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_backward_kernel(BwdArgs a) {
         const __nv_bfloat16 dl = __float2bfloat16_rn(g - __bfloat162float(dh));
         const uint32_t w0 = (uint32_t)__bfloat16_as_ushort(dh) | ((uint32_t)__bfloat16_as_ushort(dl) << 16);
         *reinterpret_cast<uint4*>(s_side + row * 16) = make_uint4(w0, 0x00003F80u, 0u, 0u);   // 0x3F80 = bf16(1.0)
+        gb_sum += g;
       }
+      tc_fence_before();
       fence_proxy_async();
-      mbar_arrive(bar_dz);
-
-      for (int j = 0; j < a.n_layers; ++j) {
-        const int l = a.l_hi - j;
-        if (!(l > 0 || has_lat)) continue;
-        mbar_wait(bar_d, ph_d); ph_d ^= 1;
-        tc_fence_after();
-        if (l > 0) {
-          const uint8_t* hprev = s_h + j * 32768;
-          uint8_t* out_s = s_dz + ((j & 1) ^ 1) * 32768;
-          const bool to_smem = (j + 1 < a.n_layers);
-          uint8_t* out_g = a.handoff + (size_t)tile * 32768;
-#pragma unroll 1
-          for (int cb = 0; cb < 2; ++cb) {
-            uint32_t v[32];
-            tmem_ld32(t_lane + BW_COL_D + ch * 64 + cb * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const int c = ch * 8 + cb * 4 + q4;
-              const uint4 hv = *reinterpret_cast<const uint4*>(hprev + c * CHUNK_BYTES + row * 16);
-              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-              uint32_t o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float lo = (hw[e] & 0x7FFFu) ? __uint_as_float(v[q4 * 8 + 2 * e]) : 0.f;
-                const float hi = (hw[e] & 0x7FFF0000u) ? __uint_as_float(v[q4 * 8 + 2 * e + 1]) : 0.f;
-                o[e] = pack_bf16x2(lo, hi);
-              }
-              const uint4 q = make_uint4(o[0], o[1], o[2], o[3]);
-              if (to_smem) *reinterpret_cast<uint4*>(out_s + c * CHUNK_BYTES + row * 16) = q;
-              else         *reinterpret_cast<uint4*>(out_g + c * CHUNK_BYTES + row * 16) = q;
-            }
-          }
-          tc_fence_before();
-          if (to_smem) {
-            fence_proxy_async();
-            mbar_arrive(bar_dz);
-          }
-        } else {
-          // latent gradient: columns [enc_dim, enc_dim + T) of dX0 live at accD columns enc_dim - 8*lat_c0 + t
-          if (ch == 0) {
-            uint32_t v[16];
-            const int phase = valid ? load_phase(a.src, p) : -1;
-            for (int c0 = 0; c0 < lat_n; c0 += 16) {
-              tmem_ld16(t_lane + BW_COL_D + c0, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int t = c0 + e - (a.enc_dim - 8 * lat_c0);
-                if (t >= 0 && t < a.n_latent && phase >= 0 && phase < a.n_phases)
-                  atomicAdd(&s_lat[phase * a.n_latent + t], __uint_as_float(v[e]));
-              }
-            }
-          }
-          tc_fence_before();
-        }
-      }
-      mbar_arrive(bar_free);
-    }
-    // ---- all tiles issued: wait for the last MMAs, then flush the TMEM-resident accumulators
-    if (n_my > 0) {
-      mbar_wait(bar_done, (uint32_t)((n_my - 1) & 1));
+      mbar_arrive(bar_e);
+      // ---- dZ3 = (dZ4 W4) * 1[H3 > 0]  -> S
+      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
-      for (int j = 0; j < a.n_layers; ++j) {
-        const int l = a.l_hi - j;
-        const int n_in = (l > 0) ? 128 : a.kpad0, k_in = (l > 0) ? 128 : a.in_dim;
-        float* gw = a.g_w[j];
-        for (int c0 = ch * 64; c0 < n_in && c0 < ch * 64 + 64; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(t_lane + (j == 0 ? BW_COL_W0 : BW_COL_W1) + c0, v);
-          tmem_ld_wait();
+      ld_acc64(t_acc, va, vb);
+      masked_grad_store(va, vb, h3, s_s, row, ch);
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(bar_e);
+      // ---- dZ2 = (dZ3 W3) * 1[H2 > 0]  -> R -> hand-off
+      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+      tc_fence_after();
+      ld_acc64(t_acc, va, vb);
+      masked_grad_store(va, vb, h2, s_r, row, ch);
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(bar_out);
+      mbar_arrive(bar_accfree);
+    }
+    // ---- flush the TMEM-resident accumulators
+    if (ch == 0) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (c0 + e < k_in) atomicAdd(gw + (size_t)row * k_in + c0 + e, __uint_as_float(v[e]));
-        }
-        if (ch == 0) {
-          uint32_t v[16];
-          tmem_ld16(t_lane + (j == 0 ? BW_COL_B0 : BW_COL_B1), v);
-          tmem_ld_wait();
-          if (a.g_b[j]) atomicAdd(a.g_b[j] + row, __uint_as_float(v[2]));
-        }
-      }
-      if (a.from_raw && ch == 1) {
+      for (int o = 16; o > 0; o >>= 1) gb_sum += __shfl_xor_sync(0xffffffffu, gb_sum, o);
+      if (lane == 0 && nt.g_b[5]) atomicAdd(s_gbout, gb_sum);
+    }
+    if (n_my > 0) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+      flush_wgrad(t_lane, TOP_WG4, nt.g_w[4], row, ch, 128, 128);
+      flush_wgrad(t_lane, TOP_WG3, nt.g_w[3], row, ch, 128, 128);
+      if (ch == 0) {
         uint32_t v[16];
-        tmem_ld16(t_lane + BW_COL_O, v);
+        tmem_ld16(t_lane + TOP_BG4, v);
         tmem_ld_wait();
-        atomicAdd(a.g_wout + row, __uint_as_float(v[0]) + __uint_as_float(v[1]));
+        if (nt.g_b[4]) atomicAdd(nt.g_b[4] + row, __uint_as_float(v[2]));
+        tmem_ld16(t_lane + TOP_BG3, v);
+        tmem_ld_wait();
+        if (nt.g_b[3]) atomicAdd(nt.g_b[3] + row, __uint_as_float(v[2]));
+      } else {
+        uint32_t v[16];
+        tmem_ld16(t_lane + TOP_ACCO, v);
+        tmem_ld_wait();
+        atomicAdd(nt.g_w[5] + row, __uint_as_float(v[0]) + __uint_as_float(v[1]));
       }
       tc_fence_before();
     }
   }
+  tc_fence_before();
   __syncthreads();
-  if (a.g_lat)
-    for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x)
-      if (s_lat[i] != 0.f) atomicAdd(a.g_lat + i, s_lat[i]);
+  if (threadIdx.x == 0 && nt.g_b[5] && n_my > 0) atomicAdd(nt.g_b[5], s_gbout[0]);
   if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
-static size_t bwd_smem_bytes(const nerfca_field_t& f, const TcDims& d, int l_hi, int n_layers) {
-  size_t w = 0;
-  for (int j = 0; j < n_layers; ++j) {
-    const int l = l_hi - j;
-    if (l > 0) w += 32768;
-    else if (f.n_latent > 0) w += (size_t)d.kpad0 * 256;
+// =====================================================================================================================
+// backward, bottom pass: layers 2, 1, 0 (+ latent gradients)
+// =====================================================================================================================
+constexpr uint32_t BOT_ACC = 0, BOT_WG2 = 128, BOT_WG1 = 256, BOT_WG0 = 384, BOT_BG2 = 480, BOT_BG1 = 496;
+
+// Four 32 KB tile buffers form a ring; every tile makes five allocations in this order
+//   a0 dZ2 (loaded)  a1 H0 (loaded)  a2 H1 (recomputed)  a3 dZ1  a4 dZ0
+// allocation k = 5 * i + j lives in buffer k % 4 and may be filled once allocation k - 4 is dead; "dead" is one
+// tcgen05.commit on dead[k % 4] issued by the MMA thread after the last GEMM reading it (and after the epilogue
+// finished reading its ReLU pattern), so the wait parity is ((k / 4) - 1) & 1.
+// smem: [W1][W2][ring 4 x 32 KB][X0: 96 * 256][W0 latent chunks 4 KB][side 4 KB][bias1 (128 f32)][latent acc 512 f32][barriers]
+__global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int net_id = blockIdx.x % a.n_nets;
+  const BwdNet& nt = a.net[net_id];
+  const long long worker = blockIdx.x / a.n_nets, n_workers = gridDim.x / a.n_nets;
+  const bool has_lat = nt.n_latent > 0;
+  const int kpad0 = nt.x0.kpad0;
+  const int lat_c0 = nt.enc_dim / 8;                                        // first chunk holding latent columns
+  const int lat_n = has_lat ? ((nt.enc_dim % 8 + nt.n_latent + 15) / 16) * 16 : 0;   // MMA N covering them
+  uint8_t* s_w1 = smem;
+  uint8_t* s_w2 = smem + TILE_BYTES;
+  uint8_t* s_ring = smem + 2 * TILE_BYTES;
+  uint8_t* s_x0 = smem + 6 * TILE_BYTES;
+  uint8_t* s_w0lat = s_x0 + 96 * 256;
+  uint8_t* s_side = s_w0lat + 4096;
+  float* s_bias1 = reinterpret_cast<float*>(s_side + 4096);
+  float* s_lat = s_bias1 + 128;
+  const int n_lat_acc = has_lat ? nt.n_phases * nt.n_latent : 0;            // <= 256 checked on the host
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_lat + 256);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
+  const uint32_t bar_w = smem_u32(s_bar), bar_ld_dz = bar_w + 8, bar_ld_h0 = bar_w + 16, bar_acc = bar_w + 24, bar_e = bar_w + 32,
+                 bar_x0 = bar_w + 40, bar_x0free = bar_w + 48, bar_accfree = bar_w + 56, bar_done = bar_w + 64, bar_dead0 = bar_w + 72;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_init(bar_w, 1); mbar_init(bar_ld_dz, 1); mbar_init(bar_ld_h0, 1); mbar_init(bar_acc, 1); mbar_init(bar_e, 256);
+      mbar_init(bar_x0, 256); mbar_init(bar_x0free, 1); mbar_init(bar_accfree, 256); mbar_init(bar_done, 1);
+      for (int b = 0; b < 4; ++b) mbar_init(bar_dead0 + 8 * b, 1);
+      mbar_init_fence();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(s_tmem), 512);
   }
-  const int l_lo = l_hi - n_layers + 1;
-  const int n_lat_acc = (f.n_latent > 0 && l_lo == 0) ? f.n_phases * f.n_latent : 0;
-  return w + 4 * 32768 + 4096 + 128 * sizeof(float) + (size_t)((n_lat_acc + 3) & ~3) * sizeof(float) + 8 * sizeof(uint64_t);
+  {
+    const float* fb = reinterpret_cast<const float*>(nt.pack + nt.f32_off);
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_bias1[i] = __ldg(fb + 128 + i);
+    for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x) s_lat[i] = 0.f;
+    // side tile: column 0 == 1 in every row (bias gradients = column sums of dZ)
+    for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(s_side)[i] = (i < 128) ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  tc_fence_before();
+  fence_proxy_async();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
+  auto ring = [&](long long k) -> uint8_t* { return s_ring + (size_t)(k & 3) * TILE_BYTES; };
+  auto wait_free = [&](long long k) {   // buffer of allocation k is reusable
+    if (k >= 4) mbar_wait(bar_dead0 + 8 * (uint32_t)(k & 3), (uint32_t)(((k >> 2) - 1) & 1));
+  };
+
+  if (warp == 8) {
+    // ================= MMA warp =================
+    if (lane == 0) {
+      const uint32_t lat_bytes = has_lat ? (uint32_t)(lat_n / 8) * CHUNK_BYTES : 0u;
+      mbar_expect_tx(bar_w, 2 * TILE_BYTES + lat_bytes);
+      bulk_g2s(smem_u32(s_w1), nt.pack + nt.w0_bytes, TILE_BYTES, bar_w);
+      bulk_g2s(smem_u32(s_w2), nt.pack + nt.w0_bytes + (size_t)TILE_BYTES, TILE_BYTES, bar_w);
+      if (has_lat) bulk_g2s(smem_u32(s_w0lat), nt.pack + (size_t)lat_c0 * CHUNK_BYTES, lat_bytes, bar_w);
+      mbar_wait(bar_w, 0);
+      const uint32_t w1 = smem_u32(s_w1), w2 = smem_u32(s_w2), side = smem_u32(s_side), x0 = smem_u32(s_x0), w0lat = smem_u32(s_w0lat);
+      constexpr uint32_t id_fwd = instr_desc(128, 128, 0, 0), id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1),
+                         id_side = instr_desc(128, 16, 1, 1);
+      const uint32_t id_wg0 = instr_desc(128, kpad0, 1, 1), id_lat = instr_desc(128, lat_n > 0 ? lat_n : 16, 0, 1);
+      uint32_t ph_dz = 0, ph_h0 = 0, ph_e = 0, ph_x0 = 0, ph_accfree = 0;
+      for (long long i = 0; i < n_my; ++i) {
+        const long long k = 5 * i;
+        const uint32_t dz2 = smem_u32(ring(k)), h0 = smem_u32(ring(k + 1)), h1 = smem_u32(ring(k + 2)), dz1 = smem_u32(ring(k + 3)),
+                       dz0 = smem_u32(ring(k + 4));
+        const uint32_t first = (i > 0) ? 1u : 0u;
+        // Z1 = H0 W1^T
+        mbar_wait(bar_ld_h0, ph_h0); ph_h0 ^= 1;
+        if (i > 0) { mbar_wait(bar_accfree, ph_accfree); ph_accfree ^= 1; }
+        tc_fence_after();
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_ACC, desc_kmajor(h0, kk), desc_kmajor(w1, kk), id_fwd, kk > 0);
+        umma_commit(bar_acc);
+        // dgrad 2, wgrad 2, bias grad 2
+        mbar_wait(bar_e, ph_e); ph_e ^= 1;           // H1 written
+        mbar_wait(bar_ld_dz, ph_dz); ph_dz ^= 1;
+        tc_fence_after();
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_ACC, desc_kmajor(dz2, kk), desc_mnmajor(w2, kk), id_dgrad, kk > 0);
+        umma_commit(bar_acc);
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_WG2, desc_mnmajor(dz2, kk), desc_mnmajor(h1, kk), id_wgrad, first | (kk > 0));
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_BG2, desc_mnmajor(dz2, kk), desc_mnmajor(side, kk), id_side, first | (kk > 0));
+        // dgrad 1, wgrad 1, bias grad 1
+        mbar_wait(bar_e, ph_e); ph_e ^= 1;           // dZ1 written, H1's pattern consumed
+        tc_fence_after();
+        umma_commit(bar_dead0 + 8 * (uint32_t)(k & 3));         // dZ2
+        umma_commit(bar_dead0 + 8 * (uint32_t)((k + 2) & 3));   // H1
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_ACC, desc_kmajor(dz1, kk), desc_mnmajor(w1, kk), id_dgrad, kk > 0);
+        umma_commit(bar_acc);
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_WG1, desc_mnmajor(dz1, kk), desc_mnmajor(h0, kk), id_wgrad, first | (kk > 0));
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_BG1, desc_mnmajor(dz1, kk), desc_mnmajor(side, kk), id_side, first | (kk > 0));
+        // wgrad 0 (its constant-1 column is the bias gradient), latent dgrad
+        mbar_wait(bar_e, ph_e); ph_e ^= 1;           // dZ0 written, H0's pattern consumed
+        mbar_wait(bar_x0, ph_x0); ph_x0 ^= 1;
+        tc_fence_after();
+        umma_commit(bar_dead0 + 8 * (uint32_t)((k + 1) & 3));   // H0
+        umma_commit(bar_dead0 + 8 * (uint32_t)((k + 3) & 3));   // dZ1
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_WG0, desc_mnmajor(dz0, kk), desc_mnmajor(x0, kk), id_wg0, first | (kk > 0));
+        if (has_lat) {
+          for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_ACC, desc_kmajor(dz0, kk), desc_mnmajor(w0lat, kk), id_lat, kk > 0);
+          umma_commit(bar_acc);
+        }
+        umma_commit(bar_dead0 + 8 * (uint32_t)((k + 4) & 3));   // dZ0
+        umma_commit(bar_x0free);
+      }
+      umma_commit(bar_done);
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ================= load warp =================
+    if (lane == 0) {
+      for (long long i = 0; i < n_my; ++i) {
+        const long long tile = worker + i * n_workers;
+        const long long k = 5 * i;
+        wait_free(k + 1);
+        mbar_expect_tx(bar_ld_h0, TILE_BYTES);
+        bulk_g2s(smem_u32(ring(k + 1)), nt.stash + (size_t)tile * STASH_TILES * TILE_BYTES, TILE_BYTES, bar_ld_h0);
+        wait_free(k);
+        mbar_expect_tx(bar_ld_dz, TILE_BYTES);
+        bulk_g2s(smem_u32(ring(k)), nt.handoff + (size_t)tile * TILE_BYTES, TILE_BYTES, bar_ld_dz);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    // nothing to store in this pass
+  } else {
+    // ================= 8 epilogue warps =================
+    const int q = warp & 3, ch = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_acc = t_lane + BOT_ACC + ch * 64;
+    uint32_t ph_acc = 0, ph_x0free = 0;
+    for (long long i = 0; i < n_my; ++i) {
+      const long long tile = worker + i * n_workers;
+      const long long p = tile * TILE_M + row;
+      const bool valid = p < a.src.n_points;
+      const long long k = 5 * i;
+      uint32_t va[32], vb[32];
+      // ---- X0 (needed last, built first: it only waits for the previous tile's wgrad 0)
+      if (i > 0) { mbar_wait(bar_x0free, ph_x0free); ph_x0free ^= 1; }
+      build_x0_row(nt.x0, a.src, p, valid, s_x0, row, ch);
+      fence_proxy_async();
+      mbar_arrive(bar_x0);
+      // ---- H1 = relu(Z1 + b1)
+      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+      tc_fence_after();
+      ld_acc64(t_acc, va, vb);
+      wait_free(k + 2);
+      relu_bias_store(va, vb, s_bias1, ring(k + 2), row, ch);
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(bar_e);
+      // ---- dZ1 = (dZ2 W2) * 1[H1 > 0]
+      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+      tc_fence_after();
+      ld_acc64(t_acc, va, vb);
+      wait_free(k + 3);
+      masked_grad_store(va, vb, ring(k + 2), ring(k + 3), row, ch);
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(bar_e);
+      // ---- dZ0 = (dZ1 W1) * 1[H0 > 0]
+      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+      tc_fence_after();
+      ld_acc64(t_acc, va, vb);
+      wait_free(k + 4);
+      masked_grad_store(va, vb, ring(k + 1), ring(k + 4), row, ch);
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(bar_e);
+      // ---- latent gradient: columns [enc_dim, enc_dim + T) of dX0 sit at accumulator columns enc_dim - 8 * lat_c0 + t
+      if (has_lat) {
+        mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+        tc_fence_after();
+        if (ch == 0) {
+          // a warp's 32 rows are consecutive samples, almost always of one ray (one phase): reduce over the warp
+          // first and add once; rows of a warp that straddles two rays fall back to per-lane atomics
+          const int phase = valid ? load_phase(a.src, p) : -1;
+          const int ph0 = __shfl_sync(0xffffffffu, phase, 0);
+          const bool uniform = __all_sync(0xffffffffu, phase == ph0 || phase < 0);
+          const bool ok = phase >= 0 && phase < nt.n_phases;
+          uint32_t v[16];
+          for (int c0 = 0; c0 < lat_n; c0 += 16) {
+            tmem_ld16(t_lane + BOT_ACC + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int t = c0 + e - (nt.enc_dim - 8 * lat_c0);
+              if (t < 0 || t >= nt.n_latent) continue;      // warp-uniform
+              float val = ok ? __uint_as_float(v[e]) : 0.f;
+              if (uniform) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                if (lane == 0 && ph0 >= 0 && ph0 < nt.n_phases) atomicAdd(&s_lat[ph0 * nt.n_latent + t], val);
+              } else if (ok) {
+                atomicAdd(&s_lat[phase * nt.n_latent + t], val);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+      }
+      mbar_arrive(bar_accfree);
+    }
+    if (n_my > 0) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+      flush_wgrad(t_lane, BOT_WG2, nt.g_w[2], row, ch, 128, 128);
+      flush_wgrad(t_lane, BOT_WG1, nt.g_w[1], row, ch, 128, 128);
+      flush_wgrad(t_lane, BOT_WG0, nt.g_w[0], row, ch, kpad0, nt.in_dim);
+      if (ch == 0) {
+        uint32_t v[16];
+        tmem_ld16(t_lane + BOT_BG2, v);
+        tmem_ld_wait();
+        if (nt.g_b[2]) atomicAdd(nt.g_b[2] + row, __uint_as_float(v[0]));
+        tmem_ld16(t_lane + BOT_BG1, v);
+        tmem_ld_wait();
+        if (nt.g_b[1]) atomicAdd(nt.g_b[1] + row, __uint_as_float(v[0]));
+      } else if (nt.g_b[0]) {   // bias 0 = the constant-1 column (index in_dim) of wgrad 0
+        const int c0 = nt.in_dim & ~15;
+        uint32_t v[16];
+        tmem_ld16(t_lane + BOT_WG0 + c0, v);
+        tmem_ld_wait();
+        float val = 0.f;
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (c0 + e == nt.in_dim) val = __uint_as_float(v[e]);
+        atomicAdd(nt.g_b[0] + row, val);
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (nt.g_lat)
+    for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x)
+      if (s_lat[i] != 0.f) atomicAdd(nt.g_lat + i, s_lat[i]);
+  if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
-int tc_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, const float* d_raw, const void* stash, void* workspace,
-                      const nerfca_field_grads_t& gr, cudaStream_t st) {
-  const TcDims d = tc_dims(f);
-  NERFCA_REQUIRE(f.n_latent == 0 || (size_t)f.n_phases * f.n_latent * sizeof(float) <= 16 * 1024, NERFCA_E_UNSUPPORTED,
-                 "tcgen05 backward: latent table too large for the shared-memory accumulator (use precision fp32)");
-  NERFCA_REQUIRE(f.n_latent == 0 || (enc_dim_of(f) % 8 + f.n_latent + 15) / 16 * 16 + enc_dim_of(f) / 8 * 8 <= d.kpad0,
-                 NERFCA_E_UNSUPPORTED, "tcgen05 backward: latent columns do not fit the padded first layer");
-  int rc = pack_params(f, d, workspace, st);   // same packing as the forward (weights may have changed since)
-  if (rc) return rc;
+// =====================================================================================================================
+// host side
+// =====================================================================================================================
+static size_t fwd_smem_bytes(const NetDims& d) { return (((size_t)d.pack_bytes + 127) & ~(size_t)127) + 2 * TILE_BYTES + 9 * 8 + 16; }
+constexpr size_t TOP_SMEM = 6 * (size_t)TILE_BYTES + 4096 + 384 * 4 + 16 + 10 * 8 + 16;
+constexpr size_t BOT_SMEM = 6 * (size_t)TILE_BYTES + 96 * 256 + 4096 + 4096 + 128 * 4 + 256 * 4 + 16 * 8 + 16;
+
+static size_t n_tiles_of(long long P) { return (size_t)((P + TILE_M - 1) / TILE_M); }
+
+// stash: [net][tile][2][32 KB]
+size_t tc_stash_bytes_n(int n_nets, long long P) { return (size_t)n_nets * n_tiles_of(P) * STASH_TILES * TILE_BYTES; }
+// workspace: [packed blocks][hand-off: net, tile, 32 KB (backward only)]
+static size_t tc_pack_bytes_n(const nerfca_field_t* const* f, int n_nets) {
+  size_t n = 0;
+  for (int i = 0; i < n_nets; ++i) n += pack_stride(net_dims(*f[i]));
+  return n;
+}
+size_t tc_workspace_bytes_n(const nerfca_field_t* const* f, int n_nets, long long P, int backward) {
+  size_t n = tc_pack_bytes_n(f, n_nets);
+  if (backward) n += (size_t)n_nets * n_tiles_of(P) * TILE_BYTES;
+  return n;
+}
+
+static X0Desc make_x0(const nerfca_field_t& f, const NetDims& d) {
+  X0Desc x;
+  x.enc = make_enc(f);
+  x.kpad0 = d.kpad0;
+  x.fast = (x.enc.mode == NERFCA_ENC_BANDS && f.n_freq == FAST_FREQ) ? 1 : 0;
+  return x;
+}
+
+static unsigned grid_for(int n_nets, long long n_tiles) {
+  long long g = sm_count() / n_nets * n_nets;
+  const long long need = n_tiles * n_nets;
+  if (need < g) g = need;
+  return (unsigned)g;
+}
+
+// Forward of n_nets (1 or 2) fields over the same sample set in one launch.  pack != 0: (re)pack the parameters into
+// the head of `workspace` first.
+int tc_fields_forward(const nerfca_field_t* const* f, int n_nets, const nerfca_samples_t& s, float* const* raw_out, void* stash,
+                      void* workspace, int pack, cudaStream_t st) {
+  if (pack) {
+    int rc = pack_params(f, n_nets, workspace, st);
+    if (rc) return rc;
+  }
+  FwdArgs a;
+  a.src = make_src(s);
+  a.n_nets = n_nets;
+  a.n_tiles = (long long)n_tiles_of(s.n_points);
+  size_t off = 0, smem = 0;
+  for (int i = 0; i < n_nets; ++i) {
+    const NetDims d = net_dims(*f[i]);
+    FwdNet& n = a.net[i];
+    n.pack = (const uint8_t*)workspace + off;
+    off += pack_stride(d);
+    n.raw_out = raw_out[i];
+    n.stash = stash ? (uint8_t*)stash + (size_t)i * a.n_tiles * STASH_TILES * TILE_BYTES : nullptr;
+    n.x0 = make_x0(*f[i], d);
+    n.w0_bytes = d.w0_bytes; n.wout_off = d.wout_off; n.f32_off = d.f32_off; n.pack_bytes = d.pack_bytes;
+    const size_t sm = fwd_smem_bytes(d);
+    smem = sm > smem ? sm : smem;
+  }
+  NERFCA_REQUIRE(smem <= 227 * 1024, NERFCA_E_UNSUPPORTED, "field does not fit the forward kernel's shared memory");
+  NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(NERFCA_K_FIELD_FWD, st);
+  tc_forward_kernel<<<grid_for(n_nets, a.n_tiles), FWD_THREADS, smem, st>>>(a);
+  NERFCA_LAUNCH_OK();
+  return NERFCA_OK;
+}
+
+int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_samples_t& s, const float* const* d_raw,
+                       const void* stash, void* workspace, int pack, const nerfca_field_grads_t* const* gr, cudaStream_t st) {
+  if (pack) {
+    int rc = pack_params(f, n_nets, workspace, st);
+    if (rc) return rc;
+  }
   BwdArgs a;
   a.src = make_src(s);
-  a.params = (const uint8_t*)workspace;
-  a.stash = (const uint8_t*)stash;
-  a.handoff = (uint8_t*)workspace + ((tc_param_bytes(d) + 255) & ~(size_t)255);
-  a.d_raw = d_raw;
-  a.g_wout = gr.weight[d.n_relu]; a.g_bout = gr.bias[d.n_relu]; a.g_lat = gr.latents;
-  a.n_tiles = (s.n_points + TILE_M - 1) / TILE_M;
-  a.kpad0 = d.kpad0; a.n_relu = d.n_relu; a.in_dim = d.in_dim; a.enc_dim = enc_dim_of(f); a.n_latent = f.n_latent;
-  a.n_phases = f.n_phases;
-  a.w_bytes = (uint32_t)d.w_bytes; a.tile_stash_bytes = (uint32_t)d.tile_stash_bytes;
-  const long long grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
-  size_t max_smem = 0;
-  for (int l_hi = d.n_relu - 1; l_hi >= 0; l_hi -= 2) {
-    const size_t sm = bwd_smem_bytes(f, d, l_hi, l_hi >= 1 ? 2 : 1);
-    max_smem = sm > max_smem ? sm : max_smem;
+  a.n_nets = n_nets;
+  a.n_tiles = (long long)n_tiles_of(s.n_points);
+  size_t off = 0;
+  uint8_t* handoff = (uint8_t*)workspace + tc_pack_bytes_n(f, n_nets);
+  for (int i = 0; i < n_nets; ++i) {
+    const NetDims d = net_dims(*f[i]);
+    BwdNet& n = a.net[i];
+    n.pack = (const uint8_t*)workspace + off;
+    off += pack_stride(d);
+    n.stash = (const uint8_t*)stash + (size_t)i * a.n_tiles * STASH_TILES * TILE_BYTES;
+    n.handoff = handoff + (size_t)i * a.n_tiles * TILE_BYTES;
+    n.d_raw = d_raw[i];
+    for (int l = 0; l < NERFCA_MAX_LAYERS; ++l) { n.g_w[l] = gr[i]->weight[l]; n.g_b[l] = gr[i]->bias[l]; }
+    n.g_lat = gr[i]->latents;
+    n.x0 = make_x0(*f[i], d);
+    n.w0_bytes = d.w0_bytes; n.f32_off = d.f32_off;
+    n.in_dim = d.in_dim; n.enc_dim = d.enc_dim; n.n_latent = f[i]->n_latent; n.n_phases = f[i]->n_phases;
+    NERFCA_REQUIRE(f[i]->n_latent == 0 || (d.enc_dim % 8 + f[i]->n_latent + 15) / 16 * 16 + d.enc_dim / 8 * 8 <= d.kpad0,
+                   NERFCA_E_UNSUPPORTED, "tcgen05 backward: latent columns do not fit the padded first layer");
+    NERFCA_REQUIRE(f[i]->n_latent == 0 || (size_t)f[i]->n_phases * f[i]->n_latent <= 256, NERFCA_E_UNSUPPORTED,
+                   "tcgen05 backward: latent table larger than 256 floats (use precision fp32)");
   }
-  NERFCA_REQUIRE(max_smem <= 227 * 1024, NERFCA_E_UNSUPPORTED, "field does not fit the backward kernel's shared memory");
-  NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-  for (int l_hi = d.n_relu - 1; l_hi >= 0; l_hi -= 2) {
-    a.l_hi = l_hi;
-    a.n_layers = l_hi >= 1 ? 2 : 1;
-    a.from_raw = (l_hi == d.n_relu - 1);
-    for (int j = 0; j < 2; ++j) {
-      const int l = l_hi - j;
-      a.g_w[j] = (j < a.n_layers) ? gr.weight[l] : nullptr;
-      a.g_b[j] = (j < a.n_layers) ? gr.bias[l] : nullptr;
-    }
-    tc_backward_kernel<<<(unsigned)grid, TC_THREADS, bwd_smem_bytes(f, d, l_hi, a.n_layers), st>>>(a);
+  NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_bwd_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOP_SMEM));
+  NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_bwd_bot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BOT_SMEM));
+  const unsigned grid = grid_for(n_nets, a.n_tiles);
+  {
+    ProfScope prof(NERFCA_K_FIELD_BWD, st);
+    tc_bwd_top_kernel<<<grid, BWD_THREADS, TOP_SMEM, st>>>(a);
+    NERFCA_LAUNCH_OK();
+  }
+  {
+    ProfScope prof(NERFCA_K_FIELD_BWD, st);
+    tc_bwd_bot_kernel<<<grid, BWD_THREADS, BOT_SMEM, st>>>(a);
     NERFCA_LAUNCH_OK();
   }
   return NERFCA_OK;
+}
+
+// ---- single-field entry points (module-level CPPN.forward / Temporal.forward_composite and their autograd) ----------
+size_t tc_stash_bytes(const nerfca_field_t& f, long long P) { (void)f; return tc_stash_bytes_n(1, P); }
+size_t tc_workspace_bytes(const nerfca_field_t& f, long long P, int backward) {
+  const nerfca_field_t* fs[1] = {&f};
+  return tc_workspace_bytes_n(fs, 1, P, backward);
+}
+int tc_field_forward(const nerfca_field_t& f, const nerfca_samples_t& s, float* raw_out, void* stash, void* workspace,
+                     cudaStream_t st) {
+  const nerfca_field_t* fs[1] = {&f};
+  float* outs[1] = {raw_out};
+  return tc_fields_forward(fs, 1, s, outs, stash, workspace, 1, st);
+}
+int tc_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, const float* d_raw, const void* stash, void* workspace,
+                      const nerfca_field_grads_t& gr, cudaStream_t st) {
+  const nerfca_field_t* fs[1] = {&f};
+  const float* ds[1] = {d_raw};
+  const nerfca_field_grads_t* gs[1] = {&gr};
+  return tc_fields_backward(fs, 1, s, ds, stash, workspace, 1, gs, st);
 }
 
 }  // namespace nerfca

@@ -48,6 +48,28 @@ class LossCfgStruct(C.Structure):
                 ("entro_use_weighting", C.c_int32), ("n_rays_global", C.c_int32)]
 
 
+class StepStruct(C.Structure):
+    _fields_ = [("static_field", C.POINTER(FieldStruct)), ("dynamic_field", C.POINTER(FieldStruct)),
+                ("static_grads", C.POINTER(FieldGradsStruct)), ("dynamic_grads", C.POINTER(FieldGradsStruct)),
+                ("samples", C.POINTER(SamplesStruct)), ("precision", C.c_int32), ("activation", C.c_int32),
+                ("i0", C.c_void_p), ("gt", C.c_void_p), ("wpix", C.c_void_p), ("gw_stride", C.c_int32), ("reserved", C.c_int32),
+                ("loss", C.POINTER(LossCfgStruct)),
+                ("raw_s", C.c_void_p), ("raw_d", C.c_void_p), ("d_raw_s", C.c_void_p), ("d_raw_d", C.c_void_p),
+                ("stash", C.c_void_p), ("workspace", C.c_void_p), ("pix_out", C.c_void_p), ("terms_out", C.c_void_p)]
+
+
+class AdamCfgStruct(C.Structure):
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("lr_end_factor", C.c_double), ("lr_decay_steps", C.c_int64)]
+
+
+K_RAYS, K_PACK, K_FIELD_FWD, K_LOSS, K_FIELD_BWD, K_ADAM, K_COUNT = range(7)
+KERNEL_FAMILY_NAMES = {K_RAYS: "rays", K_PACK: "pack_params", K_FIELD_FWD: "field_forward", K_LOSS: "integral_loss",
+                       K_FIELD_BWD: "field_backward", K_ADAM: "adam"}
+
+
+
+
 LIB_NAME = "libnerfca_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), LIB_NAME)
 
@@ -68,6 +90,14 @@ _SIGNATURES = {
     "nerfca_integrate_backward": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "nerfca_composite_loss": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, C.POINTER(LossCfgStruct), _P, _P,
                                         _P, _P, _P]),
+    "nerfca_step_stash_bytes": (C.c_size_t, [C.POINTER(StepStruct)]),
+    "nerfca_step_workspace_bytes": (C.c_size_t, [C.POINTER(StepStruct)]),
+    "nerfca_train_step": (C.c_int, [C.POINTER(StepStruct), _P]),
+    "nerfca_fields_forward": (C.c_int, [C.POINTER(FieldStruct), C.POINTER(FieldStruct), C.POINTER(SamplesStruct), _I32, _P, _P, _P, _P]),
+    "nerfca_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _P, C.POINTER(AdamCfgStruct), _F, _I32, _P]),
+    "nerfca_launch_count": (C.c_int64, []),
+    "nerfca_profile_enable": (C.c_int, [_I32]),
+    "nerfca_profile_read": (C.c_int, [_I32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

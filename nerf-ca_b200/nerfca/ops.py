@@ -374,6 +374,84 @@ def _grad_buffers(params: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     return out
 
 
+class _Scratch:
+    """Per-(device, size) scratch tensors of the fused step, reused across steps (pointer-stable for CUDA graphs)."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, key, nbytes_or_shape, dtype, device):
+        k = (key, str(device))
+        t = cls._cache.get(k)
+        shape = (int(nbytes_or_shape),) if not isinstance(nbytes_or_shape, tuple) else nbytes_or_shape
+        if t is None or t.dtype != dtype or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=dtype, device=device)
+            cls._cache[k] = t
+        return t
+
+    @classmethod
+    def clear(cls):
+        cls._cache.clear()
+
+
+def _grad_struct(spec: FieldSpec, grads: Sequence[torch.Tensor]) -> L.FieldGradsStruct:
+    glat, gws, gbs = spec.split(grads)
+    g = L.FieldGradsStruct()
+    g.latents = L.ptr(glat)
+    for k, (w, b) in enumerate(zip(gws, gbs)):
+        g.weight[k] = L.ptr(w)
+        g.bias[k] = L.ptr(b)
+    return g
+
+
+def _fused_step(static_model, temp_model, rays: torch.Tensor, phases, i0: torch.Tensor, depth: torch.Tensor, output_activation: str,
+                cfg: LossConfig, terms: Optional[torch.Tensor]):
+    """nerfca_train_step: forward of both fields (one launch), line integral + losses + dL/d_raw, both backward passes."""
+    if rays.dim() != 3 or rays.shape[1:] != (4, 3):
+        raise ValueError("rays must be [B,4,3] (origin, direction, pixel, weight rows)")
+    lib = L.load()
+    samples = Samples.from_rays(rays[:, 0, :], rays[:, 1, :], depth, phases)
+    dev = samples.device
+    B, P = rays.shape[0], samples.n_points
+    models = [static_model] + ([temp_model] if temp_model is not None else [])
+    prec = models[0]._precision_code()
+    if any(m._precision_code() != prec for m in models):
+        raise ValueError("both fields must use the same precision in a fused step")
+    specs = [m._spec() for m in models]
+    pars = [_check_params(sp, m._param_list()) for sp, m in zip(specs, models)]
+    fstructs = [sp.struct(p) for sp, p in zip(specs, pars)]
+    gstructs = [_grad_struct(sp, _grad_buffers(m._param_list())) for sp, m in zip(specs, models)]
+    gt, wpix = rays[:, 2, 0], rays[:, 3, 0]
+    if gt.dtype != torch.float64 or gt.stride(0) != wpix.stride(0):
+        gt, wpix = gt.to(torch.float64).contiguous(), wpix.to(torch.float64).contiguous()
+    pix = torch.empty((B,), dtype=torch.float64, device=dev)
+    if terms is None:
+        terms = torch.zeros((L.N_LOSS_TERMS,), dtype=torch.float64, device=dev)
+    lc = cfg.struct(B)
+    i0f = i0.to(device=dev, dtype=torch.float32).contiguous()
+    st = L.StepStruct()
+    st.static_field = C.pointer(fstructs[0])
+    st.static_grads = C.pointer(gstructs[0])
+    if len(models) > 1:
+        st.dynamic_field = C.pointer(fstructs[1])
+        st.dynamic_grads = C.pointer(gstructs[1])
+    st.samples = C.pointer(samples.struct())
+    st.precision, st.activation = prec, activation_code(output_activation)
+    st.i0, st.gt, st.wpix = L.ptr(i0f), L.ptr(gt), L.ptr(wpix)
+    st.gw_stride = gt.stride(0) if B > 1 else 1
+    st.loss = C.pointer(lc)
+    n = len(models)
+    scratch = _Scratch.get(("raw", n, P), (4 if n > 1 else 2, P), torch.float32, dev)
+    st.raw_s, st.d_raw_s = L.ptr(scratch[0]), L.ptr(scratch[1])
+    if n > 1:
+        st.raw_d, st.d_raw_d = L.ptr(scratch[2]), L.ptr(scratch[3])
+    stash = _Scratch.get(("stash", n, P, prec), lib.nerfca_step_stash_bytes(C.byref(st)), torch.uint8, dev)
+    ws = _Scratch.get(("ws", n, P, prec), lib.nerfca_step_workspace_bytes(C.byref(st)), torch.uint8, dev)
+    st.stash, st.workspace = L.ptr(stash), L.ptr(ws)
+    st.pix_out, st.terms_out = L.ptr(pix), L.ptr(terms)
+    L.check(lib.nerfca_train_step(C.byref(st), L.stream_ptr()), "nerfca_train_step")
+    return terms, pix
+
+
 def train_step_composite(static_model, temp_model, rays: torch.Tensor, phases: torch.Tensor, i0: torch.Tensor,
                          depth: torch.Tensor, output_activation: str, cfg: LossConfig, terms: Optional[torch.Tensor] = None):
     """One fused composite training step (train/run_composite.py:262-305 minus the optimizer):
@@ -381,37 +459,17 @@ def train_step_composite(static_model, temp_model, rays: torch.Tensor, phases: t
         rays [B,4,3] float64 (rows: origin, direction, pixel x3, weight x3 -- data_helpers.py:161-163), phases [B],
         depth = the already-jittered depth vector [N].
 
-    Runs fields forward (points formed in-kernel), the fused integral + loss + dL/d_raw kernel and both fields'
-    backward; parameter gradients are ACCUMULATED into `.grad`.  Returns (terms[16] float64 device sums, pix[B]).
+    Runs both fields forward in one launch (points formed in-kernel), the fused integral + loss + dL/d_raw kernel and
+    the backward passes; parameter gradients are ACCUMULATED into `.grad`.  Returns (terms[16] float64 device sums, pix[B]).
     """
-    if rays.dim() != 3 or rays.shape[1:] != (4, 3):
-        raise ValueError("rays must be [B,4,3] (origin, direction, pixel, weight rows)")
-    samples = Samples.from_rays(rays[:, 0, :], rays[:, 1, :], depth, phases)
-    act = activation_code(output_activation)
-    spec_s, spec_d = static_model._spec(), temp_model._spec()
-    par_s, par_d = static_model._param_list(), temp_model._param_list()
-    prec_s, prec_d = static_model._precision_code(), temp_model._precision_code()
-    raw_s, stash_s = field_forward_raw(spec_s, samples, prec_s, par_s, keep_stash=True)
-    raw_d, stash_d = field_forward_raw(spec_d, samples, prec_d, par_d, keep_stash=True)
-    i0f = i0.to(device=raw_s.device, dtype=torch.float32).contiguous()
-    pix, terms, g_s, g_d = composite_loss(raw_s, raw_d, samples.depth, i0f, rays[:, 2, 0], rays[:, 3, 0], act, cfg, True, terms)
-    field_backward_raw(spec_s, samples, prec_s, par_s, g_s, stash_s, _grad_buffers(par_s))
-    field_backward_raw(spec_d, samples, prec_d, par_d, g_d, stash_d, _grad_buffers(par_d))
-    return terms, pix
+    return _fused_step(static_model, temp_model, rays, phases, i0, depth, output_activation, cfg, terms)
 
 
 def train_step_static(static_model, rays: torch.Tensor, i0: torch.Tensor, depth: torch.Tensor, output_activation: str,
                       occl_weight: float, n_rays_global: int = 0, terms: Optional[torch.Tensor] = None):
     """Fused static training step (train/run_nerf.py:205-233 minus the optimizer): loss = wMSE + occl_weight * occlusion."""
-    samples = Samples.from_rays(rays[:, 0, :], rays[:, 1, :], depth)
-    act = activation_code(output_activation)
-    spec, par, prec = static_model._spec(), static_model._param_list(), static_model._precision_code()
-    raw, stash = field_forward_raw(spec, samples, prec, par, keep_stash=True)
     cfg = LossConfig(occl_weight=occl_weight, n_rays_global=n_rays_global)
-    i0f = i0.to(device=raw.device, dtype=torch.float32).contiguous()
-    pix, terms, g, _ = composite_loss(raw, None, samples.depth, i0f, rays[:, 2, 0], rays[:, 3, 0], act, cfg, True, terms)
-    field_backward_raw(spec, samples, prec, par, g, stash, _grad_buffers(par))
-    return terms, pix
+    return _fused_step(static_model, None, rays, None, i0, depth, output_activation, cfg, terms)
 
 
 def render_frame(static_model, temp_model, origins: torch.Tensor, dirs: torch.Tensor, depth: torch.Tensor, phase,
@@ -438,9 +496,22 @@ def render_frame(static_model, temp_model, origins: torch.Tensor, dirs: torch.Te
         if dyn:
             ph = phase[r0:r1] if torch.is_tensor(phase) and phase.numel() > 1 else torch.full((r1 - r0,), int(phase), device=dev)
         smp = Samples.from_rays(o[r0:r1], d[r0:r1], z, ph)
-        raw_s, _ = field_forward_raw(spec_s, smp, prec_s, par_s, keep_stash=False)
-        raw_d = field_forward_raw(spec_d, smp, prec_d, par_d, keep_stash=False)[0] if dyn else None
         B = r1 - r0
+        fs_s = spec_s.struct(_check_params(spec_s, par_s))
+        fs_d = spec_d.struct(_check_params(spec_d, par_d)) if dyn else None
+        if dyn and prec_d != prec_s:
+            raise ValueError("both fields must use the same precision")
+        raws = _Scratch.get(("render_raw", B * N), (2, B * N), torch.float32, dev)
+        raw_s, raw_d = raws[0], (raws[1] if dyn else None)
+        stp = L.StepStruct()
+        stp.static_field = C.pointer(fs_s)
+        if dyn:
+            stp.dynamic_field = C.pointer(fs_d)
+        stp.samples = C.pointer(smp.struct())
+        stp.precision = prec_s
+        ws = _Scratch.get(("render_ws", B * N, prec_s, dyn), lib.nerfca_step_workspace_bytes(C.byref(stp)), torch.uint8, dev)
+        L.check(lib.nerfca_fields_forward(C.byref(fs_s), C.byref(fs_d) if dyn else None, C.byref(smp.struct()), prec_s, L.ptr(raw_s),
+                                          L.ptr(raw_d), L.ptr(ws), L.stream_ptr()), "nerfca_fields_forward")
         i0 = torch.full((B,), i0_value, dtype=torch.float32, device=dev)
         sig_a = torch.empty((B, N), dtype=torch.float32, device=dev)
         sig_b = torch.empty((B, N), dtype=torch.float32, device=dev)
