@@ -22,6 +22,10 @@
 //   tc_bwd_top_kernel   layers 4, 3 (+ output layer): loads H2, recomputes H3, Z4; dZ4 = d_raw * w_out * 1[Z4 > 0];
 //                       wgrad / bias-grad / w_out-grad accumulate in TMEM; writes dZ2 to the hand-off buffer.
 //   tc_bwd_bot_kernel   layers 2, 1, 0: loads dZ2, H0, recomputes H1 and X0; latent gradients by phase.
+#include <stdlib.h>
+
+#include <vector>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -278,7 +282,18 @@ struct FwdArgs {
   FwdNet net[2];
   int n_nets;
   long long n_tiles;
+  long long* dbg;   // optional event timeline of CTA 0 (NERFCA_TIMELINE=1): dbg[0] = count, then (tag, clock) pairs
 };
+// Each logging thread owns a region of 1000 (tag, clock) pairs selected by tag / 1000 (1: slot-0 epilogue, 2: slot-1
+// epilogue, 3: MMA thread) and keeps its own count: no atomics, the stores are fire-and-forget.
+#define NERFCA_TL(cond, tag)                                                              \
+  do {                                                                                    \
+    if (a.dbg && blockIdx.x == 0 && (cond) && tl_n < 1000) {                              \
+      long long* r__ = a.dbg + (size_t)((tag) / 1000) * 2000 + 2 * tl_n;                  \
+      r__[0] = (tag); r__[1] = clock64();                                                 \
+      ++tl_n;                                                                             \
+    }                                                                                     \
+  } while (0)
 
 constexpr uint32_t FWD_ACC_COL = 0, FWD_OUT_COL = 256;   // slot s: acc at s * 128, output-layer accumulator at 256 + s * 16
 
@@ -318,6 +333,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
   const uint32_t tmem = *s_tmem;
   const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
   const bool stash_on = nt.stash != nullptr;
+  int tl_n = 0;
 
   if (warp == 16) {
     // ================= MMA warp =================
@@ -331,28 +347,37 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
       constexpr uint32_t idesc = instr_desc(128, 128, 0, 0);
       constexpr uint32_t idesc_out = instr_desc(128, 16, 0, 0);
       const int k0steps = nt.x0.kpad0 / 16;
-      const uint32_t w_base = smem_u32(s_pack), wout = smem_u32(s_pack + nt.wout_off);
+      const uint32_t w_base = smem_u32(s_pack);
+      Desc d_w[TC_N_RELU], d_act[2];
+      d_w[0] = kmajor(w_base);
+      for (int l = 1; l < TC_N_RELU; ++l) d_w[l] = kmajor(w_base + nt.w0_bytes + (uint32_t)(l - 1) * TILE_BYTES);
+      const Desc d_wout = kmajor_rows(smem_u32(s_pack + nt.wout_off), 256);
+      d_act[0] = kmajor(smem_u32(s_act));
+      d_act[1] = kmajor(smem_u32(s_act + TILE_BYTES));
       uint32_t ph_act[2] = {0, 0};
       for (long long i0 = 0; i0 < n_my; i0 += 2) {
         const int nslots = (n_my - i0 >= 2) ? 2 : 1;
+#pragma unroll
         for (int l = 0; l <= TC_N_RELU; ++l) {
-          for (int s = 0; s < nslots; ++s) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            if (s >= nslots) continue;
             mbar_wait(bar_act0 + 8 * s, ph_act[s]);
             ph_act[s] ^= 1;
             tc_fence_after();
-            const uint32_t act = smem_u32(s_act + s * TILE_BYTES);
+            NERFCA_TL(true, 3000 + l * 10 + s);
+            const Desc act = d_act[s];
             if (l == 0) {
-              for (int kk = 0; kk < k0steps; ++kk)
-                umma_ss(tmem + FWD_ACC_COL + s * 128, desc_kmajor(act, kk), desc_kmajor(w_base, kk), idesc, kk > 0);
-            } else if (l < TC_N_RELU) {
-              const uint32_t wl = w_base + nt.w0_bytes + (uint32_t)(l - 1) * TILE_BYTES;
-              for (int kk = 0; kk < 8; ++kk)   // accumulator already holds the bias (tcgen05.st by the epilogue)
-                umma_ss(tmem + FWD_ACC_COL + s * 128, desc_kmajor(act, kk), desc_kmajor(wl, kk), idesc, 1);
+              umma_k<5, KSTEP_KMAJOR, KSTEP_KMAJOR>(tmem + FWD_ACC_COL + s * 128, act, d_w[0], idesc, 0);
+              if (k0steps > 5)
+                umma_lh(tmem + FWD_ACC_COL + s * 128, act.lo + 5 * KSTEP_KMAJOR, act.hi, d_w[0].lo + 5 * KSTEP_KMAJOR, d_w[0].hi, idesc, 1);
+            } else if (l < TC_N_RELU) {   // accumulator already holds the bias (tcgen05.st by the epilogue)
+              umma_k<8, KSTEP_KMAJOR, KSTEP_KMAJOR>(tmem + FWD_ACC_COL + s * 128, act, d_w[l], idesc, 1);
             } else {
-              for (int kk = 0; kk < 8; ++kk)
-                umma_ss(tmem + FWD_OUT_COL + s * 16, desc_kmajor(act, kk), desc_kmajor_rows(wout, kk, 256), idesc_out, kk > 0);
+              umma_k<8, KSTEP_KMAJOR, 32u>(tmem + FWD_OUT_COL + s * 16, act, d_wout, idesc_out, 0);
             }
             umma_commit(bar_acc0 + 8 * s);
+            NERFCA_TL(true, 3500 + l * 10 + s);
           }
         }
       }
@@ -395,9 +420,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
       const long long tile = worker + i * n_workers;
       const long long p = tile * TILE_M + row;
       const bool valid = p < a.src.n_points;
+      NERFCA_TL(lane == 0 && (warp & 7) == 0, 1000 + slot * 1000);
       build_x0_row(nt.x0, a.src, p, valid, act, row, ch);
       fence_proxy_async();
       mbar_arrive(bar_act);
+      NERFCA_TL(lane == 0 && (warp & 7) == 0, 1001 + slot * 1000);
       if (!w_seen) {             // biases / b_out below come from the packed block in shared memory
         mbar_wait(bar_w, 0);
         w_seen = true;
@@ -408,8 +435,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
         mbar_wait(bar_acc, ph_acc);
         ph_acc ^= 1;
         tc_fence_after();
+        NERFCA_TL(lane == 0 && (warp & 7) == 0, 1010 + slot * 1000 + l * 10);
         uint32_t va[32], vb[32];
         ld_acc64(t_acc, va, vb);
+        NERFCA_TL(lane == 0 && (warp & 7) == 0, 1011 + slot * 1000 + l * 10);
         if (l + 1 < TC_N_RELU) {   // preload the next layer's bias into the accumulator columns just read
           const float4* bn = reinterpret_cast<const float4*>(s_f + (l + 1) * 128 + ch * 64);
 #pragma unroll
@@ -438,9 +467,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
           *reinterpret_cast<uint4*>(act + (ch * 8 + 4 + j) * CHUNK_BYTES + row * 16) = q1;
         }
         if (l + 1 < TC_N_RELU) tmem_st_wait();
+        NERFCA_TL(lane == 0 && (warp & 7) == 0, 1012 + slot * 1000 + l * 10);
         tc_fence_before();
         fence_proxy_async();
         mbar_arrive(bar_act);
+        NERFCA_TL(lane == 0 && (warp & 7) == 0, 1013 + slot * 1000 + l * 10);
         if (stash_on && (l == 0 || l == 2)) {
           mbar_arrive(bar_sr);
           store_pending = true;
@@ -609,39 +640,43 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
       bulk_g2s(smem_u32(s_w4), nt.pack + nt.w0_bytes + 3 * (size_t)TILE_BYTES, TILE_BYTES, bar_w);
       mbar_wait(bar_w, 0);
       const uint32_t w3 = smem_u32(s_w3), w4 = smem_u32(s_w4), side = smem_u32(s_side), R = smem_u32(s_r), S = smem_u32(s_s);
+      const Desc w3_k = kmajor(w3), w3_mn = mnmajor(w3), w4_k = kmajor(w4), w4_mn = mnmajor(w4), side_mn = mnmajor(side);
+      const Desc R_k = kmajor(R), R_mn = mnmajor(R), S_k = kmajor(S), S_mn = mnmajor(S);
+      constexpr uint32_t KK = KSTEP_KMAJOR, KM = KSTEP_MNMAJOR;
       constexpr uint32_t id_fwd = instr_desc(128, 128, 0, 0), id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1),
                          id_side = instr_desc(128, 16, 1, 1);
       uint32_t ph_ld = 0, ph_e = 0, ph_accfree = 0;
       for (long long i = 0; i < n_my; ++i) {
         const uint32_t h2 = smem_u32(s_bufh + (i & 1) * TILE_BYTES), h3 = smem_u32(s_bufh + ((i & 1) ^ 1) * TILE_BYTES);
+        const Desc h2_k = kmajor(h2), h2_mn = mnmajor(h2), h3_k = kmajor(h3), h3_mn = mnmajor(h3);
         const uint32_t first = (i > 0) ? 1u : 0u;
         // Z3 = H2 W3^T
         mbar_wait(bar_ld, ph_ld); ph_ld ^= 1;
         if (i > 0) { mbar_wait(bar_accfree, ph_accfree); ph_accfree ^= 1; }
         tc_fence_after();
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_ACC, desc_kmajor(h2, kk), desc_kmajor(w3, kk), id_fwd, kk > 0);
+        umma_k<8, KK, KK>(tmem + TOP_ACC, h2_k, w3_k, id_fwd, 0);
         umma_commit(bar_acc);
         // Z4 = H3 W4^T
         mbar_wait(bar_e, ph_e); ph_e ^= 1;
         tc_fence_after();
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_ACC, desc_kmajor(h3, kk), desc_kmajor(w4, kk), id_fwd, kk > 0);
+        umma_k<8, KK, KK>(tmem + TOP_ACC, h3_k, w4_k, id_fwd, 0);
         umma_commit(bar_acc);
         // output-weight grad, dgrad 4, wgrad 4, bias grad 4      (R = dZ4, S = H4)
         mbar_wait(bar_e, ph_e); ph_e ^= 1;
         tc_fence_after();
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_ACCO, desc_mnmajor(S, kk), desc_mnmajor(side, kk), id_side, first | (kk > 0));
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_ACC, desc_kmajor(R, kk), desc_mnmajor(w4, kk), id_dgrad, kk > 0);
+        umma_k<8, KM, KM>(tmem + TOP_ACCO, S_mn, side_mn, id_side, first);
+        umma_k<8, KK, KM>(tmem + TOP_ACC, R_k, w4_mn, id_dgrad, 0);
         umma_commit(bar_acc);
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_WG4, desc_mnmajor(R, kk), desc_mnmajor(h3, kk), id_wgrad, first | (kk > 0));
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_BG4, desc_mnmajor(R, kk), desc_mnmajor(side, kk), id_side, first | (kk > 0));
+        umma_k<8, KM, KM>(tmem + TOP_WG4, R_mn, h3_mn, id_wgrad, first);
+        umma_k<8, KM, KM>(tmem + TOP_BG4, R_mn, side_mn, id_side, first);
         // dgrad 3, wgrad 3, bias grad 3                           (S = dZ3)
         mbar_wait(bar_e, ph_e); ph_e ^= 1;
         tc_fence_after();
         umma_commit(bar_h3dead);   // wgrad 4 done and the epilogue has read H3's ReLU pattern: the loader may reuse the buffer
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_ACC, desc_kmajor(S, kk), desc_mnmajor(w3, kk), id_dgrad, kk > 0);
+        umma_k<8, KK, KM>(tmem + TOP_ACC, S_k, w3_mn, id_dgrad, 0);
         umma_commit(bar_acc);
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_WG3, desc_mnmajor(S, kk), desc_mnmajor(h2, kk), id_wgrad, first | (kk > 0));
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + TOP_BG3, desc_mnmajor(S, kk), desc_mnmajor(side, kk), id_side, first | (kk > 0));
+        umma_k<8, KM, KM>(tmem + TOP_WG3, S_mn, h2_mn, id_wgrad, first);
+        umma_k<8, KM, KM>(tmem + TOP_BG3, S_mn, side_mn, id_side, first);
       }
       umma_commit(bar_done);
     }
@@ -856,7 +891,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
       bulk_g2s(smem_u32(s_w2), nt.pack + nt.w0_bytes + (size_t)TILE_BYTES, TILE_BYTES, bar_w);
       if (has_lat) bulk_g2s(smem_u32(s_w0lat), nt.pack + (size_t)lat_c0 * CHUNK_BYTES, lat_bytes, bar_w);
       mbar_wait(bar_w, 0);
-      const uint32_t w1 = smem_u32(s_w1), w2 = smem_u32(s_w2), side = smem_u32(s_side), x0 = smem_u32(s_x0), w0lat = smem_u32(s_w0lat);
+      const Desc w1_k = kmajor(smem_u32(s_w1)), w1_mn = mnmajor(smem_u32(s_w1)), w2_mn = mnmajor(smem_u32(s_w2)), side_mn = mnmajor(smem_u32(s_side)),
+                 x0_mn = mnmajor(smem_u32(s_x0)), w0lat_mn = mnmajor(smem_u32(s_w0lat));
+      constexpr uint32_t KK = KSTEP_KMAJOR, KM = KSTEP_MNMAJOR;
       constexpr uint32_t id_fwd = instr_desc(128, 128, 0, 0), id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1),
                          id_side = instr_desc(128, 16, 1, 1);
       const uint32_t id_wg0 = instr_desc(128, kpad0, 1, 1), id_lat = instr_desc(128, lat_n > 0 ? lat_n : 16, 0, 1);
@@ -870,34 +907,34 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
         mbar_wait(bar_ld_h0, ph_h0); ph_h0 ^= 1;
         if (i > 0) { mbar_wait(bar_accfree, ph_accfree); ph_accfree ^= 1; }
         tc_fence_after();
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_ACC, desc_kmajor(h0, kk), desc_kmajor(w1, kk), id_fwd, kk > 0);
+        umma_k<8, KK, KK>(tmem + BOT_ACC, kmajor(h0), w1_k, id_fwd, 0);
         umma_commit(bar_acc);
         // dgrad 2, wgrad 2, bias grad 2
         mbar_wait(bar_e, ph_e); ph_e ^= 1;           // H1 written
         mbar_wait(bar_ld_dz, ph_dz); ph_dz ^= 1;
         tc_fence_after();
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_ACC, desc_kmajor(dz2, kk), desc_mnmajor(w2, kk), id_dgrad, kk > 0);
+        umma_k<8, KK, KM>(tmem + BOT_ACC, kmajor(dz2), w2_mn, id_dgrad, 0);
         umma_commit(bar_acc);
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_WG2, desc_mnmajor(dz2, kk), desc_mnmajor(h1, kk), id_wgrad, first | (kk > 0));
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_BG2, desc_mnmajor(dz2, kk), desc_mnmajor(side, kk), id_side, first | (kk > 0));
+        umma_k<8, KM, KM>(tmem + BOT_WG2, mnmajor(dz2), mnmajor(h1), id_wgrad, first);
+        umma_k<8, KM, KM>(tmem + BOT_BG2, mnmajor(dz2), side_mn, id_side, first);
         // dgrad 1, wgrad 1, bias grad 1
         mbar_wait(bar_e, ph_e); ph_e ^= 1;           // dZ1 written, H1's pattern consumed
         tc_fence_after();
         umma_commit(bar_dead0 + 8 * (uint32_t)(k & 3));         // dZ2
         umma_commit(bar_dead0 + 8 * (uint32_t)((k + 2) & 3));   // H1
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_ACC, desc_kmajor(dz1, kk), desc_mnmajor(w1, kk), id_dgrad, kk > 0);
+        umma_k<8, KK, KM>(tmem + BOT_ACC, kmajor(dz1), w1_mn, id_dgrad, 0);
         umma_commit(bar_acc);
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_WG1, desc_mnmajor(dz1, kk), desc_mnmajor(h0, kk), id_wgrad, first | (kk > 0));
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_BG1, desc_mnmajor(dz1, kk), desc_mnmajor(side, kk), id_side, first | (kk > 0));
+        umma_k<8, KM, KM>(tmem + BOT_WG1, mnmajor(dz1), mnmajor(h0), id_wgrad, first);
+        umma_k<8, KM, KM>(tmem + BOT_BG1, mnmajor(dz1), side_mn, id_side, first);
         // wgrad 0 (its constant-1 column is the bias gradient), latent dgrad
         mbar_wait(bar_e, ph_e); ph_e ^= 1;           // dZ0 written, H0's pattern consumed
         mbar_wait(bar_x0, ph_x0); ph_x0 ^= 1;
         tc_fence_after();
         umma_commit(bar_dead0 + 8 * (uint32_t)((k + 1) & 3));   // H0
         umma_commit(bar_dead0 + 8 * (uint32_t)((k + 3) & 3));   // dZ1
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_WG0, desc_mnmajor(dz0, kk), desc_mnmajor(x0, kk), id_wg0, first | (kk > 0));
+        umma_k<8, KM, KM>(tmem + BOT_WG0, mnmajor(dz0), x0_mn, id_wg0, first);
         if (has_lat) {
-          for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + BOT_ACC, desc_kmajor(dz0, kk), desc_mnmajor(w0lat, kk), id_lat, kk > 0);
+          umma_k<8, KK, KM>(tmem + BOT_ACC, kmajor(dz0), w0lat_mn, id_lat, 0);
           umma_commit(bar_acc);
         }
         umma_commit(bar_dead0 + 8 * (uint32_t)((k + 4) & 3));   // dZ0
@@ -1103,9 +1140,25 @@ int tc_fields_forward(const nerfca_field_t* const* f, int n_nets, const nerfca_s
   }
   NERFCA_REQUIRE(smem <= 227 * 1024, NERFCA_E_UNSUPPORTED, "field does not fit the forward kernel's shared memory");
   NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ProfScope prof(NERFCA_K_FIELD_FWD, st);
-  tc_forward_kernel<<<grid_for(n_nets, a.n_tiles), FWD_THREADS, smem, st>>>(a);
-  NERFCA_LAUNCH_OK();
+  static const bool timeline = getenv("NERFCA_TIMELINE") != nullptr;   // developer aid: event timeline of CTA 0 to stderr
+  a.dbg = nullptr;
+  if (timeline) {
+    NERFCA_CUDA_OK(cudaMalloc(&a.dbg, 8008 * sizeof(long long)));
+    NERFCA_CUDA_OK(cudaMemsetAsync(a.dbg, 0, 8008 * sizeof(long long), st));
+  }
+  {
+    ProfScope prof(NERFCA_K_FIELD_FWD, st);
+    tc_forward_kernel<<<grid_for(n_nets, a.n_tiles), FWD_THREADS, smem, st>>>(a);
+    NERFCA_LAUNCH_OK();
+  }
+  if (timeline) {
+    std::vector<long long> h(8008);
+    NERFCA_CUDA_OK(cudaMemcpyAsync(h.data(), a.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    NERFCA_CUDA_OK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i + 1 < h.size(); i += 2)
+      if (h[i] != 0) fprintf(stderr, "TL %lld %lld\n", h[i], h[i + 1]);
+    cudaFree(a.dbg);
+  }
   return NERFCA_OK;
 }
 

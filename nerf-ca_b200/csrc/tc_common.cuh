@@ -156,6 +156,35 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t base, int kk) { return 
 // MN-major view: M/N index = stored column (chunk direction), reduction = stored rows; step kk covers rows [16kk, 16kk+16)
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t base, int kk) { return smem_desc(base + kk * 2 * 128, 128, CHUNK_BYTES); }
 
+// ---- lean MMA issue ---------------------------------------------------------------------------------------------
+// Issuing a tcgen05.mma costs ~50 cycles even when nothing else is in the way (measured, tools/micro/mma_rate.cu), so the
+// issue loop must not rebuild 64-bit descriptors per K step: the descriptor is split into (lo, hi) once per operand and
+// every K step only adds a compile-time constant to the low word (the start-address field, in 16-byte units).
+struct Desc { uint32_t lo, hi; };
+__device__ __forceinline__ Desc desc_split(uint64_t d) { return Desc{(uint32_t)d, (uint32_t)(d >> 32)}; }
+constexpr uint32_t KSTEP_KMAJOR = (2 * CHUNK_BYTES) >> 4;   // 16 reduction elements = 2 chunks
+constexpr uint32_t KSTEP_MNMAJOR = (2 * 128) >> 4;          // 16 reduction rows of 16 B inside a chunk
+__device__ __forceinline__ Desc kmajor(uint32_t base) { return desc_split(smem_desc(base, CHUNK_BYTES, 128)); }
+__device__ __forceinline__ Desc mnmajor(uint32_t base) { return desc_split(smem_desc(base, 128, CHUNK_BYTES)); }
+__device__ __forceinline__ Desc kmajor_rows(uint32_t base, uint32_t chunk_bytes) { return desc_split(smem_desc(base, chunk_bytes, 128)); }
+
+__device__ __forceinline__ void umma_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D (+)= A * B over KSTEPS reduction steps of 16; the first step overwrites D unless acc_first != 0
+template <int KSTEPS, uint32_t A_STEP, uint32_t B_STEP>
+__device__ __forceinline__ void umma_k(uint32_t d_tmem, Desc a, Desc b, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int kk = 0; kk < KSTEPS; ++kk) umma_lh(d_tmem, a.lo + kk * A_STEP, a.hi, b.lo + kk * B_STEP, b.hi, idesc, kk > 0 ? 1u : acc_first);
+}
+
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D fp32, A/B bf16
 __host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
