@@ -104,7 +104,8 @@ __device__ __forceinline__ void load_point(const SampleSrc& s, long long q, floa
     x = __ldg(s.points + 3 * p); y = __ldg(s.points + 3 * p + 1); z = __ldg(s.points + 3 * p + 2);
     return;
   }
-  const int ray = (int)(p / s.n_depth);
+  // 32-bit index math whenever the sample index fits (a 64-bit division costs ~80 instructions)
+  const int ray = (p < 0x7fffffffLL) ? (int)((unsigned)p / (unsigned)s.n_depth) : (int)(p / s.n_depth);
   const int k = (int)(p - (long long)ray * s.n_depth);
   const float t = __ldg(s.depth + k);
   if (s.ray_f64) {
@@ -126,7 +127,7 @@ __device__ __forceinline__ void load_point(const SampleSrc& s, long long q, floa
 __device__ __forceinline__ int load_phase(const SampleSrc& s, long long q) {
   const long long p = q + s.base;
   if (s.phase_point) return __ldg(s.phase_point + p);
-  if (s.phase_ray) return __ldg(s.phase_ray + (int)(p / s.n_depth));
+  if (s.phase_ray) return __ldg(s.phase_ray + ((p < 0x7fffffffLL) ? (int)((unsigned)p / (unsigned)s.n_depth) : (int)(p / s.n_depth)));
   return 0;
 }
 

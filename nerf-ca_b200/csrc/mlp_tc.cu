@@ -39,10 +39,11 @@ constexpr int TC_N_RELU = 5;
 constexpr int STASH_TILES = 2;                   // H0 and H2
 constexpr int FWD_THREADS = 18 * 32;             // 16 epilogue warps + MMA warp + store warp
 constexpr int BWD_THREADS = 11 * 32;             // 8 epilogue warps + MMA warp + load warp + store warp
+constexpr int BOT_THREADS = 15 * 32;             // ... + 4 warps that build the encoded input tile X0 off the critical path
 constexpr int FAST_FREQ = 12;                    // band count the register-resident encoder is specialised for
 
 // ---- packed parameter block of one net (device memory, also the leading part of the forward kernel's shared memory) --
-//   [W0: kpad0 * 256][W1..W4: 4 x 32768][w_out tile: 4096][fp32: bias[5][128], w_out[128], b_out, pad]
+//   [W0: kpad0 * 256][W1..W4: 4 x 32768][fp32: bias[5][128], w_out[128], b_out, pad]
 struct NetDims {
   int in_dim, enc_dim, kpad0;
   uint32_t w0_bytes, w_bytes, wout_off, f32_off, pack_bytes;
@@ -55,8 +56,8 @@ static NetDims net_dims(const nerfca_field_t& f) {
   d.kpad0 = (d.in_dim + 1 + 15) / 16 * 16;
   d.w0_bytes = (uint32_t)d.kpad0 * 256u;
   d.w_bytes = d.w0_bytes + 4u * TILE_BYTES;
-  d.wout_off = d.w_bytes;
-  d.f32_off = d.wout_off + 4096u;
+  d.wout_off = d.w_bytes;   // (no separate output-weight tile: the 128 -> 1 layer runs on the CUDA cores)
+  d.f32_off = d.w_bytes;
   d.pack_bytes = d.f32_off + f32_block_floats() * 4u;
   return d;
 }
@@ -97,16 +98,6 @@ __global__ void pack_params_kernel(PackArgs pa) {
     else if (l == 0 && k == K) v = a.b[0] ? __ldg(a.b[0] + n) : 0.f;   // bias column of layer 0
     const size_t base = (l == 0) ? 0 : (size_t)a.kpad0 * 256 + (size_t)(l - 1) * TILE_BYTES;
     reinterpret_cast<__nv_bfloat16*>(a.out + base)[e] = __float2bfloat16_rn(v);
-  }
-  if (tid < 16 * 128) {   // output-weight tile [16 n x 128 k], chunk stride 256 B: n = 0 -> hi, n = 1 -> lo, rest 0
-    const int chunk = tid / 128, n = (tid / 8) % 16, kk = tid % 8;
-    const int k = chunk * 8 + kk;
-    const float w = __ldg(a.w[TC_N_RELU] + k);
-    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
-    if (n == 0) v = hi;
-    else if (n == 1) v = __float2bfloat16_rn(w - __bfloat162float(hi));
-    reinterpret_cast<__nv_bfloat16*>(a.out + a.wout_off)[tid] = v;
   }
   float* fb = reinterpret_cast<float*>(a.out + a.f32_off);
   const int nb = (int)f32_block_floats();
@@ -162,18 +153,33 @@ __device__ __forceinline__ void put_chunk(uint8_t* tile, int row, int c, const f
       make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
 
-__device__ __forceinline__ void build_x0_row(const X0Desc& xd, const SampleSrc& src, long long p, bool valid, uint8_t* tile, int row,
-                                             int ch) {
-  float x = 0.f, y = 0.f, z = 0.f;
-  int phase = 0;
-  const EncDesc& e = xd.enc;
+// The raw inputs of one tile row: fetched early (the loads stay in flight until first use), consumed by emit_x0_row.
+struct RowIn {
+  float x, y, z;
+  int phase;
+  bool valid;
+};
+__device__ __forceinline__ RowIn fetch_row(const X0Desc& xd, const SampleSrc& src, long long p, bool valid) {
+  RowIn r;
+  r.x = r.y = r.z = 0.f;
+  r.phase = 0;
+  r.valid = valid;
   if (valid) {
-    load_point(src, p, x, y, z);
-    if (e.n_latent > 0) {
-      phase = load_phase(src, p);
-      if (phase < 0 || phase >= e.n_phases) phase = 0;
-    }
+    load_point(src, p, r.x, r.y, r.z);
+    if (xd.enc.n_latent > 0) r.phase = load_phase(src, p);
   }
+  return r;
+}
+
+// band_w / lat_tab: per-band weights [n_freq] (or null) and the latent table [n_phases, n_latent]; either global or a
+// shared-memory copy.
+__device__ __forceinline__ void emit_x0_row(const X0Desc& xd, const RowIn& in, const float* band_w, const float* lat_tab, uint8_t* tile,
+                                            int row, int ch) {
+  const float x = in.x, y = in.y, z = in.z;
+  const bool valid = in.valid;
+  const EncDesc& e = xd.enc;
+  int phase = in.phase;
+  if (phase < 0 || phase >= e.n_phases) phase = 0;
   const float live = valid ? 1.f : 0.f;
   if (xd.fast) {
     constexpr int HB = FAST_FREQ / 2;            // bands per half
@@ -199,7 +205,7 @@ __device__ __forceinline__ void build_x0_row(const X0Desc& xd, const SampleSrc& 
       NERFCA_PUSH(x); NERFCA_PUSH(y); NERFCA_PUSH(z);
 #pragma unroll
       for (int b = 0; b < HB; ++b) {
-        const float w = (e.band_weight ? __ldg(e.band_weight + b) : 1.f) * live;
+        const float w = (band_w ? band_w[b] : 1.f) * live;
 #pragma unroll
         for (int k = 0; k < 3; ++k) NERFCA_PUSH(w * s[k]);
 #pragma unroll
@@ -211,11 +217,11 @@ __device__ __forceinline__ void build_x0_row(const X0Desc& xd, const SampleSrc& 
           s[k] = t;
         }
       }
-      NERFCA_PUSH((e.band_weight ? __ldg(e.band_weight + HB) : 1.f) * live * s[0]);   // feature 39 = sin(2^6 x) closes chunk 4
+      NERFCA_PUSH((band_w ? band_w[HB] : 1.f) * live * s[0]);   // feature 39 = sin(2^6 x) closes chunk 4
     } else {
 #pragma unroll
       for (int b = 0; b < HB; ++b) {
-        const float w = (e.band_weight ? __ldg(e.band_weight + HB + b) : 1.f) * live;
+        const float w = (band_w ? band_w[HB + b] : 1.f) * live;
 #pragma unroll
         for (int k = 0; k < 3; ++k)
           if (b > 0 || k > 0) NERFCA_PUSH(w * s[k]);                                   // feature 39 belongs to ch 0
@@ -232,7 +238,7 @@ __device__ __forceinline__ void build_x0_row(const X0Desc& xd, const SampleSrc& 
 #pragma unroll
       for (int t = 0; t < 96 - (3 + 6 * FAST_FREQ); ++t) {
         float val = 0.f;
-        if (t < e.n_latent) val = live * __ldg(e.latents + (size_t)phase * e.n_latent + t);
+        if (t < e.n_latent) val = live * lat_tab[phase * e.n_latent + t];
         else if (t == e.n_latent) val = live;
         NERFCA_PUSH(val);
       }
@@ -254,6 +260,46 @@ __device__ __forceinline__ void ld_acc64(uint32_t taddr, uint32_t (&a)[32], uint
   tmem_ld32(taddr, a);
   tmem_ld32(taddr + 32, b);
   tmem_ld_wait();
+}
+
+// dZ = acc * 1[h > 0] for this thread's 64 columns: h comes from the bf16 activation tile in shared memory, the result
+// goes to `out` (tile-canonical bf16).
+__device__ __forceinline__ void masked_grad_store(const uint32_t (&va)[32], const uint32_t (&vb)[32], const uint8_t* h_tile, uint8_t* out,
+                                                  int row, int ch) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = ch * 8 + half * 4 + j;
+      const uint4 hv = *reinterpret_cast<const uint4*>(h_tile + c * CHUNK_BYTES + row * 16);
+      const uint32_t* v = half ? vb : va;
+      uint4 o;
+      o.x = mul_bf16x2(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])), relu_mask_bf16x2(hv.x));
+      o.y = mul_bf16x2(pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])), relu_mask_bf16x2(hv.y));
+      o.z = mul_bf16x2(pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])), relu_mask_bf16x2(hv.z));
+      o.w = mul_bf16x2(pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])), relu_mask_bf16x2(hv.w));
+      *reinterpret_cast<uint4*>(out + c * CHUNK_BYTES + row * 16) = o;
+    }
+  }
+}
+// H = relu(acc + bias) for this thread's 64 columns -> bf16 tile
+__device__ __forceinline__ void relu_bias_store(const uint32_t (&va)[32], const uint32_t (&vb)[32], const float* bias, uint8_t* out,
+                                                int row, int ch) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = ch * 8 + half * 4 + j;
+      const uint32_t* v = half ? vb : va;
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + c * 8), b1 = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
+      uint4 o;
+      o.x = pack_relu_bf16x2(__uint_as_float(v[8 * j]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y);
+      o.y = pack_relu_bf16x2(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w);
+      o.z = pack_relu_bf16x2(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y);
+      o.w = pack_relu_bf16x2(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w);
+      *reinterpret_cast<uint4*>(out + c * CHUNK_BYTES + row * 16) = o;
+    }
+  }
 }
 
 static int sm_count() {
@@ -295,9 +341,11 @@ struct FwdArgs {
     }                                                                                     \
   } while (0)
 
-constexpr uint32_t FWD_ACC_COL = 0, FWD_OUT_COL = 256;   // slot s: acc at s * 128, output-layer accumulator at 256 + s * 16
+constexpr uint32_t FWD_ACC_COL = 0;   // slot s: accumulator columns [s * 128, s * 128 + 128)
 
-// smem: [packed block][act slot 0][act slot 1][barriers]
+__device__ __forceinline__ void named_bar_sync(int id, int n_threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory"); }
+
+// smem: [packed block][act slot 0][act slot 1][barriers][band weights 32 f32][latent table 256 f32][output partials 2 x 128 f32]
 __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -310,6 +358,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_act + 2 * TILE_BYTES);
   // barriers: [0] weights, [1,2] act_full, [3,4] acc_full, [5,6] stash_ready, [7,8] stash_free
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 9);
+  float* s_bw = reinterpret_cast<float*>(s_bar + 10);
+  float* s_lt = s_bw + 32;
+  float* s_part = s_lt + 256;
   const float* s_f = reinterpret_cast<const float*>(s_pack + nt.f32_off);
   const uint32_t bar_w = smem_u32(s_bar), bar_act0 = bar_w + 8, bar_acc0 = bar_w + 24, bar_sr0 = bar_w + 40, bar_sf0 = bar_w + 56;
 
@@ -325,7 +376,13 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
       mbar_init_fence();
     }
     __syncwarp();
-    tmem_alloc(smem_u32(s_tmem), 512);
+    tmem_alloc(smem_u32(s_tmem), 256);
+  }
+  {
+    const EncDesc& e = nt.x0.enc;
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) s_bw[i] = (e.band_weight && i < e.n_freq) ? __ldg(e.band_weight + i) : 1.f;
+    const int n_lt = e.n_latent > 0 ? e.n_phases * e.n_latent : 0;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lt[i] = (i < n_lt) ? __ldg(e.latents + i) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -333,6 +390,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
   const uint32_t tmem = *s_tmem;
   const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
   const bool stash_on = nt.stash != nullptr;
+  const bool lt_in_smem = nt.x0.enc.n_phases * nt.x0.enc.n_latent <= 256;
   int tl_n = 0;
 
   if (warp == 16) {
@@ -345,20 +403,18 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
       }
       mbar_wait(bar_w, 0);
       constexpr uint32_t idesc = instr_desc(128, 128, 0, 0);
-      constexpr uint32_t idesc_out = instr_desc(128, 16, 0, 0);
       const int k0steps = nt.x0.kpad0 / 16;
       const uint32_t w_base = smem_u32(s_pack);
       Desc d_w[TC_N_RELU], d_act[2];
       d_w[0] = kmajor(w_base);
       for (int l = 1; l < TC_N_RELU; ++l) d_w[l] = kmajor(w_base + nt.w0_bytes + (uint32_t)(l - 1) * TILE_BYTES);
-      const Desc d_wout = kmajor_rows(smem_u32(s_pack + nt.wout_off), 256);
       d_act[0] = kmajor(smem_u32(s_act));
       d_act[1] = kmajor(smem_u32(s_act + TILE_BYTES));
       uint32_t ph_act[2] = {0, 0};
       for (long long i0 = 0; i0 < n_my; i0 += 2) {
         const int nslots = (n_my - i0 >= 2) ? 2 : 1;
 #pragma unroll
-        for (int l = 0; l <= TC_N_RELU; ++l) {
+        for (int l = 0; l < TC_N_RELU; ++l) {
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             if (s >= nslots) continue;
@@ -371,10 +427,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
               umma_k<5, KSTEP_KMAJOR, KSTEP_KMAJOR>(tmem + FWD_ACC_COL + s * 128, act, d_w[0], idesc, 0);
               if (k0steps > 5)
                 umma_lh(tmem + FWD_ACC_COL + s * 128, act.lo + 5 * KSTEP_KMAJOR, act.hi, d_w[0].lo + 5 * KSTEP_KMAJOR, d_w[0].hi, idesc, 1);
-            } else if (l < TC_N_RELU) {   // accumulator already holds the bias (tcgen05.st by the epilogue)
-              umma_k<8, KSTEP_KMAJOR, KSTEP_KMAJOR>(tmem + FWD_ACC_COL + s * 128, act, d_w[l], idesc, 1);
             } else {
-              umma_k<8, KSTEP_KMAJOR, 32u>(tmem + FWD_OUT_COL + s * 16, act, d_wout, idesc_out, 0);
+              umma_k<8, KSTEP_KMAJOR, KSTEP_KMAJOR>(tmem + FWD_ACC_COL + s * 128, act, d_w[l], idesc, 0);
             }
             umma_commit(bar_acc0 + 8 * s);
             NERFCA_TL(true, 3500 + l * 10 + s);
@@ -410,27 +464,38 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
     const int row = q * 32 + lane;
     uint8_t* act = s_act + slot * TILE_BYTES;
     const uint32_t t_acc = tmem + FWD_ACC_COL + slot * 128 + ch * 64 + ((uint32_t)(q * 32) << 16);
-    const uint32_t t_out = tmem + FWD_OUT_COL + slot * 16 + ((uint32_t)(q * 32) << 16);
     const uint32_t bar_act = bar_act0 + 8 * slot, bar_acc = bar_acc0 + 8 * slot, bar_sr = bar_sr0 + 8 * slot, bar_sf = bar_sf0 + 8 * slot;
+    const float* lat_tab = lt_in_smem ? s_lt : nt.x0.enc.latents;
+    const float* band_w = nt.x0.enc.band_weight ? s_bw : nullptr;
     uint32_t ph_acc = 0, ph_sf = 0;
     bool store_pending = false;
     bool w_seen = false;
     float b_out = 0.f;
+    RowIn rin;
+    {
+      const long long p0 = (worker + (long long)slot * n_workers) * TILE_M + row;
+      rin = fetch_row(nt.x0, a.src, p0, slot < n_my && p0 < a.src.n_points);
+    }
     for (long long i = slot; i < n_my; i += 2) {
       const long long tile = worker + i * n_workers;
       const long long p = tile * TILE_M + row;
       const bool valid = p < a.src.n_points;
       NERFCA_TL(lane == 0 && (warp & 7) == 0, 1000 + slot * 1000);
-      build_x0_row(nt.x0, a.src, p, valid, act, row, ch);
+      emit_x0_row(nt.x0, rin, band_w, lat_tab, act, row, ch);
       fence_proxy_async();
       mbar_arrive(bar_act);
       NERFCA_TL(lane == 0 && (warp & 7) == 0, 1001 + slot * 1000);
-      if (!w_seen) {             // biases / b_out below come from the packed block in shared memory
+      {   // the next tile's ray data is fetched now and used a whole tile later
+        const long long pn = (worker + (i + 2) * n_workers) * TILE_M + row;
+        rin = fetch_row(nt.x0, a.src, pn, i + 2 < n_my && pn < a.src.n_points);
+      }
+      if (!w_seen) {             // biases / output weights below come from the packed block in shared memory
         mbar_wait(bar_w, 0);
         w_seen = true;
         b_out = s_f[TC_N_RELU * 128 + 128];
       }
 
+#pragma unroll 1
       for (int l = 0; l < TC_N_RELU; ++l) {
         mbar_wait(bar_acc, ph_acc);
         ph_acc ^= 1;
@@ -439,106 +504,78 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
         uint32_t va[32], vb[32];
         ld_acc64(t_acc, va, vb);
         NERFCA_TL(lane == 0 && (warp & 7) == 0, 1011 + slot * 1000 + l * 10);
-        if (l + 1 < TC_N_RELU) {   // preload the next layer's bias into the accumulator columns just read
-          const float4* bn = reinterpret_cast<const float4*>(s_f + (l + 1) * 128 + ch * 64);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {   // 8 columns at a time keeps the register peak at the 64 accumulator values + 8
-            const float4 t0 = bn[2 * j], t1 = bn[2 * j + 1];
-            tmem_st8(t_acc + 8 * j, __float_as_uint(t0.x), __float_as_uint(t0.y), __float_as_uint(t0.z), __float_as_uint(t0.w),
-                     __float_as_uint(t1.x), __float_as_uint(t1.y), __float_as_uint(t1.z), __float_as_uint(t1.w));
+        if (l + 1 < TC_N_RELU) {
+          // H_l = relu(Z_l + b_l) -> bf16 A operand of the next layer (layer 0's bias came through the constant-1 column)
+          if (store_pending) {       // the previous contents of this buffer are still being copied to the stash
+            mbar_wait(bar_sf, ph_sf);
+            ph_sf ^= 1;
+            store_pending = false;
           }
-        }
-        if (store_pending) {       // the previous contents of this buffer are still being copied to the stash
-          mbar_wait(bar_sf, ph_sf);
-          ph_sf ^= 1;
-          store_pending = false;
-        }
+          if (l == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 q0 = make_uint4(pack_relu_bf16x2(__uint_as_float(va[8 * j]), __uint_as_float(va[8 * j + 1])),
-                                      pack_relu_bf16x2(__uint_as_float(va[8 * j + 2]), __uint_as_float(va[8 * j + 3])),
-                                      pack_relu_bf16x2(__uint_as_float(va[8 * j + 4]), __uint_as_float(va[8 * j + 5])),
-                                      pack_relu_bf16x2(__uint_as_float(va[8 * j + 6]), __uint_as_float(va[8 * j + 7])));
-          *reinterpret_cast<uint4*>(act + (ch * 8 + j) * CHUNK_BYTES + row * 16) = q0;
-          const uint4 q1 = make_uint4(pack_relu_bf16x2(__uint_as_float(vb[8 * j]), __uint_as_float(vb[8 * j + 1])),
-                                      pack_relu_bf16x2(__uint_as_float(vb[8 * j + 2]), __uint_as_float(vb[8 * j + 3])),
-                                      pack_relu_bf16x2(__uint_as_float(vb[8 * j + 4]), __uint_as_float(vb[8 * j + 5])),
-                                      pack_relu_bf16x2(__uint_as_float(vb[8 * j + 6]), __uint_as_float(vb[8 * j + 7])));
-          *reinterpret_cast<uint4*>(act + (ch * 8 + 4 + j) * CHUNK_BYTES + row * 16) = q1;
-        }
-        if (l + 1 < TC_N_RELU) tmem_st_wait();
-        NERFCA_TL(lane == 0 && (warp & 7) == 0, 1012 + slot * 1000 + l * 10);
-        tc_fence_before();
-        fence_proxy_async();
-        mbar_arrive(bar_act);
-        NERFCA_TL(lane == 0 && (warp & 7) == 0, 1013 + slot * 1000 + l * 10);
-        if (stash_on && (l == 0 || l == 2)) {
-          mbar_arrive(bar_sr);
-          store_pending = true;
+            for (int j = 0; j < 4; ++j) {
+              *reinterpret_cast<uint4*>(act + (ch * 8 + j) * CHUNK_BYTES + row * 16) =
+                  make_uint4(pack_relu_bf16x2(__uint_as_float(va[8 * j]), __uint_as_float(va[8 * j + 1])),
+                             pack_relu_bf16x2(__uint_as_float(va[8 * j + 2]), __uint_as_float(va[8 * j + 3])),
+                             pack_relu_bf16x2(__uint_as_float(va[8 * j + 4]), __uint_as_float(va[8 * j + 5])),
+                             pack_relu_bf16x2(__uint_as_float(va[8 * j + 6]), __uint_as_float(va[8 * j + 7])));
+              *reinterpret_cast<uint4*>(act + (ch * 8 + 4 + j) * CHUNK_BYTES + row * 16) =
+                  make_uint4(pack_relu_bf16x2(__uint_as_float(vb[8 * j]), __uint_as_float(vb[8 * j + 1])),
+                             pack_relu_bf16x2(__uint_as_float(vb[8 * j + 2]), __uint_as_float(vb[8 * j + 3])),
+                             pack_relu_bf16x2(__uint_as_float(vb[8 * j + 4]), __uint_as_float(vb[8 * j + 5])),
+                             pack_relu_bf16x2(__uint_as_float(vb[8 * j + 6]), __uint_as_float(vb[8 * j + 7])));
+            }
+          } else {
+            relu_bias_store(va, vb, s_f + l * 128, act, row, ch);
+          }
+          NERFCA_TL(lane == 0 && (warp & 7) == 0, 1012 + slot * 1000 + l * 10);
+          tc_fence_before();
+          fence_proxy_async();
+          mbar_arrive(bar_act);
+          NERFCA_TL(lane == 0 && (warp & 7) == 0, 1013 + slot * 1000 + l * 10);
+          if (stash_on && (l == 0 || l == 2)) {
+            mbar_arrive(bar_sr);
+            store_pending = true;
+          }
+        } else {
+          // output layer on the CUDA cores: raw = relu(Z4 + b4) . w_out + b_out; the two column halves meet in shared memory
+          const float* b4 = s_f + l * 128 + ch * 64;
+          const float* wo = s_f + TC_N_RELU * 128 + ch * 64;
+          float dot = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = *reinterpret_cast<const float4*>(b4 + 4 * j), ww = *reinterpret_cast<const float4*>(wo + 4 * j);
+            dot = fmaf(fmaxf(__uint_as_float(va[4 * j]) + bb.x, 0.f), ww.x, dot);
+            dot = fmaf(fmaxf(__uint_as_float(va[4 * j + 1]) + bb.y, 0.f), ww.y, dot);
+            dot = fmaf(fmaxf(__uint_as_float(va[4 * j + 2]) + bb.z, 0.f), ww.z, dot);
+            dot = fmaf(fmaxf(__uint_as_float(va[4 * j + 3]) + bb.w, 0.f), ww.w, dot);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = *reinterpret_cast<const float4*>(b4 + 32 + 4 * j), ww = *reinterpret_cast<const float4*>(wo + 32 + 4 * j);
+            dot = fmaf(fmaxf(__uint_as_float(vb[4 * j]) + bb.x, 0.f), ww.x, dot);
+            dot = fmaf(fmaxf(__uint_as_float(vb[4 * j + 1]) + bb.y, 0.f), ww.y, dot);
+            dot = fmaf(fmaxf(__uint_as_float(vb[4 * j + 2]) + bb.z, 0.f), ww.z, dot);
+            dot = fmaf(fmaxf(__uint_as_float(vb[4 * j + 3]) + bb.w, 0.f), ww.w, dot);
+          }
+          tc_fence_before();
+          if (ch == 1) s_part[slot * 128 + row] = dot;
+          named_bar_sync(1 + slot, 256);
+          if (ch == 0 && valid) nt.raw_out[p] = (dot + s_part[slot * 128 + row]) + b_out;
+          named_bar_sync(1 + slot, 256);   // s_part may be overwritten by the next tile only after it was read
         }
       }
-      // output layer: raw = H4 . (w_hi + w_lo) + b_out
-      mbar_wait(bar_acc, ph_acc);
-      ph_acc ^= 1;
-      tc_fence_after();
-      if (ch == 0) {
-        uint32_t o[2];
-        tmem_ld2(t_out, o);
-        tmem_ld_wait();
-        if (valid) nt.raw_out[p] = (__uint_as_float(o[0]) + __uint_as_float(o[1])) + b_out;
-      }
-      tc_fence_before();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) tmem_dealloc(tmem, 512);
+  if (warp == 16) tmem_dealloc(tmem, 256);
 }
 
 // =====================================================================================================================
 // backward, shared pieces
 // =====================================================================================================================
-// dZ = acc * 1[h > 0] for this thread's 64 columns: h comes from the bf16 activation tile in shared memory, the result
-// goes to `out` (tile-canonical bf16).
-__device__ __forceinline__ void masked_grad_store(const uint32_t (&va)[32], const uint32_t (&vb)[32], const uint8_t* h_tile, uint8_t* out,
-                                                  int row, int ch) {
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = ch * 8 + half * 4 + j;
-      const uint4 hv = *reinterpret_cast<const uint4*>(h_tile + c * CHUNK_BYTES + row * 16);
-      const uint32_t* v = half ? vb : va;
-      uint4 o;
-      o.x = mul_bf16x2(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])), relu_mask_bf16x2(hv.x));
-      o.y = mul_bf16x2(pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])), relu_mask_bf16x2(hv.y));
-      o.z = mul_bf16x2(pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])), relu_mask_bf16x2(hv.z));
-      o.w = mul_bf16x2(pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])), relu_mask_bf16x2(hv.w));
-      *reinterpret_cast<uint4*>(out + c * CHUNK_BYTES + row * 16) = o;
-    }
-  }
-}
-// H = relu(acc + bias) for this thread's 64 columns -> bf16 tile
-__device__ __forceinline__ void relu_bias_store(const uint32_t (&va)[32], const uint32_t (&vb)[32], const float* bias, uint8_t* out,
-                                                int row, int ch) {
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = ch * 8 + half * 4 + j;
-      const uint32_t* v = half ? vb : va;
-      const float4 b0 = *reinterpret_cast<const float4*>(bias + c * 8), b1 = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
-      uint4 o;
-      o.x = pack_relu_bf16x2(__uint_as_float(v[8 * j]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y);
-      o.y = pack_relu_bf16x2(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w);
-      o.z = pack_relu_bf16x2(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y);
-      o.w = pack_relu_bf16x2(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w);
-      *reinterpret_cast<uint4*>(out + c * CHUNK_BYTES + row * 16) = o;
-    }
-  }
-}
-
 // vector reduction into global memory (4 consecutive floats, 16-byte aligned)
 __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -825,11 +862,13 @@ constexpr uint32_t BOT_ACC = 0, BOT_WG2 = 128, BOT_WG1 = 256, BOT_WG0 = 384, BOT
 
 // Four 32 KB tile buffers form a ring; every tile makes five allocations in this order
 //   a0 dZ2 (loaded)  a1 H0 (loaded)  a2 H1 (recomputed)  a3 dZ1  a4 dZ0
-// allocation k = 5 * i + j lives in buffer k % 4 and may be filled once allocation k - 4 is dead; "dead" is one
-// tcgen05.commit on dead[k % 4] issued by the MMA thread after the last GEMM reading it (and after the epilogue
-// finished reading its ReLU pattern), so the wait parity is ((k / 4) - 1) & 1.
+// allocation k = 5 * i + j lives in buffer k % 4, i.e. in the buffer of allocation k - 4 = a_{j+1} of tile i - 1 (j < 4)
+// or a0 of the same tile (j = 4), and may be filled once that one is dead.  "Dead" is one tcgen05.commit issued by the MMA
+// thread after the last GEMM reading the buffer (and after the epilogue finished reading its ReLU pattern) on the barrier
+// of the DYING allocation's role, dead[j]: it completes exactly once per tile and has exactly one waiting role, so every
+// waiter consumes every phase in order (a parity wait is only sound under that condition).
 // smem: [W1][W2][ring 4 x 32 KB][X0: 96 * 256][W0 latent chunks 4 KB][side 4 KB][bias1 (128 f32)][latent acc 512 f32][barriers]
-__global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
+__global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int net_id = blockIdx.x % a.n_nets;
@@ -856,8 +895,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
   if (warp == 8) {
     if (lane == 0) {
       mbar_init(bar_w, 1); mbar_init(bar_ld_dz, 1); mbar_init(bar_ld_h0, 1); mbar_init(bar_acc, 1); mbar_init(bar_e, 256);
-      mbar_init(bar_x0, 256); mbar_init(bar_x0free, 1); mbar_init(bar_accfree, 256); mbar_init(bar_done, 1);
-      for (int b = 0; b < 4; ++b) mbar_init(bar_dead0 + 8 * b, 1);
+      mbar_init(bar_x0, 128); mbar_init(bar_x0free, 1); mbar_init(bar_accfree, 256); mbar_init(bar_done, 1);
+      for (int b = 0; b < 5; ++b) mbar_init(bar_dead0 + 8 * b, 1);
       mbar_init_fence();
     }
     __syncwarp();
@@ -878,8 +917,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
   const uint32_t tmem = *s_tmem;
   const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
   auto ring = [&](long long k) -> uint8_t* { return s_ring + (size_t)(k & 3) * TILE_BYTES; };
-  auto wait_free = [&](long long k) {   // buffer of allocation k is reusable
-    if (k >= 4) mbar_wait(bar_dead0 + 8 * (uint32_t)(k & 3), (uint32_t)(((k >> 2) - 1) & 1));
+  // role j of tile i may be filled: j < 4 waits for the death of role j + 1 of tile i - 1, j == 4 for role 0 of tile i
+  auto wait_free = [&](long long i, int j) {
+    if (j == 4) mbar_wait(bar_dead0, (uint32_t)(i & 1));
+    else if (i > 0) mbar_wait(bar_dead0 + 8 * (uint32_t)(j + 1), (uint32_t)((i - 1) & 1));
   };
 
   if (warp == 8) {
@@ -920,8 +961,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
         // dgrad 1, wgrad 1, bias grad 1
         mbar_wait(bar_e, ph_e); ph_e ^= 1;           // dZ1 written, H1's pattern consumed
         tc_fence_after();
-        umma_commit(bar_dead0 + 8 * (uint32_t)(k & 3));         // dZ2
-        umma_commit(bar_dead0 + 8 * (uint32_t)((k + 2) & 3));   // H1
+        umma_commit(bar_dead0 + 8 * 0);   // dZ2
+        umma_commit(bar_dead0 + 8 * 2);   // H1
         umma_k<8, KK, KM>(tmem + BOT_ACC, kmajor(dz1), w1_mn, id_dgrad, 0);
         umma_commit(bar_acc);
         umma_k<8, KM, KM>(tmem + BOT_WG1, mnmajor(dz1), mnmajor(h0), id_wgrad, first);
@@ -930,14 +971,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
         mbar_wait(bar_e, ph_e); ph_e ^= 1;           // dZ0 written, H0's pattern consumed
         mbar_wait(bar_x0, ph_x0); ph_x0 ^= 1;
         tc_fence_after();
-        umma_commit(bar_dead0 + 8 * (uint32_t)((k + 1) & 3));   // H0
-        umma_commit(bar_dead0 + 8 * (uint32_t)((k + 3) & 3));   // dZ1
+        umma_commit(bar_dead0 + 8 * 1);   // H0
+        umma_commit(bar_dead0 + 8 * 3);   // dZ1
         umma_k<8, KM, KM>(tmem + BOT_WG0, mnmajor(dz0), x0_mn, id_wg0, first);
         if (has_lat) {
           umma_k<8, KK, KM>(tmem + BOT_ACC, kmajor(dz0), w0lat_mn, id_lat, 0);
           umma_commit(bar_acc);
         }
-        umma_commit(bar_dead0 + 8 * (uint32_t)((k + 4) & 3));   // dZ0
+        umma_commit(bar_dead0 + 8 * 4);   // dZ0
         umma_commit(bar_x0free);
       }
       umma_commit(bar_done);
@@ -949,10 +990,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
       for (long long i = 0; i < n_my; ++i) {
         const long long tile = worker + i * n_workers;
         const long long k = 5 * i;
-        wait_free(k + 1);
+        wait_free(i, 1);
         mbar_expect_tx(bar_ld_h0, TILE_BYTES);
         bulk_g2s(smem_u32(ring(k + 1)), nt.stash + (size_t)tile * STASH_TILES * TILE_BYTES, TILE_BYTES, bar_ld_h0);
-        wait_free(k);
+        wait_free(i, 0);
         mbar_expect_tx(bar_ld_dz, TILE_BYTES);
         bulk_g2s(smem_u32(ring(k)), nt.handoff + (size_t)tile * TILE_BYTES, TILE_BYTES, bar_ld_dz);
       }
@@ -960,29 +1001,44 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
     __syncwarp();
   } else if (warp == 10) {
     // nothing to store in this pass
+  } else if (warp >= 11) {
+    // ================= 4 X0 warps: thread = tile row; the encoded input is only needed by the last GEMM of a tile, so these
+    // warps run about one tile ahead of the rest of the CTA =================
+    const int row = (warp - 11) * 32 + lane;
+    uint32_t ph_x0free = 0;
+    RowIn rin;
+    {
+      const long long p0 = worker * TILE_M + row;
+      rin = fetch_row(nt.x0, a.src, p0, n_my > 0 && p0 < a.src.n_points);
+    }
+    for (long long i = 0; i < n_my; ++i) {
+      const RowIn cur = rin;
+      const long long pn = (worker + (i + 1) * n_workers) * TILE_M + row;
+      rin = fetch_row(nt.x0, a.src, pn, i + 1 < n_my && pn < a.src.n_points);
+      if (i > 0) { mbar_wait(bar_x0free, ph_x0free); ph_x0free ^= 1; }
+      emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight, nt.x0.enc.latents, s_x0, row, 0);
+      emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight, nt.x0.enc.latents, s_x0, row, 1);
+      fence_proxy_async();
+      mbar_arrive(bar_x0);
+    }
   } else {
     // ================= 8 epilogue warps =================
     const int q = warp & 3, ch = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t t_acc = t_lane + BOT_ACC + ch * 64;
-    uint32_t ph_acc = 0, ph_x0free = 0;
+    uint32_t ph_acc = 0;
     for (long long i = 0; i < n_my; ++i) {
       const long long tile = worker + i * n_workers;
       const long long p = tile * TILE_M + row;
       const bool valid = p < a.src.n_points;
       const long long k = 5 * i;
       uint32_t va[32], vb[32];
-      // ---- X0 (needed last, built first: it only waits for the previous tile's wgrad 0)
-      if (i > 0) { mbar_wait(bar_x0free, ph_x0free); ph_x0free ^= 1; }
-      build_x0_row(nt.x0, a.src, p, valid, s_x0, row, ch);
-      fence_proxy_async();
-      mbar_arrive(bar_x0);
       // ---- H1 = relu(Z1 + b1)
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
       ld_acc64(t_acc, va, vb);
-      wait_free(k + 2);
+      wait_free(i, 2);
       relu_bias_store(va, vb, s_bias1, ring(k + 2), row, ch);
       tc_fence_before();
       fence_proxy_async();
@@ -991,7 +1047,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
       ld_acc64(t_acc, va, vb);
-      wait_free(k + 3);
+      wait_free(i, 3);
       masked_grad_store(va, vb, ring(k + 2), ring(k + 3), row, ch);
       tc_fence_before();
       fence_proxy_async();
@@ -1000,7 +1056,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
       ld_acc64(t_acc, va, vb);
-      wait_free(k + 4);
+      wait_free(i, 4);
       masked_grad_store(va, vb, ring(k + 1), ring(k + 4), row, ch);
       tc_fence_before();
       fence_proxy_async();
@@ -1078,7 +1134,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
 // =====================================================================================================================
 // host side
 // =====================================================================================================================
-static size_t fwd_smem_bytes(const NetDims& d) { return (((size_t)d.pack_bytes + 127) & ~(size_t)127) + 2 * TILE_BYTES + 9 * 8 + 16; }
+static size_t fwd_smem_bytes(const NetDims& d) { return (((size_t)d.pack_bytes + 127) & ~(size_t)127) + 2 * TILE_BYTES + 10 * 8 + (32 + 256 + 256) * 4; }
 constexpr size_t TOP_SMEM = 6 * (size_t)TILE_BYTES + 4096 + 384 * 4 + 16 + 10 * 8 + 16;
 constexpr size_t BOT_SMEM = 6 * (size_t)TILE_BYTES + 96 * 256 + 4096 + 4096 + 128 * 4 + 256 * 4 + 16 * 8 + 16;
 
@@ -1202,7 +1258,7 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
   }
   {
     ProfScope prof(NERFCA_K_FIELD_BWD, st);
-    tc_bwd_bot_kernel<<<grid, BWD_THREADS, BOT_SMEM, st>>>(a);
+    tc_bwd_bot_kernel<<<grid, BOT_THREADS, BOT_SMEM, st>>>(a);
     NERFCA_LAUNCH_OK();
   }
   return NERFCA_OK;
