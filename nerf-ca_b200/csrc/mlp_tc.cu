@@ -23,6 +23,7 @@
 //                       wgrad / bias-grad / w_out-grad accumulate in TMEM; writes dZ2 to the hand-off buffer.
 //   tc_bwd_bot_kernel   layers 2, 1, 0: loads dZ2, H0, recomputes H1 and X0; latent gradients by phase.
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -142,7 +143,9 @@ static int pack_params(const nerfca_field_t* const* f, int n_nets, void* dst, cu
 struct X0Desc {
   EncDesc enc;
   int kpad0;
-  int fast;   // BANDS with n_freq == FAST_FREQ
+  int fast;     // BANDS with n_freq == FAST_FREQ
+  int onehot;   // > 0: columns in_dim + 1 + ph (ph < onehot) carry 1[phase == ph] (bottom backward pass: the layer-0 weight-
+                // gradient GEMM then also yields the per-phase column sums of dZ0, from which the latent gradient follows)
 };
 
 __device__ __forceinline__ void put_bf16(uint8_t* tile, int row, int f, float v) {
@@ -240,6 +243,7 @@ __device__ __forceinline__ void emit_x0_row(const X0Desc& xd, const RowIn& in, c
         float val = 0.f;
         if (t < e.n_latent) val = live * lat_tab[phase * e.n_latent + t];
         else if (t == e.n_latent) val = live;
+        else if (t - e.n_latent - 1 < xd.onehot) val = (t - e.n_latent - 1 == phase) ? live : 0.f;
         NERFCA_PUSH(val);
       }
     }
@@ -250,7 +254,11 @@ __device__ __forceinline__ void emit_x0_row(const X0Desc& xd, const RowIn& in, c
   const int f_lo = ch ? xd.kpad0 / 2 : 0, f_hi = ch ? xd.kpad0 : xd.kpad0 / 2;
   for (int f = f_lo; f < f_hi; ++f) {
     float val = 0.f;
-    if (valid) val = (f < e.in_dim) ? enc_feature(e, f, x, y, z, phase) : (f == e.in_dim ? 1.f : 0.f);
+    if (valid) {
+      if (f < e.in_dim) val = enc_feature(e, f, x, y, z, phase);
+      else if (f == e.in_dim) val = 1.f;
+      else if (f - e.in_dim - 1 < xd.onehot) val = (f - e.in_dim - 1 == phase) ? 1.f : 0.f;
+    }
     put_bf16(tile, row, f, val);
   }
 }
@@ -328,13 +336,14 @@ struct FwdArgs {
   FwdNet net[2];
   int n_nets;
   long long n_tiles;
-  long long* dbg;   // optional event timeline of CTA 0 (NERFCA_TIMELINE=1): dbg[0] = count, then (tag, clock) pairs
+  long long* dbg;   // optional event timeline of one CTA (NERFCA_TIMELINE=fwd, NERFCA_TIMELINE_CTA=n)
+  int dbg_cta;
 };
 // Each logging thread owns a region of 1000 (tag, clock) pairs selected by tag / 1000 (1: slot-0 epilogue, 2: slot-1
 // epilogue, 3: MMA thread) and keeps its own count: no atomics, the stores are fire-and-forget.
 #define NERFCA_TL(cond, tag)                                                              \
   do {                                                                                    \
-    if (a.dbg && blockIdx.x == 0 && (cond) && tl_n < 1000) {                              \
+    if (a.dbg && blockIdx.x == (unsigned)a.dbg_cta && (cond) && tl_n < 1000) {                              \
       long long* r__ = a.dbg + (size_t)((tag) / 1000) * 2000 + 2 * tl_n;                  \
       r__[0] = (tag); r__[1] = clock64();                                                 \
       ++tl_n;                                                                             \
@@ -608,6 +617,7 @@ struct BwdNet {
   float* g_w[NERFCA_MAX_LAYERS];
   float* g_b[NERFCA_MAX_LAYERS];   // may be null
   float* g_lat;
+  const float* w0_f32;       // nn.Linear weight of layer 0, [128, in_dim] fp32
   X0Desc x0;
   uint32_t w0_bytes, f32_off;
   int in_dim, enc_dim, n_latent, n_phases;
@@ -617,6 +627,8 @@ struct BwdArgs {
   BwdNet net[2];
   int n_nets;
   long long n_tiles;
+  long long* dbg;   // optional event timeline of one CTA (NERFCA_TIMELINE=bot, NERFCA_TIMELINE_CTA=n)
+  int dbg_cta;
 };
 
 // =====================================================================================================================
@@ -874,7 +886,8 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
   const int net_id = blockIdx.x % a.n_nets;
   const BwdNet& nt = a.net[net_id];
   const long long worker = blockIdx.x / a.n_nets, n_workers = gridDim.x / a.n_nets;
-  const bool has_lat = nt.n_latent > 0;
+  const bool onehot = nt.n_latent > 0 && nt.x0.onehot > 0;    // latent gradient through the one-hot columns of X0
+  const bool has_lat = nt.n_latent > 0 && !onehot;            // fallback: explicit latent dgrad + scatter by phase
   const int kpad0 = nt.x0.kpad0;
   const int lat_c0 = nt.enc_dim / 8;                                        // first chunk holding latent columns
   const int lat_n = has_lat ? ((nt.enc_dim % 8 + nt.n_latent + 15) / 16) * 16 : 0;   // MMA N covering them
@@ -917,6 +930,7 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
   const uint32_t tmem = *s_tmem;
   const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
   auto ring = [&](long long k) -> uint8_t* { return s_ring + (size_t)(k & 3) * TILE_BYTES; };
+  int tl_n = 0;
   // role j of tile i may be filled: j < 4 waits for the death of role j + 1 of tile i - 1, j == 4 for role 0 of tile i
   auto wait_free = [&](long long i, int j) {
     if (j == 4) mbar_wait(bar_dead0, (uint32_t)(i & 1));
@@ -945,22 +959,30 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
                        dz0 = smem_u32(ring(k + 4));
         const uint32_t first = (i > 0) ? 1u : 0u;
         // Z1 = H0 W1^T
+        NERFCA_TL(true, 3000);
         mbar_wait(bar_ld_h0, ph_h0); ph_h0 ^= 1;
+        NERFCA_TL(true, 3001);
         if (i > 0) { mbar_wait(bar_accfree, ph_accfree); ph_accfree ^= 1; }
         tc_fence_after();
+        NERFCA_TL(true, 3002);
         umma_k<8, KK, KK>(tmem + BOT_ACC, kmajor(h0), w1_k, id_fwd, 0);
         umma_commit(bar_acc);
         // dgrad 2, wgrad 2, bias grad 2
+        NERFCA_TL(true, 3003);
         mbar_wait(bar_e, ph_e); ph_e ^= 1;           // H1 written
+        NERFCA_TL(true, 3010);
         mbar_wait(bar_ld_dz, ph_dz); ph_dz ^= 1;
         tc_fence_after();
+        NERFCA_TL(true, 3011);
         umma_k<8, KK, KM>(tmem + BOT_ACC, kmajor(dz2), w2_mn, id_dgrad, 0);
         umma_commit(bar_acc);
         umma_k<8, KM, KM>(tmem + BOT_WG2, mnmajor(dz2), mnmajor(h1), id_wgrad, first);
         umma_k<8, KM, KM>(tmem + BOT_BG2, mnmajor(dz2), side_mn, id_side, first);
         // dgrad 1, wgrad 1, bias grad 1
+        NERFCA_TL(true, 3012);
         mbar_wait(bar_e, ph_e); ph_e ^= 1;           // dZ1 written, H1's pattern consumed
         tc_fence_after();
+        NERFCA_TL(true, 3020);
         umma_commit(bar_dead0 + 8 * 0);   // dZ2
         umma_commit(bar_dead0 + 8 * 2);   // H1
         umma_k<8, KK, KM>(tmem + BOT_ACC, kmajor(dz1), w1_mn, id_dgrad, 0);
@@ -968,9 +990,12 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
         umma_k<8, KM, KM>(tmem + BOT_WG1, mnmajor(dz1), mnmajor(h0), id_wgrad, first);
         umma_k<8, KM, KM>(tmem + BOT_BG1, mnmajor(dz1), side_mn, id_side, first);
         // wgrad 0 (its constant-1 column is the bias gradient), latent dgrad
+        NERFCA_TL(true, 3021);
         mbar_wait(bar_e, ph_e); ph_e ^= 1;           // dZ0 written, H0's pattern consumed
+        NERFCA_TL(true, 3030);
         mbar_wait(bar_x0, ph_x0); ph_x0 ^= 1;
         tc_fence_after();
+        NERFCA_TL(true, 3031);
         umma_commit(bar_dead0 + 8 * 1);   // H0
         umma_commit(bar_dead0 + 8 * 3);   // dZ1
         umma_k<8, KM, KM>(tmem + BOT_WG0, mnmajor(dz0), x0_mn, id_wg0, first);
@@ -980,6 +1005,7 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
         }
         umma_commit(bar_dead0 + 8 * 4);   // dZ0
         umma_commit(bar_x0free);
+        NERFCA_TL(true, 3032);
       }
       umma_commit(bar_done);
     }
@@ -990,10 +1016,13 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
       for (long long i = 0; i < n_my; ++i) {
         const long long tile = worker + i * n_workers;
         const long long k = 5 * i;
+        NERFCA_TL(true, 2000);
         wait_free(i, 1);
+        NERFCA_TL(true, 2001);
         mbar_expect_tx(bar_ld_h0, TILE_BYTES);
         bulk_g2s(smem_u32(ring(k + 1)), nt.stash + (size_t)tile * STASH_TILES * TILE_BYTES, TILE_BYTES, bar_ld_h0);
         wait_free(i, 0);
+        NERFCA_TL(true, 2002);
         mbar_expect_tx(bar_ld_dz, TILE_BYTES);
         bulk_g2s(smem_u32(ring(k)), nt.handoff + (size_t)tile * TILE_BYTES, TILE_BYTES, bar_ld_dz);
       }
@@ -1035,36 +1064,51 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
       const long long k = 5 * i;
       uint32_t va[32], vb[32];
       // ---- H1 = relu(Z1 + b1)
+      NERFCA_TL(threadIdx.x == 0, 1000);
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
+      NERFCA_TL(threadIdx.x == 0, 1001);
       ld_acc64(t_acc, va, vb);
+      NERFCA_TL(threadIdx.x == 0, 1002);
       wait_free(i, 2);
+      NERFCA_TL(threadIdx.x == 0, 1003);
       relu_bias_store(va, vb, s_bias1, ring(k + 2), row, ch);
+      NERFCA_TL(threadIdx.x == 0, 1004);
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar_e);
+      NERFCA_TL(threadIdx.x == 0, 1005);
       // ---- dZ1 = (dZ2 W2) * 1[H1 > 0]
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
       ld_acc64(t_acc, va, vb);
+      NERFCA_TL(threadIdx.x == 0, 1012);
       wait_free(i, 3);
+      NERFCA_TL(threadIdx.x == 0, 1013);
       masked_grad_store(va, vb, ring(k + 2), ring(k + 3), row, ch);
+      NERFCA_TL(threadIdx.x == 0, 1014);
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar_e);
+      NERFCA_TL(threadIdx.x == 0, 1015);
       // ---- dZ0 = (dZ1 W1) * 1[H0 > 0]
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
       ld_acc64(t_acc, va, vb);
+      NERFCA_TL(threadIdx.x == 0, 1022);
       wait_free(i, 4);
+      NERFCA_TL(threadIdx.x == 0, 1023);
       masked_grad_store(va, vb, ring(k + 1), ring(k + 4), row, ch);
+      NERFCA_TL(threadIdx.x == 0, 1024);
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar_e);
+      NERFCA_TL(threadIdx.x == 0, 1025);
       // ---- latent gradient: columns [enc_dim, enc_dim + T) of dX0 sit at accumulator columns enc_dim - 8 * lat_c0 + t
       if (has_lat) {
         mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
         tc_fence_after();
+        NERFCA_TL(threadIdx.x == 0, 1030);
         if (ch == 0) {
           // a warp's 32 rows are consecutive samples, almost always of one ray (one phase): reduce over the warp
           // first and add once; rows of a warp that straddles two rays fall back to per-lane atomics
@@ -1094,6 +1138,7 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
         tc_fence_before();
       }
       mbar_arrive(bar_accfree);
+      NERFCA_TL(threadIdx.x == 0, 1035);
     }
     if (n_my > 0) {
       mbar_wait(bar_done, 0);
@@ -1109,7 +1154,8 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
         tmem_ld16(t_lane + BOT_BG1, v);
         tmem_ld_wait();
         if (nt.g_b[1]) atomicAdd(nt.g_b[1] + row, __uint_as_float(v[0]));
-      } else if (nt.g_b[0]) {   // bias 0 = the constant-1 column (index in_dim) of wgrad 0
+      }
+      if (ch == 1 && nt.g_b[0]) {   // bias 0 = the constant-1 column (index in_dim) of wgrad 0
         const int c0 = nt.in_dim & ~15;
         uint32_t v[16];
         tmem_ld16(t_lane + BOT_WG0 + c0, v);
@@ -1120,12 +1166,38 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
           if (c0 + e == nt.in_dim) val = __uint_as_float(v[e]);
         atomicAdd(nt.g_b[0] + row, val);
       }
+      if (onehot && nt.g_lat) {
+        // S[n][ph] = sum over the samples of phase ph of dZ0[.][n] sits in columns in_dim + 1 + ph of wgrad 0 (all inside the
+        // last 16-column group); d latents[ph][t] = sum_n S[n][ph] * W0[n][enc_dim + t].  S goes through shared memory (the
+        // ring is idle now) so that one thread per (ph, t) can run the 128-term dot product.
+        float* s_S = reinterpret_cast<float*>(s_ring);
+        const int cg = kpad0 - 16;
+        if (ch == (cg >> 6)) {
+          uint32_t v[16];
+          tmem_ld16(t_lane + BOT_WG0 + cg, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int ph = cg + e - (nt.in_dim + 1);
+            if (ph >= 0 && ph < nt.x0.onehot) s_S[ph * 128 + row] = __uint_as_float(v[e]);
+          }
+        }
+        tc_fence_before();
+        named_bar_sync(1, 256);
+        const int tid = (int)threadIdx.x;
+        if (tid < nt.x0.onehot * nt.n_latent) {
+          const int ph = tid / nt.n_latent, t = tid - ph * nt.n_latent;
+          float g = 0.f;
+          for (int n = 0; n < 128; ++n) g = fmaf(s_S[ph * 128 + n], __ldg(nt.w0_f32 + (size_t)n * nt.in_dim + nt.enc_dim + t), g);
+          atomicAdd(nt.g_lat + tid, g);
+        }
+      }
       tc_fence_before();
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (nt.g_lat)
+  if (nt.g_lat && has_lat)
     for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x)
       if (s_lat[i] != 0.f) atomicAdd(nt.g_lat + i, s_lat[i]);
   if (warp == 8) tmem_dealloc(tmem, 512);
@@ -1154,11 +1226,26 @@ size_t tc_workspace_bytes_n(const nerfca_field_t* const* f, int n_nets, long lon
   return n;
 }
 
+static bool timeline_wanted(const char* which) {
+  const char* e = getenv("NERFCA_TIMELINE");
+  return e && strcmp(e, which) == 0;
+}
+static int timeline_dump(long long* dbg, cudaStream_t st) {
+  std::vector<long long> h(8008);
+  NERFCA_CUDA_OK(cudaMemcpyAsync(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  NERFCA_CUDA_OK(cudaStreamSynchronize(st));
+  for (size_t i = 0; i + 1 < h.size(); i += 2)
+    if (h[i] != 0) fprintf(stderr, "TL %lld %lld\n", h[i], h[i + 1]);
+  cudaFree(dbg);
+  return NERFCA_OK;
+}
+
 static X0Desc make_x0(const nerfca_field_t& f, const NetDims& d) {
   X0Desc x;
   x.enc = make_enc(f);
   x.kpad0 = d.kpad0;
   x.fast = (x.enc.mode == NERFCA_ENC_BANDS && f.n_freq == FAST_FREQ) ? 1 : 0;
+  x.onehot = 0;
   return x;
 }
 
@@ -1196,8 +1283,9 @@ int tc_fields_forward(const nerfca_field_t* const* f, int n_nets, const nerfca_s
   }
   NERFCA_REQUIRE(smem <= 227 * 1024, NERFCA_E_UNSUPPORTED, "field does not fit the forward kernel's shared memory");
   NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  static const bool timeline = getenv("NERFCA_TIMELINE") != nullptr;   // developer aid: event timeline of CTA 0 to stderr
+  const bool timeline = timeline_wanted("fwd");   // developer aid: event timeline of one CTA to stderr
   a.dbg = nullptr;
+  a.dbg_cta = getenv("NERFCA_TIMELINE_CTA") ? atoi(getenv("NERFCA_TIMELINE_CTA")) : 0;
   if (timeline) {
     NERFCA_CUDA_OK(cudaMalloc(&a.dbg, 8008 * sizeof(long long)));
     NERFCA_CUDA_OK(cudaMemsetAsync(a.dbg, 0, 8008 * sizeof(long long), st));
@@ -1208,12 +1296,8 @@ int tc_fields_forward(const nerfca_field_t* const* f, int n_nets, const nerfca_s
     NERFCA_LAUNCH_OK();
   }
   if (timeline) {
-    std::vector<long long> h(8008);
-    NERFCA_CUDA_OK(cudaMemcpyAsync(h.data(), a.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
-    NERFCA_CUDA_OK(cudaStreamSynchronize(st));
-    for (size_t i = 0; i + 1 < h.size(); i += 2)
-      if (h[i] != 0) fprintf(stderr, "TL %lld %lld\n", h[i], h[i + 1]);
-    cudaFree(a.dbg);
+    int rc = timeline_dump(a.dbg, st);
+    if (rc) return rc;
   }
   return NERFCA_OK;
 }
@@ -1240,7 +1324,9 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
     n.d_raw = d_raw[i];
     for (int l = 0; l < NERFCA_MAX_LAYERS; ++l) { n.g_w[l] = gr[i]->weight[l]; n.g_b[l] = gr[i]->bias[l]; }
     n.g_lat = gr[i]->latents;
+    n.w0_f32 = f[i]->weight[0];
     n.x0 = make_x0(*f[i], d);
+    if (f[i]->n_latent > 0 && f[i]->n_phases <= d.kpad0 - d.in_dim - 1) n.x0.onehot = f[i]->n_phases;
     n.w0_bytes = d.w0_bytes; n.f32_off = d.f32_off;
     n.in_dim = d.in_dim; n.enc_dim = d.enc_dim; n.n_latent = f[i]->n_latent; n.n_phases = f[i]->n_phases;
     NERFCA_REQUIRE(f[i]->n_latent == 0 || (d.enc_dim % 8 + f[i]->n_latent + 15) / 16 * 16 + d.enc_dim / 8 * 8 <= d.kpad0,
@@ -1251,16 +1337,24 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
   NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_bwd_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOP_SMEM));
   NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_bwd_bot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BOT_SMEM));
   const unsigned grid = grid_for(n_nets, a.n_tiles);
+  a.dbg = nullptr;
+  a.dbg_cta = getenv("NERFCA_TIMELINE_CTA") ? atoi(getenv("NERFCA_TIMELINE_CTA")) : 0;
   {
     ProfScope prof(NERFCA_K_FIELD_BWD, st);
     tc_bwd_top_kernel<<<grid, BWD_THREADS, TOP_SMEM, st>>>(a);
     NERFCA_LAUNCH_OK();
+  }
+  const bool timeline = timeline_wanted("bot");
+  if (timeline) {
+    NERFCA_CUDA_OK(cudaMalloc(&a.dbg, 8008 * sizeof(long long)));
+    NERFCA_CUDA_OK(cudaMemsetAsync(a.dbg, 0, 8008 * sizeof(long long), st));
   }
   {
     ProfScope prof(NERFCA_K_FIELD_BWD, st);
     tc_bwd_bot_kernel<<<grid, BOT_THREADS, BOT_SMEM, st>>>(a);
     NERFCA_LAUNCH_OK();
   }
+  if (timeline) return timeline_dump(a.dbg, st);
   return NERFCA_OK;
 }
 
