@@ -38,13 +38,13 @@ constexpr int TC_H = 128;
 constexpr uint32_t TILE_BYTES = 32768;           // one [128 x 128] bf16 tile
 constexpr int TC_N_RELU = 5;
 constexpr int STASH_TILES = 2;                   // H0 and H2
-constexpr int FWD_THREADS = 18 * 32;             // 16 epilogue warps + MMA warp + store warp
+constexpr int FWD_THREADS = 20 * 32;             // 16 epilogue / issue warps + 4 X0 producer warps
 constexpr int BWD_THREADS = 11 * 32;             // 8 epilogue warps + MMA warp + load warp + store warp
 constexpr int BOT_THREADS = 15 * 32;             // ... + 4 warps that build the encoded input tile X0 off the critical path
 constexpr int FAST_FREQ = 12;                    // band count the register-resident encoder is specialised for
 
 // ---- packed parameter block of one net (device memory, also the leading part of the forward kernel's shared memory) --
-//   [W0: kpad0 * 256][W1..W4: 4 x 32768][fp32: bias[5][128], w_out[128], b_out, pad]
+//   [W0: kpad0 * 256][W1..W4: 4 x 32768][w_out tile: 4096][fp32: bias[5][128], w_out[128], b_out, pad]
 struct NetDims {
   int in_dim, enc_dim, kpad0;
   uint32_t w0_bytes, w_bytes, wout_off, f32_off, pack_bytes;
@@ -57,8 +57,8 @@ static NetDims net_dims(const nerfca_field_t& f) {
   d.kpad0 = (d.in_dim + 1 + 15) / 16 * 16;
   d.w0_bytes = (uint32_t)d.kpad0 * 256u;
   d.w_bytes = d.w0_bytes + 4u * TILE_BYTES;
-  d.wout_off = d.w_bytes;   // (no separate output-weight tile: the 128 -> 1 layer runs on the CUDA cores)
-  d.f32_off = d.w_bytes;
+  d.wout_off = d.w_bytes;   // [16 x 128] bf16 tile of the 128 -> 1 layer: row 0 = hi part of w_out, row 1 = lo part, rest 0
+  d.f32_off = d.w_bytes + 4096u;
   d.pack_bytes = d.f32_off + f32_block_floats() * 4u;
   return d;
 }
@@ -99,6 +99,13 @@ __global__ void pack_params_kernel(PackArgs pa) {
     else if (l == 0 && k == K) v = a.b[0] ? __ldg(a.b[0] + n) : 0.f;   // bias column of layer 0
     const size_t base = (l == 0) ? 0 : (size_t)a.kpad0 * 256 + (size_t)(l - 1) * TILE_BYTES;
     reinterpret_cast<__nv_bfloat16*>(a.out + base)[e] = __float2bfloat16_rn(v);
+  }
+  if (tid < 16 * 128) {   // output-layer tile, 16 rows per 8-wide K chunk: byte(n, k) = (k / 8) * 256 + n * 16 + (k % 8) * 2
+    const int chunk = tid / (16 * 8), n = (tid / 8) % 16, kk = tid % 8;
+    const float wv = __ldg(a.w[TC_N_RELU] + chunk * 8 + kk);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+    const __nv_bfloat16 v = (n == 0) ? hi : ((n == 1) ? __float2bfloat16_rn(wv - __bfloat162float(hi)) : __float2bfloat16_rn(0.f));
+    reinterpret_cast<__nv_bfloat16*>(a.out + a.wout_off)[tid] = v;
   }
   float* fb = reinterpret_cast<float*>(a.out + a.f32_off);
   const int nb = (int)f32_block_floats();
@@ -148,13 +155,25 @@ struct X0Desc {
                 // gradient GEMM then also yields the per-phase column sums of dZ0, from which the latent gradient follows)
 };
 
-__device__ __forceinline__ void put_bf16(uint8_t* tile, int row, int f, float v) {
-  *reinterpret_cast<__nv_bfloat16*>(tile + (f >> 3) * CHUNK_BYTES + row * 16 + (f & 7) * 2) = __float2bfloat16_rn(v);
+__device__ __forceinline__ uint4 pack_chunk(const float* v) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
-__device__ __forceinline__ void put_chunk(uint8_t* tile, int row, int c, const float* v) {
-  *reinterpret_cast<uint4*>(tile + c * CHUNK_BYTES + row * 16) =
-      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-}
+// Where a finished 8-feature chunk of a tile row goes.
+//   SmemSink: the tile-canonical shared-memory tile (B operand of the layer-0 weight-gradient GEMM, bottom backward pass)
+//   TmemSink: the A operand of the layer-0 forward GEMM in tensor memory: lane = tile row, 32-bit column c holds the
+//             features (2c, 2c+1), so chunk c is columns [4c, 4c+4) of this thread's lane (tcgen05.st, warp-collective)
+struct SmemSink {
+  uint8_t* tile;
+  int row;
+  __device__ __forceinline__ void chunk(int c, const float* v) const { *reinterpret_cast<uint4*>(tile + c * CHUNK_BYTES + row * 16) = pack_chunk(v); }
+};
+struct TmemSink {
+  uint32_t taddr;   // lane quadrant base | first column of the A region
+  __device__ __forceinline__ void chunk(int c, const float* v) const {
+    const uint4 w = pack_chunk(v);
+    tmem_st4(taddr + 4 * c, w.x, w.y, w.z, w.w);
+  }
+};
 
 // The raw inputs of one tile row: fetched early (the loads stay in flight until first use), consumed by emit_x0_row.
 struct RowIn {
@@ -175,9 +194,10 @@ __device__ __forceinline__ RowIn fetch_row(const X0Desc& xd, const SampleSrc& sr
 }
 
 // band_w / lat_tab: per-band weights [n_freq] (or null) and the latent table [n_phases, n_latent]; either global or a
-// shared-memory copy.
-__device__ __forceinline__ void emit_x0_row(const X0Desc& xd, const RowIn& in, const float* band_w, const float* lat_tab, uint8_t* tile,
-                                            int row, int ch) {
+// shared-memory copy.  Every branch below is warp-uniform (ch, the encoding and kpad0 are), which the TMEM sink needs.
+template <class Sink>
+__device__ __forceinline__ void emit_x0_row(const X0Desc& xd, const RowIn& in, const float* band_w, const float* lat_tab, const Sink& sink,
+                                            int ch) {
   const float x = in.x, y = in.y, z = in.z;
   const bool valid = in.valid;
   const EncDesc& e = xd.enc;
@@ -189,9 +209,9 @@ __device__ __forceinline__ void emit_x0_row(const X0Desc& xd, const RowIn& in, c
     constexpr int SPLIT = 40;                    // features [0, 40) belong to ch 0 (5 chunks), the rest to ch 1
     const float scale = ch ? (float)(1 << HB) : 1.f;
     float s[3], c[3];
-    sincosf(x * scale, &s[0], &c[0]);
-    sincosf(y * scale, &s[1], &c[1]);
-    sincosf(z * scale, &s[2], &c[2]);
+    __sincosf(x * scale, &s[0], &c[0]);
+    __sincosf(y * scale, &s[1], &c[1]);
+    __sincosf(z * scale, &s[2], &c[2]);
     // features are produced in index order and leave in 16-byte chunks as soon as 8 of them exist; `cnt` is a
     // compile-time constant at every use once the loops are unrolled, so `buf` stays in registers
     float buf[8];
@@ -202,7 +222,7 @@ __device__ __forceinline__ void emit_x0_row(const X0Desc& xd, const RowIn& in, c
     do {                                                                                    \
       buf[cnt & 7] = (val);                                                                 \
       ++cnt;                                                                                \
-      if ((cnt & 7) == 0 && c_base + (cnt >> 3) - 1 < n_chunks) put_chunk(tile, row, c_base + (cnt >> 3) - 1, buf); \
+      if ((cnt & 7) == 0 && c_base + (cnt >> 3) - 1 < n_chunks) sink.chunk(c_base + (cnt >> 3) - 1, buf); \
     } while (0)
     if (ch == 0) {
       NERFCA_PUSH(x); NERFCA_PUSH(y); NERFCA_PUSH(z);
@@ -250,16 +270,22 @@ __device__ __forceinline__ void emit_x0_row(const X0Desc& xd, const RowIn& in, c
 #undef NERFCA_PUSH
     return;
   }
-  // generic encodings: ch 0 writes features [0, kpad0/2), ch 1 the rest
-  const int f_lo = ch ? xd.kpad0 / 2 : 0, f_hi = ch ? xd.kpad0 : xd.kpad0 / 2;
-  for (int f = f_lo; f < f_hi; ++f) {
-    float val = 0.f;
-    if (valid) {
-      if (f < e.in_dim) val = enc_feature(e, f, x, y, z, phase);
-      else if (f == e.in_dim) val = 1.f;
-      else if (f - e.in_dim - 1 < xd.onehot) val = (f - e.in_dim - 1 == phase) ? 1.f : 0.f;
+  // generic encodings: ch 0 writes chunks [0, kpad0/16), ch 1 the rest
+  const int c_lo = ch ? xd.kpad0 / 16 : 0, c_hi = ch ? xd.kpad0 / 8 : xd.kpad0 / 16;
+  for (int c = c_lo; c < c_hi; ++c) {
+    float buf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int f = c * 8 + j;
+      float val = 0.f;
+      if (valid) {
+        if (f < e.in_dim) val = enc_feature(e, f, x, y, z, phase);
+        else if (f == e.in_dim) val = 1.f;
+        else if (f - e.in_dim - 1 < xd.onehot) val = (f - e.in_dim - 1 == phase) ? 1.f : 0.f;
+      }
+      buf[j] = val;
     }
-    put_bf16(tile, row, f, val);
+    sink.chunk(c, buf);
   }
 }
 
@@ -341,6 +367,7 @@ struct FwdArgs {
 };
 // Each logging thread owns a region of 1000 (tag, clock) pairs selected by tag / 1000 (1: slot-0 epilogue, 2: slot-1
 // epilogue, 3: MMA thread) and keeps its own count: no atomics, the stores are fire-and-forget.
+#ifdef NERFCA_TIMELINE_BUILD   // make EXTRA=-DNERFCA_TIMELINE_BUILD: the logging costs registers and issue slots, so it is compiled out by default
 #define NERFCA_TL(cond, tag)                                                              \
   do {                                                                                    \
     if (a.dbg && blockIdx.x == (unsigned)a.dbg_cta && (cond) && tl_n < 1000) {                              \
@@ -349,12 +376,56 @@ struct FwdArgs {
       ++tl_n;                                                                             \
     }                                                                                     \
   } while (0)
+#else
+#define NERFCA_TL(cond, tag) do { } while (0)
+#endif
 
-constexpr uint32_t FWD_ACC_COL = 0;   // slot s: accumulator columns [s * 128, s * 128 + 128)
+// TMEM map of the forward kernel (512 columns): two tile slots s = 0, 1
+//   ACC  [128 s, 128 s + 128)       fp32 accumulator of the layer in flight
+//   A    [256 + 64 s, .. + 64)      bf16 activations H_l = A operand of layer l + 1
+//   X0   [384 + 48 s, .. + 48)      bf16 encoded input = A operand of layer 0, written one tile ahead by the producer warps
+//   OUT  [480 + 16 s, .. + 16)      accumulator of the 128 -> 1 layer (columns 0 / 1: hi / lo part of w_out)
+constexpr uint32_t FWD_ACC = 0, FWD_A = 256, FWD_X0 = 384, FWD_OUT = 480;
+constexpr int FWD_X0_WARP0 = 16;   // warps 0-15: the two slots' epilogue warps, 16-19: X0 producers
+constexpr uint32_t WOUT_KSTEP = (2 * 256) >> 4;
 
 __device__ __forceinline__ void named_bar_sync(int id, int n_threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory"); }
 
-// smem: [packed block][act slot 0][act slot 1][barriers][band weights 32 f32][latent table 256 f32][output partials 2 x 128 f32]
+// relu(acc [+ bias]) of 32 accumulator columns -> 16 packed bf16x2 words (word i = columns 2i, 2i+1)
+template <bool BIAS>
+__device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], const float4 (&b)[8], uint32_t (&w)[16]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float2 p0 = make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]));
+    float2 p1 = make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    if (BIAS) {
+      p0 = add_f32x2(p0, make_float2(b[j].x, b[j].y));
+      p1 = add_f32x2(p1, make_float2(b[j].z, b[j].w));
+    }
+    w[2 * j] = pack_relu_bf16x2(p0.x, p0.y);
+    w[2 * j + 1] = pack_relu_bf16x2(p1.x, p1.y);
+  }
+}
+
+// one arrival per warp: every lane's preceding tcgen05 work is complete and fenced, the warp converges, lane 0 arrives
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+// The forward keeps the whole activation chain of a tile in tensor memory: the epilogue threads read the fp32 accumulator
+// (tcgen05.ld), apply bias + ReLU, and write the bf16 result back to TMEM (tcgen05.st) where the next layer's MMA takes it as
+// its A operand (TS form).  Shared memory only carries the weights (B operands: 32 KB read per tile and layer instead of 64 KB
+// read + 32 KB written), and H0 / H2 go to the HBM stash straight from registers.
+//   * Two tiles (slots) are in flight per CTA, each served by 8 epilogue warps (TMEM lane quadrant x column half).  A slot is
+//     self-contained: when its warps have written H_l they meet at a named barrier and one elected lane of the slot's first
+//     warp issues layer l + 1 right there -- no hand-off to a separate MMA warp, one mbarrier round trip less per layer.
+//   * The encoded input X0 of a tile is produced by four dedicated warps (one thread per sample: ray point in fp64, sines by
+//     MUFU + double-angle steps) into its own TMEM region while the slot's previous tile is still in the layer chain.
+//   * The 128 -> 1 output layer is a sixth MMA (N = 16) against a (hi, lo) bf16 split of w_out into its own accumulator, so
+//     layer 0 of the slot's next tile is issued right behind it.
+// smem: [packed block][barriers][band weights 32 f32][latent table 256 f32]
 __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -363,29 +434,27 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
   const long long worker = blockIdx.x / a.n_nets, n_workers = gridDim.x / a.n_nets;
   const uint32_t pack_pad = (nt.pack_bytes + 127u) & ~127u;
   uint8_t* s_pack = smem;
-  uint8_t* s_act = smem + pack_pad;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_act + 2 * TILE_BYTES);
-  // barriers: [0] weights, [1,2] act_full, [3,4] acc_full, [5,6] stash_ready, [7,8] stash_free
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + pack_pad);
+  // barriers (slot s): [0] weights, [1+s] acc_full, [3+s] out_full, [5+s] x0_full, [7+s] x0_free
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 9);
   float* s_bw = reinterpret_cast<float*>(s_bar + 10);
   float* s_lt = s_bw + 32;
-  float* s_part = s_lt + 256;
   const float* s_f = reinterpret_cast<const float*>(s_pack + nt.f32_off);
-  const uint32_t bar_w = smem_u32(s_bar), bar_act0 = bar_w + 8, bar_acc0 = bar_w + 24, bar_sr0 = bar_w + 40, bar_sf0 = bar_w + 56;
+  const uint32_t bar_w = smem_u32(s_bar), bar_acc0 = bar_w + 8, bar_out0 = bar_w + 24, bar_x0full0 = bar_w + 40, bar_x0free0 = bar_w + 56;
 
-  if (warp == 16) {
+  if (warp == FWD_X0_WARP0) {
     if (lane == 0) {
       mbar_init(bar_w, 1);
       for (int s = 0; s < 2; ++s) {
-        mbar_init(bar_act0 + 8 * s, 256);
         mbar_init(bar_acc0 + 8 * s, 1);
-        mbar_init(bar_sr0 + 8 * s, 256);
-        mbar_init(bar_sf0 + 8 * s, 1);
+        mbar_init(bar_out0 + 8 * s, 1);
+        mbar_init(bar_x0full0 + 8 * s, 4);     // one arrival per producer warp
+        mbar_init(bar_x0free0 + 8 * s, 1);
       }
       mbar_init_fence();
     }
     __syncwarp();
-    tmem_alloc(smem_u32(s_tmem), 256);
+    tmem_alloc(smem_u32(s_tmem), 512);
   }
   {
     const EncDesc& e = nt.x0.enc;
@@ -400,186 +469,164 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
   const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
   const bool stash_on = nt.stash != nullptr;
   const bool lt_in_smem = nt.x0.enc.n_phases * nt.x0.enc.n_latent <= 256;
-  int tl_n = 0;
+  [[maybe_unused]] int tl_n = 0;
 
-  if (warp == 16) {
-    // ================= MMA warp =================
-    if (lane == 0) {
+  if (warp >= FWD_X0_WARP0) {
+    // ================= 4 producer warps: thread = tile row, tiles alternate between the slots =================
+    reg_dealloc<64>();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    if (warp == FWD_X0_WARP0 && lane == 0) {   // the packed parameter block -> shared memory
       mbar_expect_tx(bar_w, nt.pack_bytes);
       for (uint32_t off = 0; off < nt.pack_bytes; off += 32768u) {
         const uint32_t n = (nt.pack_bytes - off < 32768u) ? nt.pack_bytes - off : 32768u;
         bulk_g2s(smem_u32(s_pack + off), nt.pack + off, n, bar_w);
       }
-      mbar_wait(bar_w, 0);
-      constexpr uint32_t idesc = instr_desc(128, 128, 0, 0);
-      const int k0steps = nt.x0.kpad0 / 16;
-      const uint32_t w_base = smem_u32(s_pack);
-      Desc d_w[TC_N_RELU], d_act[2];
-      d_w[0] = kmajor(w_base);
-      for (int l = 1; l < TC_N_RELU; ++l) d_w[l] = kmajor(w_base + nt.w0_bytes + (uint32_t)(l - 1) * TILE_BYTES);
-      d_act[0] = kmajor(smem_u32(s_act));
-      d_act[1] = kmajor(smem_u32(s_act + TILE_BYTES));
-      uint32_t ph_act[2] = {0, 0};
-      for (long long i0 = 0; i0 < n_my; i0 += 2) {
-        const int nslots = (n_my - i0 >= 2) ? 2 : 1;
-#pragma unroll
-        for (int l = 0; l < TC_N_RELU; ++l) {
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            if (s >= nslots) continue;
-            mbar_wait(bar_act0 + 8 * s, ph_act[s]);
-            ph_act[s] ^= 1;
-            tc_fence_after();
-            NERFCA_TL(true, 3000 + l * 10 + s);
-            const Desc act = d_act[s];
-            if (l == 0) {
-              umma_k<5, KSTEP_KMAJOR, KSTEP_KMAJOR>(tmem + FWD_ACC_COL + s * 128, act, d_w[0], idesc, 0);
-              if (k0steps > 5)
-                umma_lh(tmem + FWD_ACC_COL + s * 128, act.lo + 5 * KSTEP_KMAJOR, act.hi, d_w[0].lo + 5 * KSTEP_KMAJOR, d_w[0].hi, idesc, 1);
-            } else {
-              umma_k<8, KSTEP_KMAJOR, KSTEP_KMAJOR>(tmem + FWD_ACC_COL + s * 128, act, d_w[l], idesc, 0);
-            }
-            umma_commit(bar_acc0 + 8 * s);
-            NERFCA_TL(true, 3500 + l * 10 + s);
-          }
-        }
-      }
     }
     __syncwarp();
-  } else if (warp == 17) {
-    // ================= stash store warp: H0 and H2 of every tile, straight from the activation buffer =================
-    if (stash_on && lane == 0) {
-      uint32_t ph[2] = {0, 0};
-      for (long long i0 = 0; i0 < n_my; i0 += 2) {
-        const int nslots = (n_my - i0 >= 2) ? 2 : 1;
-        for (int j = 0; j < STASH_TILES; ++j) {
-          for (int s = 0; s < nslots; ++s) {
-            const long long tile = worker + (i0 + s) * n_workers;
-            mbar_wait(bar_sr0 + 8 * s, ph[s]);
-            ph[s] ^= 1;
-            bulk_s2g(nt.stash + ((size_t)tile * STASH_TILES + j) * TILE_BYTES, smem_u32(s_act + s * TILE_BYTES), TILE_BYTES);
-            bulk_commit();
-            bulk_wait_read_all();
-            mbar_arrive(bar_sf0 + 8 * s);
-          }
-        }
-      }
-      bulk_wait_all();
-    }
-    __syncwarp();
-  } else {
-    // ================= 16 epilogue warps: slot = warp / 8, column half ch, TMEM lane quadrant q =================
-    const int slot = warp >> 3, ch = (warp >> 2) & 1, q = warp & 3;
-    const int row = q * 32 + lane;
-    uint8_t* act = s_act + slot * TILE_BYTES;
-    const uint32_t t_acc = tmem + FWD_ACC_COL + slot * 128 + ch * 64 + ((uint32_t)(q * 32) << 16);
-    const uint32_t bar_act = bar_act0 + 8 * slot, bar_acc = bar_acc0 + 8 * slot, bar_sr = bar_sr0 + 8 * slot, bar_sf = bar_sf0 + 8 * slot;
     const float* lat_tab = lt_in_smem ? s_lt : nt.x0.enc.latents;
     const float* band_w = nt.x0.enc.band_weight ? s_bw : nullptr;
-    uint32_t ph_acc = 0, ph_sf = 0;
-    bool store_pending = false;
-    bool w_seen = false;
-    float b_out = 0.f;
+    uint32_t ph_free[2] = {0, 0};
     RowIn rin;
     {
-      const long long p0 = (worker + (long long)slot * n_workers) * TILE_M + row;
-      rin = fetch_row(nt.x0, a.src, p0, slot < n_my && p0 < a.src.n_points);
+      const long long p0 = worker * TILE_M + row;
+      rin = fetch_row(nt.x0, a.src, p0, n_my > 0 && p0 < a.src.n_points);
     }
+    for (long long i = 0; i < n_my; ++i) {
+      const int s = (int)(i & 1);
+      const RowIn cur = rin;
+      const long long pn = (worker + (i + 1) * n_workers) * TILE_M + row;
+      rin = fetch_row(nt.x0, a.src, pn, i + 1 < n_my && pn < a.src.n_points);
+      if (i >= 2) {              // layer 0 of the slot's previous tile has consumed the region
+        mbar_wait(bar_x0free0 + 8 * s, ph_free[s]);
+        ph_free[s] ^= 1;
+        tc_fence_after();
+      }
+      const TmemSink sink{tmem + FWD_X0 + s * 48 + ((uint32_t)(q * 32) << 16)};
+      emit_x0_row(nt.x0, cur, band_w, lat_tab, sink, 0);
+      emit_x0_row(nt.x0, cur, band_w, lat_tab, sink, 1);
+      tmem_st_wait();
+      warp_arrive(bar_x0full0 + 8 * s, lane);
+    }
+  } else {
+    // ================= 16 epilogue warps: slot = warp / 8, column half ch, TMEM lane quadrant q =================
+    reg_alloc<104>();                // 16 x 104 + 4 x 64 = 20 x 96: the registers the producers hand back (the CTA pool starts empty)
+    const int slot = warp >> 3, ch = (warp >> 2) & 1, q = warp & 3;
+    const bool issuer_warp = (warp & 7) == 0;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_acc = t_lane + FWD_ACC + slot * 128 + ch * 64;    // this thread's 64 accumulator columns
+    const uint32_t t_a = t_lane + FWD_A + slot * 64 + ch * 32;         // ... and the 32 words they become
+    const uint32_t bar_acc = bar_acc0 + 8 * slot, bar_out = bar_out0 + 8 * slot, bar_x0full = bar_x0full0 + 8 * slot,
+                   bar_x0free = bar_x0free0 + 8 * slot;
+    // issue side (used by the elected lane of the slot's first warp)
+    constexpr uint32_t idesc = instr_desc(128, 128, 0, 0), idesc_out = instr_desc(128, 16, 0, 0);
+    const int k0steps = nt.x0.kpad0 / 16;
+    const uint32_t w_base = smem_u32(s_pack);
+    const uint32_t td_acc = tmem + FWD_ACC + slot * 128, td_a = tmem + FWD_A + slot * 64, td_x0 = tmem + FWD_X0 + slot * 48,
+                   td_out = tmem + FWD_OUT + slot * 16;
+    [[maybe_unused]] const int tl_base = slot ? 500 : 3000;
+    uint32_t ph_acc = 0, ph_out = 0, ph_x0 = 0;
+    mbar_wait(bar_w, 0);             // weights / biases are in shared memory
+    const float b_out = s_f[TC_N_RELU * 128 + 128];
+    // per-thread constants of the layer loop, pinned in registers (the compiler otherwise re-derives them from %tid and the
+    // shared-window base, ~25-cycle S2R reads on the critical path of every layer)
+    uint32_t k_acc = t_acc, k_a = t_a, k_bias = smem_u32(s_f) + (uint32_t)(ch * 64) * 4u, k_bar_acc = bar_acc;
+    uint32_t k_stash_off = (uint32_t)(ch * 8) * CHUNK_BYTES + (uint32_t)row * 16u;
+    pin(k_acc); pin(k_a); pin(k_bias); pin(k_bar_acc); pin(k_stash_off);
+
+    auto issue_layer0 = [&]() {      // whole warp; the X0 region of the slot's next tile feeds layer 0
+      if (elect_one()) {
+        mbar_wait(bar_x0full, ph_x0);
+        tc_fence_after();
+        NERFCA_TL(true, tl_base);
+        const Desc d_w0 = kmajor(w_base);
+        umma_ts_k<5, KSTEP_KMAJOR>(td_acc, td_x0, d_w0, idesc, 0);
+        if (k0steps > 5) umma_ts(td_acc, td_x0 + 5 * KSTEP_TMEM, d_w0.lo + 5 * KSTEP_KMAJOR, d_w0.hi, idesc, 1);
+        umma_commit(bar_x0free);
+        umma_commit(bar_acc);
+      }
+      ph_x0 ^= 1;
+      __syncwarp();
+    };
+    if (issuer_warp && slot < n_my) issue_layer0();
+
     for (long long i = slot; i < n_my; i += 2) {
       const long long tile = worker + i * n_workers;
       const long long p = tile * TILE_M + row;
       const bool valid = p < a.src.n_points;
-      NERFCA_TL(lane == 0 && (warp & 7) == 0, 1000 + slot * 1000);
-      emit_x0_row(nt.x0, rin, band_w, lat_tab, act, row, ch);
-      fence_proxy_async();
-      mbar_arrive(bar_act);
-      NERFCA_TL(lane == 0 && (warp & 7) == 0, 1001 + slot * 1000);
-      {   // the next tile's ray data is fetched now and used a whole tile later
-        const long long pn = (worker + (i + 2) * n_workers) * TILE_M + row;
-        rin = fetch_row(nt.x0, a.src, pn, i + 2 < n_my && pn < a.src.n_points);
-      }
-      if (!w_seen) {             // biases / output weights below come from the packed block in shared memory
-        mbar_wait(bar_w, 0);
-        w_seen = true;
-        b_out = s_f[TC_N_RELU * 128 + 128];
-      }
-
 #pragma unroll 1
       for (int l = 0; l < TC_N_RELU; ++l) {
-        mbar_wait(bar_acc, ph_acc);
+        // H_l = relu(Z_l + b_l) -> bf16 A operand of the next layer (layer 0's bias came through the constant-1 column), in two
+        // groups of 32 columns; the bias of the first group is fetched before the accumulator wait
+        const uint32_t bias = k_bias + (uint32_t)l * 512u;
+        const bool stash_l = stash_on && (l == 0 || l == 2);
+        // tile-canonical stash bytes: chunk c of the row at c * 2048 + row * 16 (a warp writes 512 contiguous bytes per chunk)
+        uint8_t* dst = nt.stash + ((size_t)tile * STASH_TILES + (l >> 1)) * TILE_BYTES + k_stash_off;
+        mbar_wait(k_bar_acc, ph_acc);
         ph_acc ^= 1;
         tc_fence_after();
-        NERFCA_TL(lane == 0 && (warp & 7) == 0, 1010 + slot * 1000 + l * 10);
-        uint32_t va[32], vb[32];
-        ld_acc64(t_acc, va, vb);
-        NERFCA_TL(lane == 0 && (warp & 7) == 0, 1011 + slot * 1000 + l * 10);
-        if (l + 1 < TC_N_RELU) {
-          // H_l = relu(Z_l + b_l) -> bf16 A operand of the next layer (layer 0's bias came through the constant-1 column)
-          if (store_pending) {       // the previous contents of this buffer are still being copied to the stash
-            mbar_wait(bar_sf, ph_sf);
-            ph_sf ^= 1;
-            store_pending = false;
-          }
-          if (l == 0) {
+        NERFCA_TL(lane == 0 && (warp & 7) == 1, 1010 + slot * 1000 + l * 10);
+        // both halves are requested at once: a tcgen05.ld round trip takes ~290 cycles while the other slot's MMAs run
+        uint32_t v0[32], v1[32];
+        tmem_ld32(k_acc, v0);
+        tmem_ld32(k_acc + 32, v1);
+        tmem_ld_wait();
+        NERFCA_TL(lane == 0 && (warp & 7) == 1, 1012 + slot * 1000 + l * 10);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              *reinterpret_cast<uint4*>(act + (ch * 8 + j) * CHUNK_BYTES + row * 16) =
-                  make_uint4(pack_relu_bf16x2(__uint_as_float(va[8 * j]), __uint_as_float(va[8 * j + 1])),
-                             pack_relu_bf16x2(__uint_as_float(va[8 * j + 2]), __uint_as_float(va[8 * j + 3])),
-                             pack_relu_bf16x2(__uint_as_float(va[8 * j + 4]), __uint_as_float(va[8 * j + 5])),
-                             pack_relu_bf16x2(__uint_as_float(va[8 * j + 6]), __uint_as_float(va[8 * j + 7])));
-              *reinterpret_cast<uint4*>(act + (ch * 8 + 4 + j) * CHUNK_BYTES + row * 16) =
-                  make_uint4(pack_relu_bf16x2(__uint_as_float(vb[8 * j]), __uint_as_float(vb[8 * j + 1])),
-                             pack_relu_bf16x2(__uint_as_float(vb[8 * j + 2]), __uint_as_float(vb[8 * j + 3])),
-                             pack_relu_bf16x2(__uint_as_float(vb[8 * j + 4]), __uint_as_float(vb[8 * j + 5])),
-                             pack_relu_bf16x2(__uint_as_float(vb[8 * j + 6]), __uint_as_float(vb[8 * j + 7])));
+        for (int g = 0; g < 2; ++g) {
+          uint32_t w[16];
+          float4 b[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b[j] = lds_f4(bias + (uint32_t)(32 * g + 4 * j) * 4u);
+          if (l == 0) relu_pack32<false>(g ? v1 : v0, b, w);
+          else relu_pack32<true>(g ? v1 : v0, b, w);
+          tmem_st16(k_a + 16 * g, w);
+          if (stash_l) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              __stcs(reinterpret_cast<uint4*>(dst + (4 * g + c) * CHUNK_BYTES), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+          }
+        }
+        tmem_st_wait();
+        NERFCA_TL(lane == 0 && (warp & 7) == 1, 1011 + slot * 1000 + l * 10);
+        tc_fence_before();
+        named_bar_sync(1 + slot, 256);          // the slot's H_l is complete and its accumulator has been read
+        if (issuer_warp) {
+          tc_fence_after();
+          if (elect_one()) {
+            NERFCA_TL(true, tl_base + 10 + l * 10);
+            if (l + 1 < TC_N_RELU) {
+              umma_ts_k<8, KSTEP_KMAJOR>(td_acc, td_a, kmajor(w_base + nt.w0_bytes + (uint32_t)l * TILE_BYTES), idesc, 0);
+              umma_commit(bar_acc);
+            } else {
+              umma_ts_k<8, WOUT_KSTEP>(td_out, td_a, kmajor_rows(w_base + nt.wout_off, 256), idesc_out, 0);
+              umma_commit(bar_out);
             }
-          } else {
-            relu_bias_store(va, vb, s_f + l * 128, act, row, ch);
+            NERFCA_TL(true, tl_base + 11 + l * 10);
           }
-          NERFCA_TL(lane == 0 && (warp & 7) == 0, 1012 + slot * 1000 + l * 10);
-          tc_fence_before();
-          fence_proxy_async();
-          mbar_arrive(bar_act);
-          NERFCA_TL(lane == 0 && (warp & 7) == 0, 1013 + slot * 1000 + l * 10);
-          if (stash_on && (l == 0 || l == 2)) {
-            mbar_arrive(bar_sr);
-            store_pending = true;
-          }
-        } else {
-          // output layer on the CUDA cores: raw = relu(Z4 + b4) . w_out + b_out; the two column halves meet in shared memory
-          const float* b4 = s_f + l * 128 + ch * 64;
-          const float* wo = s_f + TC_N_RELU * 128 + ch * 64;
-          float dot = 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = *reinterpret_cast<const float4*>(b4 + 4 * j), ww = *reinterpret_cast<const float4*>(wo + 4 * j);
-            dot = fmaf(fmaxf(__uint_as_float(va[4 * j]) + bb.x, 0.f), ww.x, dot);
-            dot = fmaf(fmaxf(__uint_as_float(va[4 * j + 1]) + bb.y, 0.f), ww.y, dot);
-            dot = fmaf(fmaxf(__uint_as_float(va[4 * j + 2]) + bb.z, 0.f), ww.z, dot);
-            dot = fmaf(fmaxf(__uint_as_float(va[4 * j + 3]) + bb.w, 0.f), ww.w, dot);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = *reinterpret_cast<const float4*>(b4 + 32 + 4 * j), ww = *reinterpret_cast<const float4*>(wo + 32 + 4 * j);
-            dot = fmaf(fmaxf(__uint_as_float(vb[4 * j]) + bb.x, 0.f), ww.x, dot);
-            dot = fmaf(fmaxf(__uint_as_float(vb[4 * j + 1]) + bb.y, 0.f), ww.y, dot);
-            dot = fmaf(fmaxf(__uint_as_float(vb[4 * j + 2]) + bb.z, 0.f), ww.z, dot);
-            dot = fmaf(fmaxf(__uint_as_float(vb[4 * j + 3]) + bb.w, 0.f), ww.w, dot);
-          }
-          tc_fence_before();
-          if (ch == 1) s_part[slot * 128 + row] = dot;
-          named_bar_sync(1 + slot, 256);
-          if (ch == 0 && valid) nt.raw_out[p] = (dot + s_part[slot * 128 + row]) + b_out;
-          named_bar_sync(1 + slot, 256);   // s_part may be overwritten by the next tile only after it was read
+          __syncwarp();
+          if (l + 1 == TC_N_RELU && i + 2 < n_my) issue_layer0();   // the accumulator is free: start the slot's next tile
         }
       }
+      // output layer: raw = H4 . (w_hi + w_lo) + b_out sits in columns 0 (hi part) and 1 (lo part) of the OUT accumulator
+      mbar_wait(bar_out, ph_out);
+      ph_out ^= 1;
+      tc_fence_after();
+      if (ch == 0) {
+        uint32_t v[2];
+        tmem_ld2(t_lane + FWD_OUT + slot * 16, v);
+        tmem_ld_wait();
+        if (valid) nt.raw_out[p] = (__uint_as_float(v[0]) + __uint_as_float(v[1])) + b_out;
+      }
+      NERFCA_TL(lane == 0 && (warp & 7) == 1, 1060 + slot * 1000);
+      // (the next output MMA of this slot is issued after five more named barriers of the slot: OUT has long been read)
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) tmem_dealloc(tmem, 256);
+  if (warp == FWD_X0_WARP0) tmem_dealloc(tmem, 512);
 }
 
 // =====================================================================================================================
@@ -930,7 +977,7 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
   const uint32_t tmem = *s_tmem;
   const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
   auto ring = [&](long long k) -> uint8_t* { return s_ring + (size_t)(k & 3) * TILE_BYTES; };
-  int tl_n = 0;
+  [[maybe_unused]] int tl_n = 0;
   // role j of tile i may be filled: j < 4 waits for the death of role j + 1 of tile i - 1, j == 4 for role 0 of tile i
   auto wait_free = [&](long long i, int j) {
     if (j == 4) mbar_wait(bar_dead0, (uint32_t)(i & 1));
@@ -1045,8 +1092,8 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
       const long long pn = (worker + (i + 1) * n_workers) * TILE_M + row;
       rin = fetch_row(nt.x0, a.src, pn, i + 1 < n_my && pn < a.src.n_points);
       if (i > 0) { mbar_wait(bar_x0free, ph_x0free); ph_x0free ^= 1; }
-      emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight, nt.x0.enc.latents, s_x0, row, 0);
-      emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight, nt.x0.enc.latents, s_x0, row, 1);
+      emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight, nt.x0.enc.latents, SmemSink{s_x0, row}, 0);
+      emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight, nt.x0.enc.latents, SmemSink{s_x0, row}, 1);
       fence_proxy_async();
       mbar_arrive(bar_x0);
     }
@@ -1206,7 +1253,7 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
 // =====================================================================================================================
 // host side
 // =====================================================================================================================
-static size_t fwd_smem_bytes(const NetDims& d) { return (((size_t)d.pack_bytes + 127) & ~(size_t)127) + 2 * TILE_BYTES + 10 * 8 + (32 + 256 + 256) * 4; }
+static size_t fwd_smem_bytes(const NetDims& d) { return (((size_t)d.pack_bytes + 127) & ~(size_t)127) + 10 * 8 + (32 + 256) * 4; }
 constexpr size_t TOP_SMEM = 6 * (size_t)TILE_BYTES + 4096 + 384 * 4 + 16 + 10 * 8 + 16;
 constexpr size_t BOT_SMEM = 6 * (size_t)TILE_BYTES + 96 * 256 + 4096 + 4096 + 128 * 4 + 256 * 4 + 16 * 8 + 16;
 

@@ -52,6 +52,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// one lane of a converged warp (elect.sync)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// 16-byte shared-memory load by 32-bit shared-space address (no generic -> shared conversion at the use site)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// makes a value opaque to the optimizer so that it lives in a register instead of being recomputed at every use
+__device__ __forceinline__ void pin(uint32_t& x) { asm volatile("" : "+r"(x)); }
+
+// per-warpgroup register budget (all four warps of a warpgroup execute it): the kernel launches with the launch-bound count,
+// light roles hand registers back and heavy roles take them
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---- async proxy ------------------------------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies reading smem)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -141,6 +162,17 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, uint32_t a0, uint32_t a
                "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7)
                : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ----------------------------------------------------------------------------------------------
@@ -185,6 +217,24 @@ __device__ __forceinline__ void umma_k(uint32_t d_tmem, Desc a, Desc b, uint32_t
   for (int kk = 0; kk < KSTEPS; ++kk) umma_lh(d_tmem, a.lo + kk * A_STEP, a.hi, b.lo + kk * B_STEP, b.hi, idesc, kk > 0 ? 1u : acc_first);
 }
 
+// A from tensor memory (TS form): the [128 x K] bf16 A operand sits in TMEM with lane = row and two K-consecutive elements per
+// 32-bit column (cute UMMA::tmem_frg, M = 128), so one K step of 16 is 8 columns.  A must be K-major in this form.
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+constexpr uint32_t KSTEP_TMEM = 8;   // 16 bf16 reduction elements = 8 TMEM columns
+template <int KSTEPS, uint32_t B_STEP>
+__device__ __forceinline__ void umma_ts_k(uint32_t d_tmem, uint32_t a_tmem, Desc b, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int kk = 0; kk < KSTEPS; ++kk) umma_ts(d_tmem, a_tmem + kk * KSTEP_TMEM, b.lo + kk * B_STEP, b.hi, idesc, kk > 0 ? 1u : acc_first);
+}
+
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D fp32, A/B bf16
 __host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -213,6 +263,15 @@ __device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
   uint32_t d;
   asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
   return d;
+}
+
+// packed fp32 pair add (FADD2): {a.x + b.x, a.y + b.y}
+__device__ __forceinline__ float2 add_f32x2(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -1,6 +1,7 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, bench, launch list, one full ncu capture of the two tensor-core kernels.
-# Usage (from the repo root): gpurun --timeout 1500 -- 'bash tools/gpu_check.sh [tag]'
+# One GPU-box visit: parity tests, bench (both arms), ncu launch list of the bench command, one full ncu capture of the
+# tensor-core kernels + the fused loss kernel.
+# Usage (from the repo root): gpurun --timeout 1800 -- 'bash tools/gpu_check.sh [tag]'
 TAG=${1:-run}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
@@ -13,6 +14,7 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_r
 cat $OUT/bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_(forward|backward)_kernel' -s 8 -c 4 \
-    -o $OUT/prof python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_(forward|bwd_top|bwd_bot)_kernel|composite_loss' -s 8 -c 4 \
+    -o $OUT/prof -f python tools/profile_step.py 1024 500 3 > $OUT/ncu_full.log 2>&1
+tail -3 $OUT/ncu_full.log
 ls -la $OUT
