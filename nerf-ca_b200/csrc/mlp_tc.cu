@@ -39,7 +39,6 @@ constexpr uint32_t TILE_BYTES = 32768;           // one [128 x 128] bf16 tile
 constexpr int TC_N_RELU = 5;
 constexpr int STASH_TILES = 2;                   // H0 and H2
 constexpr int FWD_THREADS = 20 * 32;             // 16 epilogue / issue warps + 4 X0 producer warps
-constexpr int BWD_THREADS = 11 * 32;             // 8 epilogue warps + MMA warp + load warp + store warp
 constexpr int BOT_THREADS = 15 * 32;             // ... + 4 warps that build the encoded input tile X0 off the critical path
 constexpr int FAST_FREQ = 12;                    // band count the register-resident encoder is specialised for
 
@@ -581,7 +580,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
           for (int j = 0; j < 8; ++j) b[j] = lds_f4(bias + (uint32_t)(32 * g + 4 * j) * 4u);
           if (l == 0) relu_pack32<false>(g ? v1 : v0, b, w);
           else relu_pack32<true>(g ? v1 : v0, b, w);
+          NERFCA_TL(lane == 0 && (warp & 7) == 1, 1014 + 2 * g + slot * 1000 + l * 10);
           tmem_st16(k_a + 16 * g, w);
+          NERFCA_TL(lane == 0 && (warp & 7) == 1, 1015 + 2 * g + slot * 1000 + l * 10);
           if (stash_l) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -665,6 +666,7 @@ struct BwdNet {
   float* g_b[NERFCA_MAX_LAYERS];   // may be null
   float* g_lat;
   const float* w0_f32;       // nn.Linear weight of layer 0, [128, in_dim] fp32
+  const float* w4_f32;       // nn.Linear weight of layer 4, [128, 128] fp32
   X0Desc x0;
   uint32_t w0_bytes, f32_off;
   int in_dim, enc_dim, n_latent, n_phases;
@@ -681,10 +683,78 @@ struct BwdArgs {
 // =====================================================================================================================
 // backward, top pass: output layer, layers 4 and 3
 // =====================================================================================================================
-constexpr uint32_t TOP_ACC = 0, TOP_WG4 = 128, TOP_WG3 = 256, TOP_BG4 = 384, TOP_BG3 = 400, TOP_ACCO = 416;
+// TMEM: ACC [0,128) chain accumulator | WG4 [128,272) | WG3 [272,416): weight-gradient accumulators, 144 columns each: 128 input
+// features + the column sums of dZ (bias gradient) in column 128, from a constant-1 chunk appended to the H tiles | A [416,480):
+// bf16 A operand of the chain GEMMs that take their input from the epilogue (Z4, dgrad 4, dgrad 3; TS form).
+constexpr uint32_t TOP_ACC = 0, TOP_WG4 = 128, TOP_WG3 = 272, TOP_A = 416;
+constexpr int TOP_THREADS = 9 * 32;                  // 8 epilogue warps (warp 0 holds the issuing lane) + load warp
+constexpr uint32_t HBUF_BYTES = TILE_BYTES + 2 * CHUNK_BYTES;   // an H tile + 2 chunks [1, 0, ..., 0] (N = 144 weight-gradient B operand)
+constexpr int WG_COLS = 144;
 
-// smem: [W3][W4][bufH 0][bufH 1][R][S][side 4 KB][fp32: bias3, bias4, w_out (384 floats)][g_bout acc][barriers]
-__global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// 32 packed words (64 bf16 columns of one row) -> the row's 8 chunks of a tile-canonical shared-memory tile
+__device__ __forceinline__ void sts_row64(uint32_t tile_row_addr, const uint32_t (&w)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) sts_u4(tile_row_addr + c * CHUNK_BYTES, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+}
+// relu(acc + bias) of 64 columns -> 32 packed bf16x2 words; bias by 32-bit shared address
+__device__ __forceinline__ void relu_bias_pack64(const uint32_t (&va)[32], const uint32_t (&vb)[32], uint32_t bias, uint32_t (&w)[32]) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t* v = half ? vb : va;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = lds_f4(bias + (uint32_t)(half * 32 + 4 * j) * 4u);
+      const float2 p0 = add_f32x2(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b.x, b.y));
+      const float2 p1 = add_f32x2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b.z, b.w));
+      w[half * 16 + 2 * j] = pack_relu_bf16x2(p0.x, p0.y);
+      w[half * 16 + 2 * j + 1] = pack_relu_bf16x2(p1.x, p1.y);
+    }
+  }
+}
+// dZ = acc * 1[h > 0] of 64 columns -> 32 packed words (h = the activation's packed bf16 words)
+__device__ __forceinline__ void masked_grad_pack64(const uint32_t (&va)[32], const uint32_t (&vb)[32], const uint32_t (&h)[32], uint32_t (&w)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const uint32_t* v = (i < 16) ? va : vb;
+    const int j = (i & 15) * 2;
+    w[i] = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), relu_mask_bf16x2(h[i]));
+  }
+}
+// flush a TMEM-resident [128 out x 128 in (+ bias column)] weight-gradient accumulator scaled per output row: thread = (row, column half)
+__device__ __forceinline__ void flush_wgrad_scaled(uint32_t t_lane, uint32_t col0, float* gw, int row, int ch, float scale) {
+  for (int c0 = ch * 64; c0 < ch * 64 + 64; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(t_lane + col0 + c0, v);
+    tmem_ld_wait();
+    float* dst = gw + (size_t)row * 128 + c0;
+#pragma unroll
+    for (int e = 0; e < 16; e += 4)
+      red_add_v4(dst + e, scale * __uint_as_float(v[e]), scale * __uint_as_float(v[e + 1]), scale * __uint_as_float(v[e + 2]),
+                 scale * __uint_as_float(v[e + 3]));
+  }
+}
+
+// One tile at a time per CTA (shared memory holds W3, W4, H2 / H3 and the two gradient tiles of a single tile), so the chain
+//   Z3 -> Z4 -> dgrad 4 -> dgrad 3      (each: MMA -> accumulator read -> bf16 tile -> next MMA)
+// is serial; what keeps the tensor pipe busy in between are the two weight-gradient GEMMs, issued as soon as their operands exist.
+//   * The epilogue warps issue the MMAs themselves: after the tile of a step is written they meet at a named barrier and the
+//     elected lane of warp 0 issues the next GEMMs -- no hand-off through a separate MMA warp.
+//   * GEMMs whose A operand comes out of the epilogue (Z4, dgrad 4, dgrad 3) take it from tensor memory; the shared-memory copy
+//     of those tiles is only read by the weight-gradient GEMMs (MN-major views).
+//   * R holds dZ4' = d_raw * 1[Z4 > 0] WITHOUT the output weight (TMEM gets dZ4 = dZ4' * w_out for dgrad 4); then
+//       dW4 = diag(w_out) R^T H3,  db4 = w_out . colsum(R),  dw_out[j] = sum_k W4[j,k] (R^T H3)[j,k] + b4[j] colsum(R)[j]
+//     (the last because H4 = relu(H3 W4^T + b4)), so H4 is never materialised and there are no side GEMMs.
+//   * dZ2 goes to the hand-off buffer straight from registers.
+// smem: [W3][W4][bufH 0 + ones][bufH 1 + ones][R][S][fp32: bias3, bias4, w_out (384 floats)][bf16x2 w_out pairs (64 words)][barriers]
+__global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int net_id = blockIdx.x % a.n_nets;
@@ -693,20 +763,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
   uint8_t* s_w3 = smem;
   uint8_t* s_w4 = smem + TILE_BYTES;
   uint8_t* s_bufh = smem + 2 * TILE_BYTES;           // two buffers: H2 / H3 swap roles every tile
-  uint8_t* s_r = smem + 4 * TILE_BYTES;
-  uint8_t* s_s = smem + 5 * TILE_BYTES;
-  uint8_t* s_side = smem + 6 * TILE_BYTES;
-  float* s_f = reinterpret_cast<float*>(s_side + 4096);   // bias3[128], bias4[128], w_out[128]
-  float* s_gbout = s_f + 384;
+  uint8_t* s_r = s_bufh + 2 * HBUF_BYTES;
+  uint8_t* s_s = s_r + TILE_BYTES;
+  float* s_f = reinterpret_cast<float*>(s_s + TILE_BYTES);   // bias3[128], bias4[128], w_out[128]
+  uint32_t* s_wo2 = reinterpret_cast<uint32_t*>(s_f + 384);  // w_out as packed bf16 pairs
+  float* s_g = reinterpret_cast<float*>(s_wo2 + 64);         // d_raw of the tile's rows, two tiles deep (filled by the load warp)
+  float* s_gbout = s_g + 256;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_gbout + 4);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 10);
-  const uint32_t bar_w = smem_u32(s_bar), bar_ld = bar_w + 8, bar_acc = bar_w + 16, bar_e = bar_w + 24, bar_h3dead = bar_w + 32,
-                 bar_out = bar_w + 40, bar_stfree = bar_w + 48, bar_accfree = bar_w + 56, bar_done = bar_w + 64;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 6);
+  const uint32_t bar_w = smem_u32(s_bar), bar_ld = bar_w + 8, bar_acc = bar_w + 16, bar_h3dead = bar_w + 24, bar_done = bar_w + 32;
 
   if (warp == 8) {
     if (lane == 0) {
-      mbar_init(bar_w, 1); mbar_init(bar_ld, 1); mbar_init(bar_acc, 1); mbar_init(bar_e, 256); mbar_init(bar_h3dead, 1);
-      mbar_init(bar_out, 256); mbar_init(bar_stfree, 1); mbar_init(bar_accfree, 256); mbar_init(bar_done, 1);
+      mbar_init(bar_w, 1); mbar_init(bar_ld, 1); mbar_init(bar_acc, 1); mbar_init(bar_h3dead, 1); mbar_init(bar_done, 1);
       mbar_init_fence();
     }
     __syncwarp();
@@ -718,7 +787,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
       const int which = i >> 7;   // 0: bias3, 1: bias4, 2: w_out
       s_f[i] = __ldg(fb + (which == 0 ? 3 * 128 : (which == 1 ? 4 * 128 : 5 * 128)) + (i & 127));
     }
-    for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_side)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_wo2[i] = pack_bf16x2(__ldg(fb + 5 * 128 + 2 * i), __ldg(fb + 5 * 128 + 2 * i + 1));
+    // the constant chunks behind both H buffers: column 128 = 1, columns 129 .. 143 = 0
+    for (int i = threadIdx.x; i < 2 * 256; i += blockDim.x) {
+      const int b = i >> 8, r = i & 255;
+      reinterpret_cast<uint4*>(s_bufh + b * HBUF_BYTES + TILE_BYTES)[r] = (r < 128) ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    }
     if (threadIdx.x == 0) s_gbout[0] = 0.f;
   }
   tc_fence_before();
@@ -727,158 +801,204 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
   const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
+  [[maybe_unused]] int tl_n = 0;
 
   if (warp == 8) {
-    // ================= MMA warp =================
+    // ================= load warp: weights, then H2 of tile i + 1 into the buffer H3 of tile i vacates =================
     if (lane == 0) {
       mbar_expect_tx(bar_w, 2 * TILE_BYTES);
       bulk_g2s(smem_u32(s_w3), nt.pack + nt.w0_bytes + 2 * (size_t)TILE_BYTES, TILE_BYTES, bar_w);
       bulk_g2s(smem_u32(s_w4), nt.pack + nt.w0_bytes + 3 * (size_t)TILE_BYTES, TILE_BYTES, bar_w);
-      mbar_wait(bar_w, 0);
-      const uint32_t w3 = smem_u32(s_w3), w4 = smem_u32(s_w4), side = smem_u32(s_side), R = smem_u32(s_r), S = smem_u32(s_s);
-      const Desc w3_k = kmajor(w3), w3_mn = mnmajor(w3), w4_k = kmajor(w4), w4_mn = mnmajor(w4), side_mn = mnmajor(side);
-      const Desc R_k = kmajor(R), R_mn = mnmajor(R), S_k = kmajor(S), S_mn = mnmajor(S);
-      constexpr uint32_t KK = KSTEP_KMAJOR, KM = KSTEP_MNMAJOR;
-      constexpr uint32_t id_fwd = instr_desc(128, 128, 0, 0), id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1),
-                         id_side = instr_desc(128, 16, 1, 1);
-      uint32_t ph_ld = 0, ph_e = 0, ph_accfree = 0;
-      for (long long i = 0; i < n_my; ++i) {
-        const uint32_t h2 = smem_u32(s_bufh + (i & 1) * TILE_BYTES), h3 = smem_u32(s_bufh + ((i & 1) ^ 1) * TILE_BYTES);
-        const Desc h2_k = kmajor(h2), h2_mn = mnmajor(h2), h3_k = kmajor(h3), h3_mn = mnmajor(h3);
-        const uint32_t first = (i > 0) ? 1u : 0u;
-        // Z3 = H2 W3^T
-        mbar_wait(bar_ld, ph_ld); ph_ld ^= 1;
-        if (i > 0) { mbar_wait(bar_accfree, ph_accfree); ph_accfree ^= 1; }
-        tc_fence_after();
-        umma_k<8, KK, KK>(tmem + TOP_ACC, h2_k, w3_k, id_fwd, 0);
-        umma_commit(bar_acc);
-        // Z4 = H3 W4^T
-        mbar_wait(bar_e, ph_e); ph_e ^= 1;
-        tc_fence_after();
-        umma_k<8, KK, KK>(tmem + TOP_ACC, h3_k, w4_k, id_fwd, 0);
-        umma_commit(bar_acc);
-        // output-weight grad, dgrad 4, wgrad 4, bias grad 4      (R = dZ4, S = H4)
-        mbar_wait(bar_e, ph_e); ph_e ^= 1;
-        tc_fence_after();
-        umma_k<8, KM, KM>(tmem + TOP_ACCO, S_mn, side_mn, id_side, first);
-        umma_k<8, KK, KM>(tmem + TOP_ACC, R_k, w4_mn, id_dgrad, 0);
-        umma_commit(bar_acc);
-        umma_k<8, KM, KM>(tmem + TOP_WG4, R_mn, h3_mn, id_wgrad, first);
-        umma_k<8, KM, KM>(tmem + TOP_BG4, R_mn, side_mn, id_side, first);
-        // dgrad 3, wgrad 3, bias grad 3                           (S = dZ3)
-        mbar_wait(bar_e, ph_e); ph_e ^= 1;
-        tc_fence_after();
-        umma_commit(bar_h3dead);   // wgrad 4 done and the epilogue has read H3's ReLU pattern: the loader may reuse the buffer
-        umma_k<8, KK, KM>(tmem + TOP_ACC, S_k, w3_mn, id_dgrad, 0);
-        umma_commit(bar_acc);
-        umma_k<8, KM, KM>(tmem + TOP_WG3, S_mn, h2_mn, id_wgrad, first);
-        umma_k<8, KM, KM>(tmem + TOP_BG3, S_mn, side_mn, id_side, first);
-      }
-      umma_commit(bar_done);
     }
-    __syncwarp();
-  } else if (warp == 9) {
-    // ================= load warp: H2 of tile i + 1 goes into the buffer H3 of tile i vacates =================
-    if (lane == 0) {
-      uint32_t ph_dead = 0;
-      for (long long i = 0; i < n_my; ++i) {
-        const long long tile = worker + i * n_workers;
-        if (i > 0) { mbar_wait(bar_h3dead, ph_dead); ph_dead ^= 1; }
+    uint32_t ph_dead = 0;
+    for (long long i = 0; i < n_my; ++i) {
+      const long long tile = worker + i * n_workers;
+      // d_raw of the tile's 128 rows -> shared memory (plain loads: the last tile may be ragged); published by the arrival below
+      float gv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const long long p = tile * TILE_M + lane * 4 + e;
+        gv[e] = (p < a.src.n_points) ? __ldg(nt.d_raw + p) : 0.f;
+      }
+      *reinterpret_cast<float4*>(s_g + (i & 1) * 128 + lane * 4) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+      __syncwarp();
+      if (lane == 0) {
+        if (i > 0) mbar_wait(bar_h3dead, ph_dead);
         mbar_expect_tx(bar_ld, TILE_BYTES);
-        bulk_g2s(smem_u32(s_bufh + (i & 1) * TILE_BYTES), nt.stash + ((size_t)tile * STASH_TILES + 1) * TILE_BYTES, TILE_BYTES, bar_ld);
+        bulk_g2s(smem_u32(s_bufh + (i & 1) * HBUF_BYTES), nt.stash + ((size_t)tile * STASH_TILES + 1) * TILE_BYTES, TILE_BYTES, bar_ld);
       }
-    }
-    __syncwarp();
-  } else if (warp == 10) {
-    // ================= store warp: dZ2 -> hand-off buffer =================
-    if (lane == 0) {
-      uint32_t ph_out = 0;
-      for (long long i = 0; i < n_my; ++i) {
-        const long long tile = worker + i * n_workers;
-        mbar_wait(bar_out, ph_out); ph_out ^= 1;
-        bulk_s2g(nt.handoff + (size_t)tile * TILE_BYTES, smem_u32(s_r), TILE_BYTES);
-        bulk_commit();
-        bulk_wait_read_all();
-        mbar_arrive(bar_stfree);
-      }
-      bulk_wait_all();
+      if (i > 0) ph_dead ^= 1;
+      __syncwarp();
     }
     __syncwarp();
   } else {
-    // ================= 8 epilogue warps: thread = (row, column half) =================
+    // ================= 8 epilogue warps: thread = (row, column half); the elected lane of warp 0 issues =================
     const int q = warp & 3, ch = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
-    const uint32_t t_acc = t_lane + TOP_ACC + ch * 64;
-    const float* bias3 = s_f, *bias4 = s_f + 128, *wout = s_f + 256;
-    uint32_t ph_acc = 0, ph_stfree = 0;
+    uint32_t k_acc = t_lane + TOP_ACC + ch * 64, k_a = t_lane + TOP_A + ch * 32;
+    uint32_t k_bias3 = smem_u32(s_f) + (uint32_t)(ch * 64) * 4u, k_wo2 = smem_u32(s_wo2) + (uint32_t)(ch * 32) * 4u;
+    uint32_t k_rowoff = (uint32_t)(ch * 8) * CHUNK_BYTES + (uint32_t)row * 16u;     // this thread's first chunk inside a tile
+    uint32_t k_bufh = smem_u32(s_bufh), k_r = smem_u32(s_r), k_s = smem_u32(s_s);
+    pin(k_acc); pin(k_a); pin(k_bias3); pin(k_wo2); pin(k_rowoff); pin(k_bufh); pin(k_r); pin(k_s);
+    const uint32_t w3 = smem_u32(s_w3), w4 = smem_u32(s_w4);
+    constexpr uint32_t KK = KSTEP_KMAJOR, KM = KSTEP_MNMAJOR;
+    constexpr uint32_t id_fwd = instr_desc(128, 128, 0, 0), id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, WG_COLS, 1, 1);
+    const uint32_t td_acc = tmem + TOP_ACC, td_a = tmem + TOP_A;
+    uint32_t ph_acc = 0, ph_ld = 0;
     float gb_sum = 0.f;
+    mbar_wait(bar_w, 0);
     for (long long i = 0; i < n_my; ++i) {
       const long long tile = worker + i * n_workers;
-      const long long p = tile * TILE_M + row;
-      const bool valid = p < a.src.n_points;
-      uint8_t* h2 = s_bufh + (i & 1) * TILE_BYTES;
-      uint8_t* h3 = s_bufh + ((i & 1) ^ 1) * TILE_BYTES;
-      const float g = valid ? __ldg(nt.d_raw + p) : 0.f;
-      uint32_t va[32], vb[32];
-      // ---- H3 = relu(Z3 + b3)
+      const uint32_t h2 = k_bufh + (uint32_t)(i & 1) * HBUF_BYTES, h3 = k_bufh + (uint32_t)((i & 1) ^ 1) * HBUF_BYTES;
+      const uint32_t first = (i > 0) ? 1u : 0u;
+      // ---- issue Z3 = H2 W3^T (the accumulator was released by the barrier that closed the previous tile)
+      if (warp == 0) {
+        if (elect_one()) {
+          mbar_wait(bar_ld, ph_ld);
+          tc_fence_after();
+          NERFCA_TL(true, 3000);
+          umma_k<8, KK, KK>(td_acc, kmajor(h2), kmajor(w3), id_fwd, 0);
+          umma_commit(bar_acc);
+        }
+        __syncwarp();
+      }
+      ph_ld ^= 1;
+      uint32_t va[32], vb[32], h3w[32], w[32];
+      // ---- H3 = relu(Z3 + b3) -> shared memory (B operand of wgrad 4) and tensor memory (A operand of Z4)
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
-      ld_acc64(t_acc, va, vb);
-      relu_bias_store(va, vb, bias3, h3, row, ch);
+      NERFCA_TL(warp == 1 && lane == 0, 1010);
+      ld_acc64(k_acc, va, vb);
+      NERFCA_TL(warp == 1 && lane == 0, 1011);
+      relu_bias_pack64(va, vb, k_bias3, h3w);
+      tmem_st32(k_a, h3w);
+      sts_row64(h3 + k_rowoff, h3w);
+      NERFCA_TL(warp == 1 && lane == 0, 1012);
+      tmem_st_wait();
       tc_fence_before();
       fence_proxy_async();
-      mbar_arrive(bar_e);
-      // ---- Z4 -> H4 (S) and dZ4 = d_raw * w_out * 1[Z4 > 0] (R)
+      NERFCA_TL(warp == 1 && lane == 0, 1013);
+      named_bar_sync(1, 256);
+      NERFCA_TL(warp == 1 && lane == 0, 1014);
+
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+          NERFCA_TL(true, 3010);
+          umma_ts_k<8, KK>(td_acc, td_a, kmajor(w4), id_fwd, 0);        // Z4 = H3 W4^T
+          umma_commit(bar_acc);
+          NERFCA_TL(true, 3011);
+        }
+        __syncwarp();
+      }
+      // ---- Z4 -> R = dZ4' = d_raw 1[Z4 + b4 > 0] (shared memory, A of wgrad 4), A = dZ4 = dZ4' w_out (tensor memory, A of dgrad 4)
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
-      ld_acc64(t_acc, va, vb);
-      if (i > 0) { mbar_wait(bar_stfree, ph_stfree); ph_stfree ^= 1; }   // previous dZ2 has left R
+      NERFCA_TL(warp == 1 && lane == 0, 1020);
+      ld_acc64(k_acc, va, vb);
+      NERFCA_TL(warp == 1 && lane == 0, 1021);
+      {
+        const float g_cur = s_g[(i & 1) * 128 + row];
+        const uint32_t gb = pack_bf16x2(g_cur, g_cur);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = ch * 8 + half * 4 + j;
+        for (int half = 0; half < 2; ++half) {
           const uint32_t* v = half ? vb : va;
-          float zz[8], dz[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            zz[e] = __uint_as_float(v[8 * j + e]) + bias4[c * 8 + e];
-            dz[e] = zz[e] > 0.f ? g * wout[c * 8 + e] : 0.f;
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = lds_f4(k_bias3 + 512u + (uint32_t)(half * 32 + 4 * j) * 4u);     // bias4 sits 128 floats behind bias3
+            const float2 p0 = add_f32x2(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b.x, b.y));
+            const float2 p1 = add_f32x2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b.z, b.w));
+            w[half * 16 + 2 * j] = pack_bf16x2(p0.x, p0.y);
+            w[half * 16 + 2 * j + 1] = pack_bf16x2(p1.x, p1.y);
           }
-          *reinterpret_cast<uint4*>(s_s + c * CHUNK_BYTES + row * 16) =
-              make_uint4(pack_relu_bf16x2(zz[0], zz[1]), pack_relu_bf16x2(zz[2], zz[3]), pack_relu_bf16x2(zz[4], zz[5]), pack_relu_bf16x2(zz[6], zz[7]));
-          *reinterpret_cast<uint4*>(s_r + c * CHUNK_BYTES + row * 16) =
-              make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]), pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7]));
+        }
+#pragma unroll
+        for (int i2 = 0; i2 < 32; ++i2) w[i2] = mul_bf16x2(relu_mask_bf16x2(w[i2]), gb);     // dZ4'
+        sts_row64(k_r + k_rowoff, w);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 wo = lds_u4(k_wo2 + (uint32_t)c * 16u);
+          w[4 * c] = mul_bf16x2(w[4 * c], wo.x);
+          w[4 * c + 1] = mul_bf16x2(w[4 * c + 1], wo.y);
+          w[4 * c + 2] = mul_bf16x2(w[4 * c + 2], wo.z);
+          w[4 * c + 3] = mul_bf16x2(w[4 * c + 3], wo.w);
+        }
+        tmem_st32(k_a, w);
+        if (ch == 0) gb_sum += g_cur;
+      }
+      NERFCA_TL(warp == 1 && lane == 0, 1022);
+      tmem_st_wait();
+      tc_fence_before();
+      fence_proxy_async();
+      NERFCA_TL(warp == 1 && lane == 0, 1023);
+      named_bar_sync(1, 256);
+      NERFCA_TL(warp == 1 && lane == 0, 1024);
+
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+          NERFCA_TL(true, 3020);
+          umma_ts_k<8, KM>(td_acc, td_a, mnmajor(w4), id_dgrad, 0);                                  // dH3 = dZ4 W4
+          umma_commit(bar_acc);
+          umma_k<8, KM, KM>(tmem + TOP_WG4, mnmajor(k_r), mnmajor(h3), id_wgrad, first);             // WG4 += R^T [H3 | 1]
+          NERFCA_TL(true, 3021);
+          umma_commit(bar_h3dead);     // H3's buffer may take the next tile's H2 (the ReLU pattern of H3 lives in registers)
+        }
+        __syncwarp();
+      }
+      // ---- dZ3 = dH3 * 1[H3 > 0] -> S (shared memory, A of wgrad 3) and tensor memory (A of dgrad 3)
+      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+      tc_fence_after();
+      NERFCA_TL(warp == 1 && lane == 0, 1030);
+      ld_acc64(k_acc, va, vb);
+      NERFCA_TL(warp == 1 && lane == 0, 1031);
+      masked_grad_pack64(va, vb, h3w, w);
+      tmem_st32(k_a, w);
+      sts_row64(k_s + k_rowoff, w);
+      NERFCA_TL(warp == 1 && lane == 0, 1032);
+      tmem_st_wait();
+      tc_fence_before();
+      fence_proxy_async();
+      NERFCA_TL(warp == 1 && lane == 0, 1033);
+      named_bar_sync(1, 256);
+      NERFCA_TL(warp == 1 && lane == 0, 1034);
+
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+          NERFCA_TL(true, 3030);
+          umma_ts_k<8, KM>(td_acc, td_a, mnmajor(w3), id_dgrad, 0);                                  // dH2 = dZ3 W3
+          umma_commit(bar_acc);
+          umma_k<8, KM, KM>(tmem + TOP_WG3, mnmajor(k_s), mnmajor(h2), id_wgrad, first);             // WG3 += S^T [H2 | 1]
+          NERFCA_TL(true, 3031);
+        }
+        __syncwarp();
+      }
+      // ---- dZ2 = dH2 * 1[H2 > 0] -> hand-off buffer (tile-canonical bytes, straight from registers)
+      {
+        mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+        tc_fence_after();
+        NERFCA_TL(warp == 1 && lane == 0, 1040);
+        ld_acc64(k_acc, va, vb);
+        NERFCA_TL(warp == 1 && lane == 0, 1041);
+        uint8_t* dst = nt.handoff + (size_t)tile * TILE_BYTES + k_rowoff;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 hv = lds_u4(h2 + k_rowoff + (uint32_t)c * CHUNK_BYTES);
+          const uint32_t* v = (c < 4) ? va : vb;
+          const int j = (c & 3) * 8;
+          uint4 o;
+          o.x = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), relu_mask_bf16x2(hv.x));
+          o.y = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), relu_mask_bf16x2(hv.y));
+          o.z = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])), relu_mask_bf16x2(hv.z));
+          o.w = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])), relu_mask_bf16x2(hv.w));
+          __stcs(reinterpret_cast<uint4*>(dst + c * CHUNK_BYTES), o);
         }
       }
-      if (ch == 0) {   // side tile row: [d_hi, d_lo, 1, 0, ...]
-        const __nv_bfloat16 dh = __float2bfloat16_rn(g);
-        const __nv_bfloat16 dl = __float2bfloat16_rn(g - __bfloat162float(dh));
-        const uint32_t w0 = (uint32_t)__bfloat16_as_ushort(dh) | ((uint32_t)__bfloat16_as_ushort(dl) << 16);
-        *reinterpret_cast<uint4*>(s_side + row * 16) = make_uint4(w0, 0x00003F80u, 0u, 0u);   // 0x3F80 = bf16(1.0)
-        gb_sum += g;
-      }
+      NERFCA_TL(warp == 1 && lane == 0, 1043);
       tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(bar_e);
-      // ---- dZ3 = (dZ4 W4) * 1[H3 > 0]  -> S
-      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
-      tc_fence_after();
-      ld_acc64(t_acc, va, vb);
-      masked_grad_store(va, vb, h3, s_s, row, ch);
-      tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(bar_e);
-      // ---- dZ2 = (dZ3 W3) * 1[H2 > 0]  -> R -> hand-off
-      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
-      tc_fence_after();
-      ld_acc64(t_acc, va, vb);
-      masked_grad_store(va, vb, h2, s_r, row, ch);
-      tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(bar_out);
-      mbar_arrive(bar_accfree);
+      named_bar_sync(1, 256);      // the accumulator has been read: the next tile's Z3 may overwrite it
     }
     // ---- flush the TMEM-resident accumulators
     if (ch == 0) {
@@ -887,24 +1007,42 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
       if (lane == 0 && nt.g_b[5]) atomicAdd(s_gbout, gb_sum);
     }
     if (n_my > 0) {
+      if (warp == 0) {
+        if (elect_one()) umma_commit(bar_done);
+        __syncwarp();
+      }
       mbar_wait(bar_done, 0);
       tc_fence_after();
-      flush_wgrad(t_lane, TOP_WG4, nt.g_w[4], row, ch, 128, 128);
-      flush_wgrad(t_lane, TOP_WG3, nt.g_w[3], row, ch, 128, 128);
-      if (ch == 0) {
+      const float wo_row = s_f[256 + row], b4_row = s_f[128 + row];
+      // dw_out[row] = sum_k W4[row, k] (R^T H3)[row, k] + b4[row] colsum(R)[row]   (this thread: its 64 columns, then the bias term)
+      float dot = 0.f;
+      for (int c0 = ch * 64; c0 < ch * 64 + 64; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(t_lane + TOP_BG4, v);
+        tmem_ld16(t_lane + TOP_WG4 + c0, v);
         tmem_ld_wait();
-        if (nt.g_b[4]) atomicAdd(nt.g_b[4] + row, __uint_as_float(v[2]));
-        tmem_ld16(t_lane + TOP_BG3, v);
-        tmem_ld_wait();
-        if (nt.g_b[3]) atomicAdd(nt.g_b[3] + row, __uint_as_float(v[2]));
-      } else {
-        uint32_t v[16];
-        tmem_ld16(t_lane + TOP_ACCO, v);
-        tmem_ld_wait();
-        atomicAdd(nt.g_w[5] + row, __uint_as_float(v[0]) + __uint_as_float(v[1]));
+        const float* wrow = nt.w4_f32 + (size_t)row * 128 + c0;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + e));
+          dot = fmaf(wv.x, __uint_as_float(v[e]), dot);
+          dot = fmaf(wv.y, __uint_as_float(v[e + 1]), dot);
+          dot = fmaf(wv.z, __uint_as_float(v[e + 2]), dot);
+          dot = fmaf(wv.w, __uint_as_float(v[e + 3]), dot);
+        }
       }
+      flush_wgrad_scaled(t_lane, TOP_WG4, nt.g_w[4], row, ch, wo_row);
+      flush_wgrad_scaled(t_lane, TOP_WG3, nt.g_w[3], row, ch, 1.f);
+      uint32_t vb4[16], vb3[16];
+      tmem_ld16(t_lane + TOP_WG4 + 128, vb4);
+      tmem_ld16(t_lane + TOP_WG3 + 128, vb3);
+      tmem_ld_wait();
+      const float cs4 = __uint_as_float(vb4[0]), cs3 = __uint_as_float(vb3[0]);
+      if (ch == 0) {
+        if (nt.g_b[4]) atomicAdd(nt.g_b[4] + row, wo_row * cs4);
+        if (nt.g_b[3]) atomicAdd(nt.g_b[3] + row, cs3);
+        dot = fmaf(b4_row, cs4, dot);
+      }
+      atomicAdd(nt.g_w[5] + row, dot);
       tc_fence_before();
     }
   }
@@ -1254,7 +1392,7 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
 // host side
 // =====================================================================================================================
 static size_t fwd_smem_bytes(const NetDims& d) { return (((size_t)d.pack_bytes + 127) & ~(size_t)127) + 10 * 8 + (32 + 256) * 4; }
-constexpr size_t TOP_SMEM = 6 * (size_t)TILE_BYTES + 4096 + 384 * 4 + 16 + 10 * 8 + 16;
+constexpr size_t TOP_SMEM = 4 * (size_t)TILE_BYTES + 2 * (size_t)HBUF_BYTES + 384 * 4 + 64 * 4 + 256 * 4 + 16 + 6 * 8 + 16;
 constexpr size_t BOT_SMEM = 6 * (size_t)TILE_BYTES + 96 * 256 + 4096 + 4096 + 128 * 4 + 256 * 4 + 16 * 8 + 16;
 
 static size_t n_tiles_of(long long P) { return (size_t)((P + TILE_M - 1) / TILE_M); }
@@ -1372,6 +1510,7 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
     for (int l = 0; l < NERFCA_MAX_LAYERS; ++l) { n.g_w[l] = gr[i]->weight[l]; n.g_b[l] = gr[i]->bias[l]; }
     n.g_lat = gr[i]->latents;
     n.w0_f32 = f[i]->weight[0];
+    n.w4_f32 = f[i]->weight[4];
     n.x0 = make_x0(*f[i], d);
     if (f[i]->n_latent > 0 && f[i]->n_phases <= d.kpad0 - d.in_dim - 1) n.x0.onehot = f[i]->n_phases;
     n.w0_bytes = d.w0_bytes; n.f32_off = d.f32_off;
@@ -1386,10 +1525,19 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
   const unsigned grid = grid_for(n_nets, a.n_tiles);
   a.dbg = nullptr;
   a.dbg_cta = getenv("NERFCA_TIMELINE_CTA") ? atoi(getenv("NERFCA_TIMELINE_CTA")) : 0;
+  if (timeline_wanted("top")) {
+    NERFCA_CUDA_OK(cudaMalloc(&a.dbg, 8008 * sizeof(long long)));
+    NERFCA_CUDA_OK(cudaMemsetAsync(a.dbg, 0, 8008 * sizeof(long long), st));
+  }
   {
     ProfScope prof(NERFCA_K_FIELD_BWD, st);
-    tc_bwd_top_kernel<<<grid, BWD_THREADS, TOP_SMEM, st>>>(a);
+    tc_bwd_top_kernel<<<grid, TOP_THREADS, TOP_SMEM, st>>>(a);
     NERFCA_LAUNCH_OK();
+  }
+  if (timeline_wanted("top")) {
+    int rc = timeline_dump(a.dbg, st);
+    if (rc) return rc;
+    a.dbg = nullptr;
   }
   const bool timeline = timeline_wanted("bot");
   if (timeline) {

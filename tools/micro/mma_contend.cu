@@ -7,7 +7,7 @@
 using namespace nerfca::tc;
 
 // hammer: 0 none, 1 tcgen05.ld.x32 loops, 2 tcgen05.st.x16 loops, 3 ld + st (epilogue-like), 4 LDS.128 loops; n_hammer warps (<= 8)
-__global__ void __launch_bounds__(384, 1) mma_contend(int ts, int hammer, int n_hammer, int n_mma, long long* out) {
+__global__ void __launch_bounds__(640, 1) mma_contend(int ts, int hammer, int n_hammer, int n_mma, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_ptr;
@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(384, 1) mma_contend(int ts, int hammer, int n_
     while (!done) {
       if (hammer == 1 || hammer == 3) { uint32_t v[32]; tmem_ld32(ta + (n & 1) * 32, v); tmem_ld_wait(); for (int j = 0; j < 32; ++j) acc += v[j]; }
       if (hammer == 2 || hammer == 3) { uint32_t v[16]; for (int j = 0; j < 16; ++j) v[j] = acc + j; tmem_st16(ta + 192, v); tmem_st_wait(); }
+      if (hammer == 5) { uint32_t v[32], w[32]; tmem_ld32(ta, v); tmem_ld32(ta + 32, w); tmem_ld_wait(); for (int j = 0; j < 32; ++j) acc += v[j] ^ w[j]; }
       if (hammer == 4) { for (int j = 0; j < 8; ++j) { uint32_t x0, x1, x2, x3; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(smem_u32(smem + 1024 * j + (warp & 3) * 16))); acc += x0 ^ x3; } }
       ++n;
     }
@@ -61,17 +62,18 @@ __global__ void __launch_bounds__(384, 1) mma_contend(int ts, int hammer, int n_
 int main() {
   long long* d; cudaMalloc(&d, 128);
   cudaFuncSetAttribute(mma_contend, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024);
-  const char* hn[] = {"none", "ld.x32", "st.x16", "ld+st", "lds"};
-  for (int ts = 0; ts < 2; ++ts) for (int hammer = 0; hammer < 5; ++hammer) for (int nh : {4, 8}) {
-    if (hammer == 0 && nh == 8) continue;
+  const char* hn[] = {"none", "ld.x32", "st.x16", "ld+st", "lds", "2xld.x32"};
+  for (int ts = 0; ts < 2; ++ts) for (int hammer : {0, 1, 5, 2}) for (int nh : {4, 8, 16}) {
+    if (hammer == 0 && nh != 4) continue;
     for (int rep = 0; rep < 2; ++rep) {
       cudaMemset(d, 0, 128);
-      mma_contend<<<1, 384, 65536 + 1024>>>(ts, hammer, nh, 512, d);
+      mma_contend<<<1, 640, 65536 + 1024>>>(ts, hammer, nh, 512, d);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("%s\n", cudaGetErrorString(e)); return 1; }
     }
     long long h[16]; cudaMemcpy(h, d, 128, cudaMemcpyDeviceToHost);
-    printf("%s hammer=%-7s x%d warps: %6.1f cyc/MMA (512 MMAs N=128); hammer iterations per warp %lld\n", ts ? "TS" : "SS", hn[hammer], nh, h[0] / 512.0, h[1]);
+    double bytes = (hammer == 5 ? 8192.0 : hammer == 1 ? 4096.0 : hammer == 2 ? 2048.0 : 0.0) * h[1] * nh;
+    printf("%s hammer=%-8s x%2d warps: %6.1f cyc/MMA (512 MMAs N=128); iterations per warp %4lld -> %6.1f B/clk/SM TMEM traffic by the hammer warps\n", ts ? "TS" : "SS", hn[hammer], nh, h[0] / 512.0, h[1], bytes / h[0]);
   }
   return 0;
 }
