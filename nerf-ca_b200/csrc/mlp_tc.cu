@@ -37,9 +37,10 @@ using namespace tc;
 constexpr int TC_H = 128;
 constexpr uint32_t TILE_BYTES = 32768;           // one [128 x 128] bf16 tile
 constexpr int TC_N_RELU = 5;
-constexpr int STASH_TILES = 2;                   // H0 and H2
+constexpr int STASH_TILES = 4;                   // H0 .. H3 of every tile (bf16, tile-canonical bytes)
+constexpr uint32_t MASK_BYTES = 16384;           // + the high bytes of H4 (nonzero <=> Z4 + b4 > 0): chunk c (16 columns) at c * 2048 + row * 16
+constexpr size_t STASH_STRIDE = (size_t)STASH_TILES * 32768 + MASK_BYTES;   // bytes per tile and net
 constexpr int FWD_THREADS = 20 * 32;             // 16 epilogue / issue warps + 4 X0 producer warps
-constexpr int BOT_THREADS = 15 * 32;             // ... + 4 warps that build the encoded input tile X0 off the critical path
 constexpr int FAST_FREQ = 12;                    // band count the register-resident encoder is specialised for
 
 // ---- packed parameter block of one net (device memory, also the leading part of the forward kernel's shared memory) --
@@ -532,7 +533,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
     // shared-window base, ~25-cycle S2R reads on the critical path of every layer)
     uint32_t k_acc = t_acc, k_a = t_a, k_bias = smem_u32(s_f) + (uint32_t)(ch * 64) * 4u, k_bar_acc = bar_acc;
     uint32_t k_stash_off = (uint32_t)(ch * 8) * CHUNK_BYTES + (uint32_t)row * 16u;
-    pin(k_acc); pin(k_a); pin(k_bias); pin(k_bar_acc); pin(k_stash_off);
+    uint32_t k_mask_off = (uint32_t)(ch * 4) * CHUNK_BYTES + (uint32_t)row * 16u;
+    pin(k_acc); pin(k_a); pin(k_bias); pin(k_bar_acc); pin(k_stash_off); pin(k_mask_off);
 
     auto issue_layer0 = [&]() {      // whole warp; the X0 region of the slot's next tile feeds layer 0
       if (elect_one()) {
@@ -559,9 +561,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
         // H_l = relu(Z_l + b_l) -> bf16 A operand of the next layer (layer 0's bias came through the constant-1 column), in two
         // groups of 32 columns; the bias of the first group is fetched before the accumulator wait
         const uint32_t bias = k_bias + (uint32_t)l * 512u;
-        const bool stash_l = stash_on && (l == 0 || l == 2);
-        // tile-canonical stash bytes: chunk c of the row at c * 2048 + row * 16 (a warp writes 512 contiguous bytes per chunk)
-        uint8_t* dst = nt.stash + ((size_t)tile * STASH_TILES + (l >> 1)) * TILE_BYTES + k_stash_off;
+        // tile-canonical stash bytes: chunk c of the row at c * 2048 + row * 16 (a warp writes 512 contiguous bytes per chunk);
+        // layer 4 leaves only the high byte of every H4 element (the ReLU pattern the backward needs), 16 columns per chunk
+        uint8_t* dst = nt.stash + (size_t)tile * STASH_STRIDE + (size_t)(l < 4 ? l : STASH_TILES) * TILE_BYTES + ((l < 4) ? k_stash_off : k_mask_off);
         mbar_wait(k_bar_acc, ph_acc);
         ph_acc ^= 1;
         tc_fence_after();
@@ -583,10 +585,18 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
           NERFCA_TL(lane == 0 && (warp & 7) == 1, 1014 + 2 * g + slot * 1000 + l * 10);
           tmem_st16(k_a + 16 * g, w);
           NERFCA_TL(lane == 0 && (warp & 7) == 1, 1015 + 2 * g + slot * 1000 + l * 10);
-          if (stash_l) {
+          if (stash_on) {
+            if (l < 4) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              __stcs(reinterpret_cast<uint4*>(dst + (4 * g + c) * CHUNK_BYTES), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+              for (int c = 0; c < 4; ++c)
+                __stcs(reinterpret_cast<uint4*>(dst + (4 * g + c) * CHUNK_BYTES), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 2; ++c)
+                __stcs(reinterpret_cast<uint4*>(dst + (2 * g + c) * CHUNK_BYTES),
+                       make_uint4(__byte_perm(w[8 * c], w[8 * c + 1], 0x7531), __byte_perm(w[8 * c + 2], w[8 * c + 3], 0x7531),
+                                  __byte_perm(w[8 * c + 4], w[8 * c + 5], 0x7531), __byte_perm(w[8 * c + 6], w[8 * c + 7], 0x7531)));
+            }
           }
         }
         tmem_st_wait();
@@ -683,13 +693,23 @@ struct BwdArgs {
 // =====================================================================================================================
 // backward, top pass: output layer, layers 4 and 3
 // =====================================================================================================================
-// TMEM: ACC [0,128) chain accumulator | WG4 [128,272) | WG3 [272,416): weight-gradient accumulators, 144 columns each: 128 input
-// features + the column sums of dZ (bias gradient) in column 128, from a constant-1 chunk appended to the H tiles | A [416,480):
-// bf16 A operand of the chain GEMMs that take their input from the epilogue (Z4, dgrad 4, dgrad 3; TS form).
-constexpr uint32_t TOP_ACC = 0, TOP_WG4 = 128, TOP_WG3 = 272, TOP_A = 416;
+// Nothing is recomputed here: the forward stashed H2, H3 and the ReLU pattern of H4 (one byte per element), so a tile is two
+// chain steps
+//     R = dZ4' = d_raw 1[H4 > 0]  ->  dgrad 4  ->  S = dZ3 = (.) 1[H3 > 0]  ->  dgrad 3  ->  dZ2 = (.) 1[H2 > 0]  -> hand-off
+// with the weight-gradient GEMMs (and their N = 16 bias-gradient companions against a constant-1 tile) filling the tensor pipe
+// while the epilogue converts.
+//   * The epilogue warps issue the MMAs themselves: after the tile of a step is written they meet at a named barrier and the
+//     elected lane of warp 0 issues the next GEMMs.
+//   * The dgrad GEMMs take their A operand (the gradient tile just produced) from tensor memory (TS form); the shared-memory copy
+//     is only read by the weight-gradient GEMMs (MN-major views).
+//   * R holds dZ4' WITHOUT the output weight (TMEM gets dZ4 = dZ4' w_out for dgrad 4); then
+//       dW4 = diag(w_out) R^T H3,  db4 = w_out . colsum(R),  dw_out[j] = sum_k W4[j,k] (R^T H3)[j,k] + b4[j] colsum(R)[j]
+//     (the last because H4 = relu(H3 W4^T + b4)), so H4 itself is never needed.
+//   * Four 32 KB tile buffers rotate: role k of tile i (0: H2, 1: H3, 2: R, 3: S) lives in buffer (i + k) % 4, so the loads of
+//     tile i + 1 go into the buffers H3 / R of tile i vacate when weight gradient 4 completes.
+// TMEM: ACC [0,128) | WG4 [128,256) | WG3 [256,384) | BG4 [384,400) | BG3 [400,416) | A [416,480)
+constexpr uint32_t TOP_ACC = 0, TOP_WG4 = 128, TOP_WG3 = 256, TOP_BG4 = 384, TOP_BG3 = 400, TOP_A = 416;
 constexpr int TOP_THREADS = 9 * 32;                  // 8 epilogue warps (warp 0 holds the issuing lane) + load warp
-constexpr uint32_t HBUF_BYTES = TILE_BYTES + 2 * CHUNK_BYTES;   // an H tile + 2 chunks [1, 0, ..., 0] (N = 144 weight-gradient B operand)
-constexpr int WG_COLS = 144;
 
 __device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -704,31 +724,20 @@ __device__ __forceinline__ void sts_row64(uint32_t tile_row_addr, const uint32_t
 #pragma unroll
   for (int c = 0; c < 8; ++c) sts_u4(tile_row_addr + c * CHUNK_BYTES, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
 }
-// relu(acc + bias) of 64 columns -> 32 packed bf16x2 words; bias by 32-bit shared address
-__device__ __forceinline__ void relu_bias_pack64(const uint32_t (&va)[32], const uint32_t (&vb)[32], uint32_t bias, uint32_t (&w)[32]) {
+// dZ = acc * 1[h > 0] of this thread's 64 columns -> 32 packed words; h = the activation tile in shared memory (row address)
+__device__ __forceinline__ void masked_grad_pack64(const uint32_t (&va)[32], const uint32_t (&vb)[32], uint32_t h_row_addr, uint32_t (&w)[32]) {
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const uint32_t* v = half ? vb : va;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 b = lds_f4(bias + (uint32_t)(half * 32 + 4 * j) * 4u);
-      const float2 p0 = add_f32x2(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b.x, b.y));
-      const float2 p1 = add_f32x2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b.z, b.w));
-      w[half * 16 + 2 * j] = pack_relu_bf16x2(p0.x, p0.y);
-      w[half * 16 + 2 * j + 1] = pack_relu_bf16x2(p1.x, p1.y);
-    }
+  for (int c = 0; c < 8; ++c) {
+    const uint4 hv = lds_u4(h_row_addr + (uint32_t)c * CHUNK_BYTES);
+    const uint32_t* v = (c < 4) ? va : vb;
+    const int j = (c & 3) * 8;
+    w[4 * c] = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), relu_mask_bf16x2(hv.x));
+    w[4 * c + 1] = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), relu_mask_bf16x2(hv.y));
+    w[4 * c + 2] = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])), relu_mask_bf16x2(hv.z));
+    w[4 * c + 3] = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])), relu_mask_bf16x2(hv.w));
   }
 }
-// dZ = acc * 1[h > 0] of 64 columns -> 32 packed words (h = the activation's packed bf16 words)
-__device__ __forceinline__ void masked_grad_pack64(const uint32_t (&va)[32], const uint32_t (&vb)[32], const uint32_t (&h)[32], uint32_t (&w)[32]) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const uint32_t* v = (i < 16) ? va : vb;
-    const int j = (i & 15) * 2;
-    w[i] = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), relu_mask_bf16x2(h[i]));
-  }
-}
-// flush a TMEM-resident [128 out x 128 in (+ bias column)] weight-gradient accumulator scaled per output row: thread = (row, column half)
+// flush a TMEM-resident [128 out x 128 in] weight-gradient accumulator scaled per output row: thread = (row, column half)
 __device__ __forceinline__ void flush_wgrad_scaled(uint32_t t_lane, uint32_t col0, float* gw, int row, int ch, float scale) {
   for (int c0 = ch * 64; c0 < ch * 64 + 64; c0 += 16) {
     uint32_t v[16];
@@ -742,18 +751,7 @@ __device__ __forceinline__ void flush_wgrad_scaled(uint32_t t_lane, uint32_t col
   }
 }
 
-// One tile at a time per CTA (shared memory holds W3, W4, H2 / H3 and the two gradient tiles of a single tile), so the chain
-//   Z3 -> Z4 -> dgrad 4 -> dgrad 3      (each: MMA -> accumulator read -> bf16 tile -> next MMA)
-// is serial; what keeps the tensor pipe busy in between are the two weight-gradient GEMMs, issued as soon as their operands exist.
-//   * The epilogue warps issue the MMAs themselves: after the tile of a step is written they meet at a named barrier and the
-//     elected lane of warp 0 issues the next GEMMs -- no hand-off through a separate MMA warp.
-//   * GEMMs whose A operand comes out of the epilogue (Z4, dgrad 4, dgrad 3) take it from tensor memory; the shared-memory copy
-//     of those tiles is only read by the weight-gradient GEMMs (MN-major views).
-//   * R holds dZ4' = d_raw * 1[Z4 > 0] WITHOUT the output weight (TMEM gets dZ4 = dZ4' * w_out for dgrad 4); then
-//       dW4 = diag(w_out) R^T H3,  db4 = w_out . colsum(R),  dw_out[j] = sum_k W4[j,k] (R^T H3)[j,k] + b4[j] colsum(R)[j]
-//     (the last because H4 = relu(H3 W4^T + b4)), so H4 is never materialised and there are no side GEMMs.
-//   * dZ2 goes to the hand-off buffer straight from registers.
-// smem: [W3][W4][bufH 0 + ones][bufH 1 + ones][R][S][fp32: bias3, bias4, w_out (384 floats)][bf16x2 w_out pairs (64 words)][barriers]
+// smem: [W3][W4][4 tile buffers][ones tile 4 KB][H4 pattern 16 KB][fp32: w_out (128)][bf16x2 w_out pairs (64 words)][d_raw 2 x 128][barriers]
 __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -762,20 +760,22 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
   const long long worker = blockIdx.x / a.n_nets, n_workers = gridDim.x / a.n_nets;
   uint8_t* s_w3 = smem;
   uint8_t* s_w4 = smem + TILE_BYTES;
-  uint8_t* s_bufh = smem + 2 * TILE_BYTES;           // two buffers: H2 / H3 swap roles every tile
-  uint8_t* s_r = s_bufh + 2 * HBUF_BYTES;
-  uint8_t* s_s = s_r + TILE_BYTES;
-  float* s_f = reinterpret_cast<float*>(s_s + TILE_BYTES);   // bias3[128], bias4[128], w_out[128]
-  uint32_t* s_wo2 = reinterpret_cast<uint32_t*>(s_f + 384);  // w_out as packed bf16 pairs
-  float* s_g = reinterpret_cast<float*>(s_wo2 + 64);         // d_raw of the tile's rows, two tiles deep (filled by the load warp)
+  uint8_t* s_buf = smem + 2 * TILE_BYTES;            // 4 rotating tile buffers
+  uint8_t* s_ones = s_buf + 4 * TILE_BYTES;          // [128 x 16] bf16, column 0 = 1: B operand of the bias-gradient GEMMs
+  uint8_t* s_m4 = s_ones + 4096;                     // high bytes of H4 of the current tile
+  float* s_wo = reinterpret_cast<float*>(s_m4 + MASK_BYTES);
+  uint32_t* s_wo2 = reinterpret_cast<uint32_t*>(s_wo + 128);   // w_out as packed bf16 pairs
+  float* s_g = reinterpret_cast<float*>(s_wo2 + 64);           // d_raw of the tile's rows, two tiles deep (filled by the load warp)
   float* s_gbout = s_g + 256;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_gbout + 4);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 6);
-  const uint32_t bar_w = smem_u32(s_bar), bar_ld = bar_w + 8, bar_acc = bar_w + 16, bar_h3dead = bar_w + 24, bar_done = bar_w + 32;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+  const uint32_t bar_w = smem_u32(s_bar), bar_ldh = bar_w + 8, bar_ldm = bar_w + 16, bar_acc = bar_w + 24, bar_half = bar_w + 32,
+                 bar_mfree = bar_w + 40, bar_tile = bar_w + 48, bar_done = bar_w + 56;
 
   if (warp == 8) {
     if (lane == 0) {
-      mbar_init(bar_w, 1); mbar_init(bar_ld, 1); mbar_init(bar_acc, 1); mbar_init(bar_h3dead, 1); mbar_init(bar_done, 1);
+      mbar_init(bar_w, 1); mbar_init(bar_ldh, 1); mbar_init(bar_ldm, 1); mbar_init(bar_acc, 1); mbar_init(bar_half, 1);
+      mbar_init(bar_mfree, 8); mbar_init(bar_tile, 1); mbar_init(bar_done, 1);
       mbar_init_fence();
     }
     __syncwarp();
@@ -783,16 +783,10 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
   }
   {
     const float* fb = reinterpret_cast<const float*>(nt.pack + nt.f32_off);
-    for (int i = threadIdx.x; i < 384; i += blockDim.x) {
-      const int which = i >> 7;   // 0: bias3, 1: bias4, 2: w_out
-      s_f[i] = __ldg(fb + (which == 0 ? 3 * 128 : (which == 1 ? 4 * 128 : 5 * 128)) + (i & 127));
-    }
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_wo[i] = __ldg(fb + 5 * 128 + i);
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_wo2[i] = pack_bf16x2(__ldg(fb + 5 * 128 + 2 * i), __ldg(fb + 5 * 128 + 2 * i + 1));
-    // the constant chunks behind both H buffers: column 128 = 1, columns 129 .. 143 = 0
-    for (int i = threadIdx.x; i < 2 * 256; i += blockDim.x) {
-      const int b = i >> 8, r = i & 255;
-      reinterpret_cast<uint4*>(s_bufh + b * HBUF_BYTES + TILE_BYTES)[r] = (r < 128) ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-    }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+      reinterpret_cast<uint4*>(s_ones)[i] = (i < 128) ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
     if (threadIdx.x == 0) s_gbout[0] = 0.f;
   }
   tc_fence_before();
@@ -804,16 +798,18 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
   [[maybe_unused]] int tl_n = 0;
 
   if (warp == 8) {
-    // ================= load warp: weights, then H2 of tile i + 1 into the buffer H3 of tile i vacates =================
+    // ================= load warp =================
     if (lane == 0) {
       mbar_expect_tx(bar_w, 2 * TILE_BYTES);
       bulk_g2s(smem_u32(s_w3), nt.pack + nt.w0_bytes + 2 * (size_t)TILE_BYTES, TILE_BYTES, bar_w);
       bulk_g2s(smem_u32(s_w4), nt.pack + nt.w0_bytes + 3 * (size_t)TILE_BYTES, TILE_BYTES, bar_w);
     }
-    uint32_t ph_dead = 0;
+    uint32_t ph_half = 0, ph_mfree = 0;
     for (long long i = 0; i < n_my; ++i) {
       const long long tile = worker + i * n_workers;
-      // d_raw of the tile's 128 rows -> shared memory (plain loads: the last tile may be ragged); published by the arrival below
+      const uint8_t* st = nt.stash + (size_t)tile * STASH_STRIDE;
+      // H4 pattern + d_raw of tile i: as soon as step A of tile i - 1 has consumed its own (plain loads for d_raw: the last tile
+      // may be ragged; they are published by the arrival on bar_ldm below)
       float gv[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -823,99 +819,63 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
       *reinterpret_cast<float4*>(s_g + (i & 1) * 128 + lane * 4) = make_float4(gv[0], gv[1], gv[2], gv[3]);
       __syncwarp();
       if (lane == 0) {
-        if (i > 0) mbar_wait(bar_h3dead, ph_dead);
-        mbar_expect_tx(bar_ld, TILE_BYTES);
-        bulk_g2s(smem_u32(s_bufh + (i & 1) * HBUF_BYTES), nt.stash + ((size_t)tile * STASH_TILES + 1) * TILE_BYTES, TILE_BYTES, bar_ld);
+        if (i > 0) mbar_wait(bar_mfree, ph_mfree);
+        mbar_expect_tx(bar_ldm, MASK_BYTES);
+        bulk_g2s(smem_u32(s_m4), st + (size_t)STASH_TILES * TILE_BYTES, MASK_BYTES, bar_ldm);
+        // H2, H3 of tile i: into the buffers that H3 / R of tile i - 1 leave when its weight gradient 4 is complete
+        if (i > 0) mbar_wait(bar_half, ph_half);
+        mbar_expect_tx(bar_ldh, 2 * TILE_BYTES);
+        bulk_g2s(smem_u32(s_buf + (size_t)(i & 3) * TILE_BYTES), st + 2 * (size_t)TILE_BYTES, TILE_BYTES, bar_ldh);
+        bulk_g2s(smem_u32(s_buf + (size_t)((i + 1) & 3) * TILE_BYTES), st + 3 * (size_t)TILE_BYTES, TILE_BYTES, bar_ldh);
       }
-      if (i > 0) ph_dead ^= 1;
+      if (i > 0) { ph_half ^= 1; ph_mfree ^= 1; }
       __syncwarp();
     }
-    __syncwarp();
   } else {
     // ================= 8 epilogue warps: thread = (row, column half); the elected lane of warp 0 issues =================
     const int q = warp & 3, ch = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t k_acc = t_lane + TOP_ACC + ch * 64, k_a = t_lane + TOP_A + ch * 32;
-    uint32_t k_bias3 = smem_u32(s_f) + (uint32_t)(ch * 64) * 4u, k_wo2 = smem_u32(s_wo2) + (uint32_t)(ch * 32) * 4u;
+    uint32_t k_wo2 = smem_u32(s_wo2) + (uint32_t)(ch * 32) * 4u;
     uint32_t k_rowoff = (uint32_t)(ch * 8) * CHUNK_BYTES + (uint32_t)row * 16u;     // this thread's first chunk inside a tile
-    uint32_t k_bufh = smem_u32(s_bufh), k_r = smem_u32(s_r), k_s = smem_u32(s_s);
-    pin(k_acc); pin(k_a); pin(k_bias3); pin(k_wo2); pin(k_rowoff); pin(k_bufh); pin(k_r); pin(k_s);
-    const uint32_t w3 = smem_u32(s_w3), w4 = smem_u32(s_w4);
-    constexpr uint32_t KK = KSTEP_KMAJOR, KM = KSTEP_MNMAJOR;
-    constexpr uint32_t id_fwd = instr_desc(128, 128, 0, 0), id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, WG_COLS, 1, 1);
+    uint32_t k_m4 = smem_u32(s_m4) + (uint32_t)(ch * 4) * CHUNK_BYTES + (uint32_t)row * 16u;
+    uint32_t k_buf = smem_u32(s_buf);
+    pin(k_acc); pin(k_a); pin(k_wo2); pin(k_rowoff); pin(k_m4); pin(k_buf);
+    const uint32_t w3 = smem_u32(s_w3), w4 = smem_u32(s_w4), ones = smem_u32(s_ones);
+    constexpr uint32_t KM = KSTEP_MNMAJOR;
+    constexpr uint32_t id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1), id_side = instr_desc(128, 16, 1, 1);
     const uint32_t td_acc = tmem + TOP_ACC, td_a = tmem + TOP_A;
-    uint32_t ph_acc = 0, ph_ld = 0;
+    uint32_t ph_acc = 0;
     float gb_sum = 0.f;
     mbar_wait(bar_w, 0);
     for (long long i = 0; i < n_my; ++i) {
       const long long tile = worker + i * n_workers;
-      const uint32_t h2 = k_bufh + (uint32_t)(i & 1) * HBUF_BYTES, h3 = k_bufh + (uint32_t)((i & 1) ^ 1) * HBUF_BYTES;
+      const uint32_t par = (uint32_t)(i & 1);
+      const uint32_t h2 = k_buf + (uint32_t)(i & 3) * TILE_BYTES, h3 = k_buf + (uint32_t)((i + 1) & 3) * TILE_BYTES,
+                     R = k_buf + (uint32_t)((i + 2) & 3) * TILE_BYTES, S = k_buf + (uint32_t)((i + 3) & 3) * TILE_BYTES;
       const uint32_t first = (i > 0) ? 1u : 0u;
-      // ---- issue Z3 = H2 W3^T (the accumulator was released by the barrier that closed the previous tile)
-      if (warp == 0) {
-        if (elect_one()) {
-          mbar_wait(bar_ld, ph_ld);
-          tc_fence_after();
-          NERFCA_TL(true, 3000);
-          umma_k<8, KK, KK>(td_acc, kmajor(h2), kmajor(w3), id_fwd, 0);
-          umma_commit(bar_acc);
-        }
-        __syncwarp();
-      }
-      ph_ld ^= 1;
-      uint32_t va[32], vb[32], h3w[32], w[32];
-      // ---- H3 = relu(Z3 + b3) -> shared memory (B operand of wgrad 4) and tensor memory (A operand of Z4)
-      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
-      tc_fence_after();
+      uint32_t va[32], vb[32], w[32];
+      // ---- step A: R = dZ4' = d_raw 1[H4 > 0] (shared memory, A of wgrad 4), A = dZ4 = dZ4' w_out (tensor memory, A of dgrad 4)
+      mbar_wait(bar_ldm, par);
+      if (i > 0) mbar_wait(bar_tile, par ^ 1);      // weight gradient 3 of the previous tile has released the R / S buffers
       NERFCA_TL(warp == 1 && lane == 0, 1010);
-      ld_acc64(k_acc, va, vb);
-      NERFCA_TL(warp == 1 && lane == 0, 1011);
-      relu_bias_pack64(va, vb, k_bias3, h3w);
-      tmem_st32(k_a, h3w);
-      sts_row64(h3 + k_rowoff, h3w);
-      NERFCA_TL(warp == 1 && lane == 0, 1012);
-      tmem_st_wait();
-      tc_fence_before();
-      fence_proxy_async();
-      NERFCA_TL(warp == 1 && lane == 0, 1013);
-      named_bar_sync(1, 256);
-      NERFCA_TL(warp == 1 && lane == 0, 1014);
-
-      if (warp == 0) {
-        tc_fence_after();
-        if (elect_one()) {
-          NERFCA_TL(true, 3010);
-          umma_ts_k<8, KK>(td_acc, td_a, kmajor(w4), id_fwd, 0);        // Z4 = H3 W4^T
-          umma_commit(bar_acc);
-          NERFCA_TL(true, 3011);
-        }
-        __syncwarp();
-      }
-      // ---- Z4 -> R = dZ4' = d_raw 1[Z4 + b4 > 0] (shared memory, A of wgrad 4), A = dZ4 = dZ4' w_out (tensor memory, A of dgrad 4)
-      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
-      tc_fence_after();
-      NERFCA_TL(warp == 1 && lane == 0, 1020);
-      ld_acc64(k_acc, va, vb);
-      NERFCA_TL(warp == 1 && lane == 0, 1021);
       {
-        const float g_cur = s_g[(i & 1) * 128 + row];
+        const float g_cur = s_g[par * 128 + row];
         const uint32_t gb = pack_bf16x2(g_cur, g_cur);
+        if (ch == 0) gb_sum += g_cur;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t* v = half ? vb : va;
+        for (int c = 0; c < 4; ++c) {
+          const uint4 mb = lds_u4(k_m4 + (uint32_t)c * CHUNK_BYTES);      // 16 pattern bytes = 16 columns
+          const uint32_t m[4] = {mb.x, mb.y, mb.z, mb.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = lds_f4(k_bias3 + 512u + (uint32_t)(half * 32 + 4 * j) * 4u);     // bias4 sits 128 floats behind bias3
-            const float2 p0 = add_f32x2(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b.x, b.y));
-            const float2 p1 = add_f32x2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b.z, b.w));
-            w[half * 16 + 2 * j] = pack_bf16x2(p0.x, p0.y);
-            w[half * 16 + 2 * j + 1] = pack_bf16x2(p1.x, p1.y);
+          for (int e = 0; e < 4; ++e) {
+            // byte b of the word -> bf16 halfword b << 8 (> 0 exactly when H4 was): columns (4e, 4e+1) and (4e+2, 4e+3) of the chunk
+            w[8 * c + 2 * e] = mul_bf16x2(relu_mask_bf16x2(__byte_perm(m[e], 0u, 0x1404)), gb);
+            w[8 * c + 2 * e + 1] = mul_bf16x2(relu_mask_bf16x2(__byte_perm(m[e], 0u, 0x3424)), gb);
           }
         }
-#pragma unroll
-        for (int i2 = 0; i2 < 32; ++i2) w[i2] = mul_bf16x2(relu_mask_bf16x2(w[i2]), gb);     // dZ4'
-        sts_row64(k_r + k_rowoff, w);
+        sts_row64(R + k_rowoff, w);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint4 wo = lds_u4(k_wo2 + (uint32_t)c * 16u);
@@ -925,80 +885,73 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
           w[4 * c + 3] = mul_bf16x2(w[4 * c + 3], wo.w);
         }
         tmem_st32(k_a, w);
-        if (ch == 0) gb_sum += g_cur;
       }
-      NERFCA_TL(warp == 1 && lane == 0, 1022);
+      tmem_st_wait();
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_mfree);        // the pattern and d_raw of this tile have been consumed
+      NERFCA_TL(warp == 1 && lane == 0, 1013);
+      named_bar_sync(1, 256);
+      NERFCA_TL(warp == 1 && lane == 0, 1014);
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+          NERFCA_TL(true, 3010);
+          umma_ts_k<8, KM>(td_acc, td_a, mnmajor(w4), id_dgrad, 0);                                  // dH3 = dZ4 W4
+          umma_commit(bar_acc);
+          mbar_wait(bar_ldh, par);
+          tc_fence_after();
+          umma_k<8, KM, KM>(tmem + TOP_WG4, mnmajor(R), mnmajor(h3), id_wgrad, first);               // WG4 += R^T H3
+          umma_k<8, KM, KM>(tmem + TOP_BG4, mnmajor(R), mnmajor(ones), id_side, first);              // BG4 += colsum(R)
+          umma_commit(bar_half);
+          NERFCA_TL(true, 3011);
+        }
+        __syncwarp();
+      }
+      // ---- step B: dZ3 = dH3 * 1[H3 > 0] -> S (shared memory, A of wgrad 3) and tensor memory (A of dgrad 3)
+      mbar_wait(bar_ldh, par);
+      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
+      tc_fence_after();
+      NERFCA_TL(warp == 1 && lane == 0, 1020);
+      ld_acc64(k_acc, va, vb);
+      masked_grad_pack64(va, vb, h3 + k_rowoff, w);
+      NERFCA_TL(warp == 1 && lane == 0, 1021);
+      tmem_st32(k_a, w);
+      sts_row64(S + k_rowoff, w);
       tmem_st_wait();
       tc_fence_before();
       fence_proxy_async();
       NERFCA_TL(warp == 1 && lane == 0, 1023);
       named_bar_sync(1, 256);
       NERFCA_TL(warp == 1 && lane == 0, 1024);
-
       if (warp == 0) {
         tc_fence_after();
         if (elect_one()) {
           NERFCA_TL(true, 3020);
-          umma_ts_k<8, KM>(td_acc, td_a, mnmajor(w4), id_dgrad, 0);                                  // dH3 = dZ4 W4
+          umma_ts_k<8, KM>(td_acc, td_a, mnmajor(w3), id_dgrad, 0);                                  // dH2 = dZ3 W3
           umma_commit(bar_acc);
-          umma_k<8, KM, KM>(tmem + TOP_WG4, mnmajor(k_r), mnmajor(h3), id_wgrad, first);             // WG4 += R^T [H3 | 1]
+          umma_k<8, KM, KM>(tmem + TOP_WG3, mnmajor(S), mnmajor(h2), id_wgrad, first);               // WG3 += S^T H2
+          umma_k<8, KM, KM>(tmem + TOP_BG3, mnmajor(S), mnmajor(ones), id_side, first);              // BG3 += colsum(S)
+          umma_commit(bar_tile);
           NERFCA_TL(true, 3021);
-          umma_commit(bar_h3dead);     // H3's buffer may take the next tile's H2 (the ReLU pattern of H3 lives in registers)
         }
         __syncwarp();
       }
-      // ---- dZ3 = dH3 * 1[H3 > 0] -> S (shared memory, A of wgrad 3) and tensor memory (A of dgrad 3)
+      // ---- step C: dZ2 = dH2 * 1[H2 > 0] -> hand-off buffer (tile-canonical bytes, straight from registers)
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
       NERFCA_TL(warp == 1 && lane == 0, 1030);
       ld_acc64(k_acc, va, vb);
-      NERFCA_TL(warp == 1 && lane == 0, 1031);
-      masked_grad_pack64(va, vb, h3w, w);
-      tmem_st32(k_a, w);
-      sts_row64(k_s + k_rowoff, w);
-      NERFCA_TL(warp == 1 && lane == 0, 1032);
-      tmem_st_wait();
-      tc_fence_before();
-      fence_proxy_async();
-      NERFCA_TL(warp == 1 && lane == 0, 1033);
-      named_bar_sync(1, 256);
-      NERFCA_TL(warp == 1 && lane == 0, 1034);
-
-      if (warp == 0) {
-        tc_fence_after();
-        if (elect_one()) {
-          NERFCA_TL(true, 3030);
-          umma_ts_k<8, KM>(td_acc, td_a, mnmajor(w3), id_dgrad, 0);                                  // dH2 = dZ3 W3
-          umma_commit(bar_acc);
-          umma_k<8, KM, KM>(tmem + TOP_WG3, mnmajor(k_s), mnmajor(h2), id_wgrad, first);             // WG3 += S^T [H2 | 1]
-          NERFCA_TL(true, 3031);
-        }
-        __syncwarp();
-      }
-      // ---- dZ2 = dH2 * 1[H2 > 0] -> hand-off buffer (tile-canonical bytes, straight from registers)
+      masked_grad_pack64(va, vb, h2 + k_rowoff, w);
       {
-        mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
-        tc_fence_after();
-        NERFCA_TL(warp == 1 && lane == 0, 1040);
-        ld_acc64(k_acc, va, vb);
-        NERFCA_TL(warp == 1 && lane == 0, 1041);
         uint8_t* dst = nt.handoff + (size_t)tile * TILE_BYTES + k_rowoff;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 hv = lds_u4(h2 + k_rowoff + (uint32_t)c * CHUNK_BYTES);
-          const uint32_t* v = (c < 4) ? va : vb;
-          const int j = (c & 3) * 8;
-          uint4 o;
-          o.x = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), relu_mask_bf16x2(hv.x));
-          o.y = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), relu_mask_bf16x2(hv.y));
-          o.z = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])), relu_mask_bf16x2(hv.z));
-          o.w = mul_bf16x2(pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])), relu_mask_bf16x2(hv.w));
-          __stcs(reinterpret_cast<uint4*>(dst + c * CHUNK_BYTES), o);
-        }
+        for (int c = 0; c < 8; ++c)
+          __stcs(reinterpret_cast<uint4*>(dst + c * CHUNK_BYTES), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
       }
-      NERFCA_TL(warp == 1 && lane == 0, 1043);
       tc_fence_before();
-      named_bar_sync(1, 256);      // the accumulator has been read: the next tile's Z3 may overwrite it
+      NERFCA_TL(warp == 1 && lane == 0, 1033);
     }
     // ---- flush the TMEM-resident accumulators
     if (ch == 0) {
@@ -1007,13 +960,15 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
       if (lane == 0 && nt.g_b[5]) atomicAdd(s_gbout, gb_sum);
     }
     if (n_my > 0) {
+      named_bar_sync(1, 256);
       if (warp == 0) {
         if (elect_one()) umma_commit(bar_done);
         __syncwarp();
       }
       mbar_wait(bar_done, 0);
       tc_fence_after();
-      const float wo_row = s_f[256 + row], b4_row = s_f[128 + row];
+      const float* fb = reinterpret_cast<const float*>(nt.pack + nt.f32_off);
+      const float wo_row = s_wo[row], b4_row = __ldg(fb + 4 * 128 + row);
       // dw_out[row] = sum_k W4[row, k] (R^T H3)[row, k] + b4[row] colsum(R)[row]   (this thread: its 64 columns, then the bias term)
       float dot = 0.f;
       for (int c0 = ch * 64; c0 < ch * 64 + 64; c0 += 16) {
@@ -1032,12 +987,12 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
       }
       flush_wgrad_scaled(t_lane, TOP_WG4, nt.g_w[4], row, ch, wo_row);
       flush_wgrad_scaled(t_lane, TOP_WG3, nt.g_w[3], row, ch, 1.f);
-      uint32_t vb4[16], vb3[16];
-      tmem_ld16(t_lane + TOP_WG4 + 128, vb4);
-      tmem_ld16(t_lane + TOP_WG3 + 128, vb3);
-      tmem_ld_wait();
-      const float cs4 = __uint_as_float(vb4[0]), cs3 = __uint_as_float(vb3[0]);
       if (ch == 0) {
+        uint32_t v4[16], v3[16];
+        tmem_ld16(t_lane + TOP_BG4, v4);
+        tmem_ld16(t_lane + TOP_BG3, v3);
+        tmem_ld_wait();
+        const float cs4 = __uint_as_float(v4[0]), cs3 = __uint_as_float(v3[0]);
         if (nt.g_b[4]) atomicAdd(nt.g_b[4] + row, wo_row * cs4);
         if (nt.g_b[3]) atomicAdd(nt.g_b[3] + row, cs3);
         dot = fmaf(b4_row, cs4, dot);
@@ -1055,16 +1010,18 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
 // =====================================================================================================================
 // backward, bottom pass: layers 2, 1, 0 (+ latent gradients)
 // =====================================================================================================================
+// Loads dZ2 (hand-off from the top pass), H1 and H0 (forward stash); nothing is recomputed except the encoded input X0, which
+// four producer warps rebuild one tile ahead.  Two chain steps per tile
+//     dgrad 2 -> dZ1 = (.) 1[H1 > 0] -> dgrad 1 -> dZ0 = (.) 1[H0 > 0]
+// plus the weight-gradient GEMMs (dZ2^T H1, dZ1^T H0, dZ0^T X0) and their bias companions, which run while the epilogue converts.
+// Four 32 KB buffers rotate: role k of tile i (0: dZ2 and later dZ0, 1: H1, 2: H0, 3: dZ1) lives in buffer (i + k) % 4; the load
+// of dZ2 of tile i + 1 goes into H1's buffer as soon as weight gradient 2 is complete and step B has read H1's ReLU pattern, the
+// loads of H1 / H0 into the H0 / dZ1 buffers when weight gradient 1 is complete.
+// TMEM: ACC [0,128) | WG2 [128,256) | WG1 [256,384) | WG0 [384,480) | BG2 [480,496) | BG1 [496,512)
 constexpr uint32_t BOT_ACC = 0, BOT_WG2 = 128, BOT_WG1 = 256, BOT_WG0 = 384, BOT_BG2 = 480, BOT_BG1 = 496;
+constexpr int BOT_THREADS = 16 * 32;   // warps 0-7 epilogue (warp 0 holds the issuing lane), 8-11 X0 producers, 12 loader, 13-15 idle
 
-// Four 32 KB tile buffers form a ring; every tile makes five allocations in this order
-//   a0 dZ2 (loaded)  a1 H0 (loaded)  a2 H1 (recomputed)  a3 dZ1  a4 dZ0
-// allocation k = 5 * i + j lives in buffer k % 4, i.e. in the buffer of allocation k - 4 = a_{j+1} of tile i - 1 (j < 4)
-// or a0 of the same tile (j = 4), and may be filled once that one is dead.  "Dead" is one tcgen05.commit issued by the MMA
-// thread after the last GEMM reading the buffer (and after the epilogue finished reading its ReLU pattern) on the barrier
-// of the DYING allocation's role, dead[j]: it completes exactly once per tile and has exactly one waiting role, so every
-// waiter consumes every phase in order (a parity wait is only sound under that condition).
-// smem: [W1][W2][ring 4 x 32 KB][X0: 96 * 256][W0 latent chunks 4 KB][side 4 KB][bias1 (128 f32)][latent acc 512 f32][barriers]
+// smem: [W1][W2][4 tile buffers][X0: 96 * 256][W0 latent chunks 4 KB][ones tile 4 KB][latent acc 256 f32][barriers]
 __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1078,35 +1035,31 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
   const int lat_n = has_lat ? ((nt.enc_dim % 8 + nt.n_latent + 15) / 16) * 16 : 0;   // MMA N covering them
   uint8_t* s_w1 = smem;
   uint8_t* s_w2 = smem + TILE_BYTES;
-  uint8_t* s_ring = smem + 2 * TILE_BYTES;
+  uint8_t* s_buf = smem + 2 * TILE_BYTES;
   uint8_t* s_x0 = smem + 6 * TILE_BYTES;
   uint8_t* s_w0lat = s_x0 + 96 * 256;
-  uint8_t* s_side = s_w0lat + 4096;
-  float* s_bias1 = reinterpret_cast<float*>(s_side + 4096);
-  float* s_lat = s_bias1 + 128;
+  uint8_t* s_ones = s_w0lat + 4096;
+  float* s_lat = reinterpret_cast<float*>(s_ones + 4096);
   const int n_lat_acc = has_lat ? nt.n_phases * nt.n_latent : 0;            // <= 256 checked on the host
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_lat + 256);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
-  const uint32_t bar_w = smem_u32(s_bar), bar_ld_dz = bar_w + 8, bar_ld_h0 = bar_w + 16, bar_acc = bar_w + 24, bar_e = bar_w + 32,
-                 bar_x0 = bar_w + 40, bar_x0free = bar_w + 48, bar_accfree = bar_w + 56, bar_done = bar_w + 64, bar_dead0 = bar_w + 72;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 10);
+  const uint32_t bar_w = smem_u32(s_bar), bar_ld_dz = bar_w + 8, bar_ld_h1 = bar_w + 16, bar_ld_h0 = bar_w + 24, bar_acc = bar_w + 32,
+                 bar_free1 = bar_w + 40, bar_free2 = bar_w + 48, bar_x0 = bar_w + 56, bar_x0free = bar_w + 64, bar_done = bar_w + 72;
 
-  if (warp == 8) {
+  if (warp == 12) {
     if (lane == 0) {
-      mbar_init(bar_w, 1); mbar_init(bar_ld_dz, 1); mbar_init(bar_ld_h0, 1); mbar_init(bar_acc, 1); mbar_init(bar_e, 256);
-      mbar_init(bar_x0, 128); mbar_init(bar_x0free, 1); mbar_init(bar_accfree, 256); mbar_init(bar_done, 1);
-      for (int b = 0; b < 5; ++b) mbar_init(bar_dead0 + 8 * b, 1);
+      mbar_init(bar_w, 1); mbar_init(bar_ld_dz, 1); mbar_init(bar_ld_h1, 1); mbar_init(bar_ld_h0, 1); mbar_init(bar_acc, 1);
+      mbar_init(bar_free1, 1); mbar_init(bar_free2, 1); mbar_init(bar_x0, 4); mbar_init(bar_x0free, 1); mbar_init(bar_done, 1);
       mbar_init_fence();
     }
     __syncwarp();
     tmem_alloc(smem_u32(s_tmem), 512);
   }
   {
-    const float* fb = reinterpret_cast<const float*>(nt.pack + nt.f32_off);
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_bias1[i] = __ldg(fb + 128 + i);
     for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x) s_lat[i] = 0.f;
-    // side tile: column 0 == 1 in every row (bias gradients = column sums of dZ)
+    // ones tile: column 0 == 1 in every row (bias gradients = column sums of dZ)
     for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
-      reinterpret_cast<uint4*>(s_side)[i] = (i < 128) ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+      reinterpret_cast<uint4*>(s_ones)[i] = (i < 128) ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
   }
   tc_fence_before();
   fence_proxy_async();
@@ -1114,111 +1067,37 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
   const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
-  auto ring = [&](long long k) -> uint8_t* { return s_ring + (size_t)(k & 3) * TILE_BYTES; };
   [[maybe_unused]] int tl_n = 0;
-  // role j of tile i may be filled: j < 4 waits for the death of role j + 1 of tile i - 1, j == 4 for role 0 of tile i
-  auto wait_free = [&](long long i, int j) {
-    if (j == 4) mbar_wait(bar_dead0, (uint32_t)(i & 1));
-    else if (i > 0) mbar_wait(bar_dead0 + 8 * (uint32_t)(j + 1), (uint32_t)((i - 1) & 1));
-  };
 
-  if (warp == 8) {
-    // ================= MMA warp =================
-    if (lane == 0) {
+  if (warp >= 12) {
+    // ================= warp 12: loader (warps 13-15 only fill the warpgroup) =================
+    reg_dealloc<24>();
+    if (warp == 12 && lane == 0) {
       const uint32_t lat_bytes = has_lat ? (uint32_t)(lat_n / 8) * CHUNK_BYTES : 0u;
       mbar_expect_tx(bar_w, 2 * TILE_BYTES + lat_bytes);
       bulk_g2s(smem_u32(s_w1), nt.pack + nt.w0_bytes, TILE_BYTES, bar_w);
       bulk_g2s(smem_u32(s_w2), nt.pack + nt.w0_bytes + (size_t)TILE_BYTES, TILE_BYTES, bar_w);
       if (has_lat) bulk_g2s(smem_u32(s_w0lat), nt.pack + (size_t)lat_c0 * CHUNK_BYTES, lat_bytes, bar_w);
-      mbar_wait(bar_w, 0);
-      const Desc w1_k = kmajor(smem_u32(s_w1)), w1_mn = mnmajor(smem_u32(s_w1)), w2_mn = mnmajor(smem_u32(s_w2)), side_mn = mnmajor(smem_u32(s_side)),
-                 x0_mn = mnmajor(smem_u32(s_x0)), w0lat_mn = mnmajor(smem_u32(s_w0lat));
-      constexpr uint32_t KK = KSTEP_KMAJOR, KM = KSTEP_MNMAJOR;
-      constexpr uint32_t id_fwd = instr_desc(128, 128, 0, 0), id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1),
-                         id_side = instr_desc(128, 16, 1, 1);
-      const uint32_t id_wg0 = instr_desc(128, kpad0, 1, 1), id_lat = instr_desc(128, lat_n > 0 ? lat_n : 16, 0, 1);
-      uint32_t ph_dz = 0, ph_h0 = 0, ph_e = 0, ph_x0 = 0, ph_accfree = 0;
-      for (long long i = 0; i < n_my; ++i) {
-        const long long k = 5 * i;
-        const uint32_t dz2 = smem_u32(ring(k)), h0 = smem_u32(ring(k + 1)), h1 = smem_u32(ring(k + 2)), dz1 = smem_u32(ring(k + 3)),
-                       dz0 = smem_u32(ring(k + 4));
-        const uint32_t first = (i > 0) ? 1u : 0u;
-        // Z1 = H0 W1^T
-        NERFCA_TL(true, 3000);
-        mbar_wait(bar_ld_h0, ph_h0); ph_h0 ^= 1;
-        NERFCA_TL(true, 3001);
-        if (i > 0) { mbar_wait(bar_accfree, ph_accfree); ph_accfree ^= 1; }
-        tc_fence_after();
-        NERFCA_TL(true, 3002);
-        umma_k<8, KK, KK>(tmem + BOT_ACC, kmajor(h0), w1_k, id_fwd, 0);
-        umma_commit(bar_acc);
-        // dgrad 2, wgrad 2, bias grad 2
-        NERFCA_TL(true, 3003);
-        mbar_wait(bar_e, ph_e); ph_e ^= 1;           // H1 written
-        NERFCA_TL(true, 3010);
-        mbar_wait(bar_ld_dz, ph_dz); ph_dz ^= 1;
-        tc_fence_after();
-        NERFCA_TL(true, 3011);
-        umma_k<8, KK, KM>(tmem + BOT_ACC, kmajor(dz2), w2_mn, id_dgrad, 0);
-        umma_commit(bar_acc);
-        umma_k<8, KM, KM>(tmem + BOT_WG2, mnmajor(dz2), mnmajor(h1), id_wgrad, first);
-        umma_k<8, KM, KM>(tmem + BOT_BG2, mnmajor(dz2), side_mn, id_side, first);
-        // dgrad 1, wgrad 1, bias grad 1
-        NERFCA_TL(true, 3012);
-        mbar_wait(bar_e, ph_e); ph_e ^= 1;           // dZ1 written, H1's pattern consumed
-        tc_fence_after();
-        NERFCA_TL(true, 3020);
-        umma_commit(bar_dead0 + 8 * 0);   // dZ2
-        umma_commit(bar_dead0 + 8 * 2);   // H1
-        umma_k<8, KK, KM>(tmem + BOT_ACC, kmajor(dz1), w1_mn, id_dgrad, 0);
-        umma_commit(bar_acc);
-        umma_k<8, KM, KM>(tmem + BOT_WG1, mnmajor(dz1), mnmajor(h0), id_wgrad, first);
-        umma_k<8, KM, KM>(tmem + BOT_BG1, mnmajor(dz1), side_mn, id_side, first);
-        // wgrad 0 (its constant-1 column is the bias gradient), latent dgrad
-        NERFCA_TL(true, 3021);
-        mbar_wait(bar_e, ph_e); ph_e ^= 1;           // dZ0 written, H0's pattern consumed
-        NERFCA_TL(true, 3030);
-        mbar_wait(bar_x0, ph_x0); ph_x0 ^= 1;
-        tc_fence_after();
-        NERFCA_TL(true, 3031);
-        umma_commit(bar_dead0 + 8 * 1);   // H0
-        umma_commit(bar_dead0 + 8 * 3);   // dZ1
-        umma_k<8, KM, KM>(tmem + BOT_WG0, mnmajor(dz0), x0_mn, id_wg0, first);
-        if (has_lat) {
-          umma_k<8, KK, KM>(tmem + BOT_ACC, kmajor(dz0), w0lat_mn, id_lat, 0);
-          umma_commit(bar_acc);
-        }
-        umma_commit(bar_dead0 + 8 * 4);   // dZ0
-        umma_commit(bar_x0free);
-        NERFCA_TL(true, 3032);
-      }
-      umma_commit(bar_done);
-    }
-    __syncwarp();
-  } else if (warp == 9) {
-    // ================= load warp =================
-    if (lane == 0) {
+      uint32_t ph1 = 0, ph2 = 0;
       for (long long i = 0; i < n_my; ++i) {
         const long long tile = worker + i * n_workers;
-        const long long k = 5 * i;
-        NERFCA_TL(true, 2000);
-        wait_free(i, 1);
-        NERFCA_TL(true, 2001);
-        mbar_expect_tx(bar_ld_h0, TILE_BYTES);
-        bulk_g2s(smem_u32(ring(k + 1)), nt.stash + (size_t)tile * STASH_TILES * TILE_BYTES, TILE_BYTES, bar_ld_h0);
-        wait_free(i, 0);
-        NERFCA_TL(true, 2002);
+        const uint8_t* st = nt.stash + (size_t)tile * STASH_STRIDE;
+        if (i > 0) { mbar_wait(bar_free1, ph1); ph1 ^= 1; }     // H1's buffer of tile i - 1
         mbar_expect_tx(bar_ld_dz, TILE_BYTES);
-        bulk_g2s(smem_u32(ring(k)), nt.handoff + (size_t)tile * TILE_BYTES, TILE_BYTES, bar_ld_dz);
+        bulk_g2s(smem_u32(s_buf + (size_t)(i & 3) * TILE_BYTES), nt.handoff + (size_t)tile * TILE_BYTES, TILE_BYTES, bar_ld_dz);
+        if (i > 0) { mbar_wait(bar_free2, ph2); ph2 ^= 1; }     // H0's and dZ1's buffers of tile i - 1
+        mbar_expect_tx(bar_ld_h1, TILE_BYTES);
+        bulk_g2s(smem_u32(s_buf + (size_t)((i + 1) & 3) * TILE_BYTES), st + (size_t)TILE_BYTES, TILE_BYTES, bar_ld_h1);
+        mbar_expect_tx(bar_ld_h0, TILE_BYTES);
+        bulk_g2s(smem_u32(s_buf + (size_t)((i + 2) & 3) * TILE_BYTES), st, TILE_BYTES, bar_ld_h0);
       }
     }
     __syncwarp();
-  } else if (warp == 10) {
-    // nothing to store in this pass
-  } else if (warp >= 11) {
+  } else if (warp >= 8) {
     // ================= 4 X0 warps: thread = tile row; the encoded input is only needed by the last GEMM of a tile, so these
     // warps run about one tile ahead of the rest of the CTA =================
-    const int row = (warp - 11) * 32 + lane;
+    reg_dealloc<64>();
+    const int row = (warp - 8) * 32 + lane;
     uint32_t ph_x0free = 0;
     RowIn rin;
     {
@@ -1233,67 +1112,114 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
       emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight, nt.x0.enc.latents, SmemSink{s_x0, row}, 0);
       emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight, nt.x0.enc.latents, SmemSink{s_x0, row}, 1);
       fence_proxy_async();
-      mbar_arrive(bar_x0);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_x0);
     }
   } else {
-    // ================= 8 epilogue warps =================
+    // ================= 8 epilogue warps: thread = (row, column half); the elected lane of warp 0 issues =================
+    reg_alloc<200>();
     const int q = warp & 3, ch = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
-    const uint32_t t_acc = t_lane + BOT_ACC + ch * 64;
+    uint32_t k_acc = t_lane + BOT_ACC + ch * 64;
+    uint32_t k_rowoff = (uint32_t)(ch * 8) * CHUNK_BYTES + (uint32_t)row * 16u;     // this thread's first chunk inside a tile
+    uint32_t k_buf = smem_u32(s_buf);
+    pin(k_acc); pin(k_rowoff); pin(k_buf);
+    const uint32_t w1 = smem_u32(s_w1), w2 = smem_u32(s_w2), ones = smem_u32(s_ones), x0 = smem_u32(s_x0), w0lat = smem_u32(s_w0lat);
+    constexpr uint32_t KK = KSTEP_KMAJOR, KM = KSTEP_MNMAJOR;
+    constexpr uint32_t id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1), id_side = instr_desc(128, 16, 1, 1);
+    const uint32_t id_wg0 = instr_desc(128, kpad0, 1, 1), id_lat = instr_desc(128, lat_n > 0 ? lat_n : 16, 0, 1);
+    const uint32_t td_acc = tmem + BOT_ACC;
     uint32_t ph_acc = 0;
+    mbar_wait(bar_w, 0);
     for (long long i = 0; i < n_my; ++i) {
       const long long tile = worker + i * n_workers;
       const long long p = tile * TILE_M + row;
       const bool valid = p < a.src.n_points;
-      const long long k = 5 * i;
-      uint32_t va[32], vb[32];
-      // ---- H1 = relu(Z1 + b1)
-      NERFCA_TL(threadIdx.x == 0, 1000);
+      const uint32_t par = (uint32_t)(i & 1);
+      const uint32_t dz2 = k_buf + (uint32_t)(i & 3) * TILE_BYTES, h1 = k_buf + (uint32_t)((i + 1) & 3) * TILE_BYTES,
+                     h0 = k_buf + (uint32_t)((i + 2) & 3) * TILE_BYTES, dz1 = k_buf + (uint32_t)((i + 3) & 3) * TILE_BYTES, dz0 = dz2;
+      const uint32_t first = (i > 0) ? 1u : 0u;
+      uint32_t va[32], vb[32], w[32];
+      // ---- issue dgrad 2: dH1 = dZ2 W2 (the barrier that closed the previous tile released the accumulator)
+      if (warp == 0) {
+        if (elect_one()) {
+          mbar_wait(bar_ld_dz, par);
+          tc_fence_after();
+          NERFCA_TL(true, 3000);
+          umma_k<8, KK, KM>(td_acc, kmajor(dz2), mnmajor(w2), id_dgrad, 0);
+          umma_commit(bar_acc);
+          mbar_wait(bar_ld_h1, par);
+          tc_fence_after();
+          umma_k<8, KM, KM>(tmem + BOT_WG2, mnmajor(dz2), mnmajor(h1), id_wgrad, first);             // WG2 += dZ2^T H1
+          umma_k<8, KM, KM>(tmem + BOT_BG2, mnmajor(dz2), mnmajor(ones), id_side, first);            // BG2 += colsum(dZ2)
+          NERFCA_TL(true, 3001);
+        }
+        __syncwarp();
+      }
+      // ---- step B: dZ1 = dH1 * 1[H1 > 0] -> shared memory (A of dgrad 1 and of wgrad 1)
+      mbar_wait(bar_ld_h1, par);
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
-      NERFCA_TL(threadIdx.x == 0, 1001);
-      ld_acc64(t_acc, va, vb);
-      NERFCA_TL(threadIdx.x == 0, 1002);
-      wait_free(i, 2);
-      NERFCA_TL(threadIdx.x == 0, 1003);
-      relu_bias_store(va, vb, s_bias1, ring(k + 2), row, ch);
-      NERFCA_TL(threadIdx.x == 0, 1004);
+      NERFCA_TL(warp == 1 && lane == 0, 1010);
+      ld_acc64(k_acc, va, vb);
+      masked_grad_pack64(va, vb, h1 + k_rowoff, w);
+      NERFCA_TL(warp == 1 && lane == 0, 1011);
+      sts_row64(dz1 + k_rowoff, w);
       tc_fence_before();
       fence_proxy_async();
-      mbar_arrive(bar_e);
-      NERFCA_TL(threadIdx.x == 0, 1005);
-      // ---- dZ1 = (dZ2 W2) * 1[H1 > 0]
+      named_bar_sync(1, 256);
+      NERFCA_TL(warp == 1 && lane == 0, 1014);
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+          NERFCA_TL(true, 3010);
+          umma_commit(bar_free1);      // wgrad 2 complete and H1's pattern read: H1's buffer may take dZ2 of the next tile
+          umma_k<8, KK, KM>(td_acc, kmajor(dz1), mnmajor(w1), id_dgrad, 0);                          // dH0 = dZ1 W1
+          umma_commit(bar_acc);
+          mbar_wait(bar_ld_h0, par);
+          tc_fence_after();
+          umma_k<8, KM, KM>(tmem + BOT_WG1, mnmajor(dz1), mnmajor(h0), id_wgrad, first);             // WG1 += dZ1^T H0
+          umma_k<8, KM, KM>(tmem + BOT_BG1, mnmajor(dz1), mnmajor(ones), id_side, first);            // BG1 += colsum(dZ1)
+          NERFCA_TL(true, 3011);
+        }
+        __syncwarp();
+      }
+      // ---- step C: dZ0 = dH0 * 1[H0 > 0] -> shared memory (A of wgrad 0), into the buffer dZ2 occupied
+      mbar_wait(bar_ld_h0, par);
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
-      ld_acc64(t_acc, va, vb);
-      NERFCA_TL(threadIdx.x == 0, 1012);
-      wait_free(i, 3);
-      NERFCA_TL(threadIdx.x == 0, 1013);
-      masked_grad_store(va, vb, ring(k + 2), ring(k + 3), row, ch);
-      NERFCA_TL(threadIdx.x == 0, 1014);
+      NERFCA_TL(warp == 1 && lane == 0, 1020);
+      ld_acc64(k_acc, va, vb);
+      masked_grad_pack64(va, vb, h0 + k_rowoff, w);
+      NERFCA_TL(warp == 1 && lane == 0, 1021);
+      mbar_wait(bar_free1, par);       // weight gradient 2 no longer reads dZ2
+      sts_row64(dz0 + k_rowoff, w);
       tc_fence_before();
       fence_proxy_async();
-      mbar_arrive(bar_e);
-      NERFCA_TL(threadIdx.x == 0, 1015);
-      // ---- dZ0 = (dZ1 W1) * 1[H0 > 0]
-      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
-      tc_fence_after();
-      ld_acc64(t_acc, va, vb);
-      NERFCA_TL(threadIdx.x == 0, 1022);
-      wait_free(i, 4);
-      NERFCA_TL(threadIdx.x == 0, 1023);
-      masked_grad_store(va, vb, ring(k + 1), ring(k + 4), row, ch);
-      NERFCA_TL(threadIdx.x == 0, 1024);
-      tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(bar_e);
-      NERFCA_TL(threadIdx.x == 0, 1025);
-      // ---- latent gradient: columns [enc_dim, enc_dim + T) of dX0 sit at accumulator columns enc_dim - 8 * lat_c0 + t
+      named_bar_sync(1, 256);
+      NERFCA_TL(warp == 1 && lane == 0, 1024);
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+          NERFCA_TL(true, 3020);
+          umma_commit(bar_free2);      // wgrad 1 complete and H0's pattern read: the H0 / dZ1 buffers may be reloaded
+          mbar_wait(bar_x0, par);
+          tc_fence_after();
+          umma_k<8, KM, KM>(tmem + BOT_WG0, mnmajor(dz0), mnmajor(x0), id_wg0, first);               // WG0 += dZ0^T X0
+          umma_commit(bar_x0free);
+          if (has_lat) {
+            umma_k<8, KK, KM>(td_acc, kmajor(dz0), mnmajor(w0lat), id_lat, 0);                       // latent columns of dX0
+            umma_commit(bar_acc);
+          }
+          NERFCA_TL(true, 3021);
+        }
+        __syncwarp();
+      }
+      // ---- latent gradient (fallback): columns [enc_dim, enc_dim + T) of dX0 sit at accumulator columns enc_dim - 8 * lat_c0 + t
       if (has_lat) {
         mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
         tc_fence_after();
-        NERFCA_TL(threadIdx.x == 0, 1030);
         if (ch == 0) {
           // a warp's 32 rows are consecutive samples, almost always of one ray (one phase): reduce over the warp
           // first and add once; rows of a warp that straddles two rays fall back to per-lane atomics
@@ -1321,11 +1247,15 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
           }
         }
         tc_fence_before();
+        named_bar_sync(1, 256);        // the accumulator has been read: the next tile's dgrad 2 may overwrite it
       }
-      mbar_arrive(bar_accfree);
-      NERFCA_TL(threadIdx.x == 0, 1035);
+      // (without the fallback the accumulator was last read before the barrier of step C)
     }
     if (n_my > 0) {
+      if (warp == 0) {
+        if (elect_one()) umma_commit(bar_done);
+        __syncwarp();
+      }
       mbar_wait(bar_done, 0);
       tc_fence_after();
       flush_wgrad(t_lane, BOT_WG2, nt.g_w[2], row, ch, 128, 128);
@@ -1354,8 +1284,8 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
       if (onehot && nt.g_lat) {
         // S[n][ph] = sum over the samples of phase ph of dZ0[.][n] sits in columns in_dim + 1 + ph of wgrad 0 (all inside the
         // last 16-column group); d latents[ph][t] = sum_n S[n][ph] * W0[n][enc_dim + t].  S goes through shared memory (the
-        // ring is idle now) so that one thread per (ph, t) can run the 128-term dot product.
-        float* s_S = reinterpret_cast<float*>(s_ring);
+        // tile buffers are idle now) so that one thread per (ph, t) can run the 128-term dot product.
+        float* s_S = reinterpret_cast<float*>(s_buf);
         const int cg = kpad0 - 16;
         if (ch == (cg >> 6)) {
           uint32_t v[16];
@@ -1385,20 +1315,20 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
   if (nt.g_lat && has_lat)
     for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x)
       if (s_lat[i] != 0.f) atomicAdd(nt.g_lat + i, s_lat[i]);
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == 12) tmem_dealloc(tmem, 512);
 }
 
 // =====================================================================================================================
 // host side
 // =====================================================================================================================
 static size_t fwd_smem_bytes(const NetDims& d) { return (((size_t)d.pack_bytes + 127) & ~(size_t)127) + 10 * 8 + (32 + 256) * 4; }
-constexpr size_t TOP_SMEM = 4 * (size_t)TILE_BYTES + 2 * (size_t)HBUF_BYTES + 384 * 4 + 64 * 4 + 256 * 4 + 16 + 6 * 8 + 16;
-constexpr size_t BOT_SMEM = 6 * (size_t)TILE_BYTES + 96 * 256 + 4096 + 4096 + 128 * 4 + 256 * 4 + 16 * 8 + 16;
+constexpr size_t TOP_SMEM = 6 * (size_t)TILE_BYTES + 4096 + MASK_BYTES + 128 * 4 + 64 * 4 + 256 * 4 + 16 + 8 * 8 + 16;
+constexpr size_t BOT_SMEM = 6 * (size_t)TILE_BYTES + 96 * 256 + 4096 + 4096 + 256 * 4 + 10 * 8 + 16;
 
 static size_t n_tiles_of(long long P) { return (size_t)((P + TILE_M - 1) / TILE_M); }
 
 // stash: [net][tile][2][32 KB]
-size_t tc_stash_bytes_n(int n_nets, long long P) { return (size_t)n_nets * n_tiles_of(P) * STASH_TILES * TILE_BYTES; }
+size_t tc_stash_bytes_n(int n_nets, long long P) { return (size_t)n_nets * n_tiles_of(P) * STASH_STRIDE; }
 // workspace: [packed blocks][hand-off: net, tile, 32 KB (backward only)]
 static size_t tc_pack_bytes_n(const nerfca_field_t* const* f, int n_nets) {
   size_t n = 0;
@@ -1460,7 +1390,7 @@ int tc_fields_forward(const nerfca_field_t* const* f, int n_nets, const nerfca_s
     n.pack = (const uint8_t*)workspace + off;
     off += pack_stride(d);
     n.raw_out = raw_out[i];
-    n.stash = stash ? (uint8_t*)stash + (size_t)i * a.n_tiles * STASH_TILES * TILE_BYTES : nullptr;
+    n.stash = stash ? (uint8_t*)stash + (size_t)i * a.n_tiles * STASH_STRIDE : nullptr;
     n.x0 = make_x0(*f[i], d);
     n.w0_bytes = d.w0_bytes; n.wout_off = d.wout_off; n.f32_off = d.f32_off; n.pack_bytes = d.pack_bytes;
     const size_t sm = fwd_smem_bytes(d);
@@ -1504,7 +1434,7 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
     BwdNet& n = a.net[i];
     n.pack = (const uint8_t*)workspace + off;
     off += pack_stride(d);
-    n.stash = (const uint8_t*)stash + (size_t)i * a.n_tiles * STASH_TILES * TILE_BYTES;
+    n.stash = (const uint8_t*)stash + (size_t)i * a.n_tiles * STASH_STRIDE;
     n.handoff = handoff + (size_t)i * a.n_tiles * TILE_BYTES;
     n.d_raw = d_raw[i];
     for (int l = 0; l < NERFCA_MAX_LAYERS; ++l) { n.g_w[l] = gr[i]->weight[l]; n.g_b[l] = gr[i]->bias[l]; }
