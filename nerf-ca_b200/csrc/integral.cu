@@ -1,5 +1,6 @@
 // X-ray line integral (A9), its autograd, and the fused training loss + closed-form dL/d_raw (A9 + A10).
-// One warp per ray; ray sums by warp shuffle; HBM traffic = the raw field outputs in, sigma / gradients out.
+// One warp per ray (one CTA per ray in the fused loss kernel); ray sums by warp shuffle; HBM traffic = the raw field outputs in,
+// sigma / gradients out.
 #include "common.cuh"
 
 namespace nerfca {
@@ -78,25 +79,48 @@ struct LossCfg {
 };
 
 // Fused A9 + A10 + closed-form backward (SURVEY 8(a')), training dtypes (float64 ray sums).
-// One warp per ray; sigma_s / sigma_d of the ray live in shared memory between the three sweeps.
+// One CTA of LOSS_THREADS threads per ray (a warp per ray leaves the SMs at ~10 % occupancy for 1024 rays, and the fp64 logarithms
+// make the kernel latency bound); sigma_s / sigma_d of the ray live in shared memory between the three sweeps, the ray sums go
+// through warp shuffles and a small shared-memory exchange (fixed order: the result does not depend on scheduling).
+constexpr int LOSS_THREADS = 128;
+// sums `v[0..N)` over the CTA; every thread returns with the totals.  scratch: N * (LOSS_THREADS / 32) doubles
+template <int N>
+__device__ __forceinline__ void block_sum(double (&v)[N], double* scratch) {
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();                       // the scratch area of the previous exchange has been read
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) scratch[k * (LOSS_THREADS / 32) + wib] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < LOSS_THREADS / 32; ++w) t += scratch[k * (LOSS_THREADS / 32) + w];
+    v[k] = t;
+  }
+}
 __global__ void composite_loss_kernel(const float* __restrict__ raw_s, const float* __restrict__ raw_d,
                                       const float* __restrict__ z, const float* __restrict__ i0,
                                       const double* __restrict__ gt, const double* __restrict__ wpix, int gw_stride,
                                       int n_rays, int n, int act, LossCfg c, double* __restrict__ pix_out,
                                       double* __restrict__ terms, float* __restrict__ d_raw_s, float* __restrict__ d_raw_d) {
-  extern __shared__ float sm[];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ray = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (ray >= n_rays) return;
-  float* ss_c = sm + (size_t)wib * 2 * n;
+  extern __shared__ double sm_d[];
+  double* scratch = sm_d;                                   // 8 * (LOSS_THREADS / 32) doubles
+  float* ss_c = reinterpret_cast<float*>(sm_d + 8 * (LOSS_THREADS / 32));
   float* sd_c = ss_c + n;
+  const int ray = blockIdx.x, lane = threadIdx.x;           // `lane`: index of the thread within the ray's CTA
+  if (ray >= n_rays) return;
   const size_t off = (size_t)ray * n;
   const double B = (double)c.b_global, BN = B * (double)n;
 
   // sweep 1: sigma, ray sums, blend-ratio terms
   double W = 0, Ss = 0, Sd = 0, l2 = 0, bw_sum = 0, fav_sum = 0;
   float mx_s = 0.f, mx_d = 0.f;
-  for (int s = lane; s < n; s += 32) {
+  for (int s = lane; s < n; s += LOSS_THREADS) {
     const double d = delta_at<double>(z, s, n);
     const float ss = __fmul_rn(act_fwd(act, raw_s[off + s]), 0.01f);
     const float sd = __fmul_rn(act_fwd(act, raw_d[off + s]), 0.01f);
@@ -112,10 +136,18 @@ __global__ void composite_loss_kernel(const float* __restrict__ raw_s, const flo
     bw_sum += (double)bw;
     fav_sum += (double)(-(b * logf(b) + r * logf(r)));
   }
-  W = warp_sum(W); Ss = warp_sum(Ss); Sd = warp_sum(Sd); l2 = warp_sum(l2);
-  bw_sum = warp_sum(bw_sum); fav_sum = warp_sum(fav_sum);
-  mx_s = warp_max(mx_s); mx_d = warp_max(mx_d);
-  __syncwarp();
+  {
+    // the six ray sums in one exchange, the two maxima in a second one
+    double v[6] = {W, Ss, Sd, l2, bw_sum, fav_sum};
+    block_sum<6>(v, scratch);
+    W = v[0]; Ss = v[1]; Sd = v[2]; l2 = v[3]; bw_sum = v[4]; fav_sum = v[5];
+    mx_s = warp_max(mx_s); mx_d = warp_max(mx_d);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { scratch[2 * (threadIdx.x >> 5)] = (double)mx_s; scratch[2 * (threadIdx.x >> 5) + 1] = (double)mx_d; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < LOSS_THREADS / 32; ++w) { mx_s = fmaxf(mx_s, (float)scratch[2 * w]); mx_d = fmaxf(mx_d, (float)scratch[2 * w + 1]); }
+  }
 
   const double w = wpix[(size_t)ray * gw_stride];
   const double pix = (double)__ldg(i0 + ray) - W;
@@ -126,7 +158,7 @@ __global__ void composite_loss_kernel(const float* __restrict__ raw_s, const flo
 
   // sweep 2: ray entropies and the sum_j h_j p_j normaliser of the dynamic-entropy gradient
   double ent_s = 0, ent_d = 0, hp_d = 0;
-  for (int s = lane; s < n; s += 32) {
+  for (int s = lane; s < n; s += LOSS_THREADS) {
     const double d = delta_at<double>(z, s, n);
     const double ps = (double)ss_c[s] * d / Ss_hat, pd = (double)sd_c[s] * d / Sd_hat;
     ent_s -= ps * log(ps + 1e-10);
@@ -134,7 +166,11 @@ __global__ void composite_loss_kernel(const float* __restrict__ raw_s, const flo
     ent_d -= pd * lg;
     hp_d += -(lg + pd / (pd + 1e-10)) * pd;
   }
-  ent_s = warp_sum(ent_s); ent_d = warp_sum(ent_d); hp_d = warp_sum(hp_d);
+  {
+    double v[3] = {ent_s, ent_d, hp_d};
+    block_sum<3>(v, scratch);
+    ent_s = v[0]; ent_d = v[1]; hp_d = v[2];
+  }
 
   if (lane == 0) {
     pix_out[ray] = pix;
@@ -157,7 +193,7 @@ __global__ void composite_loss_kernel(const float* __restrict__ raw_s, const flo
   // sweep 3: dL/d_raw
   const double g_px_c = -(2.0 / B) * w * res;
   const double live_d = (Sd >= 1e-19) ? 1.0 : 0.0;
-  for (int s = lane; s < n; s += 32) {
+  for (int s = lane; s < n; s += LOSS_THREADS) {
     const double d = delta_at<double>(z, s, n);
     const float ssf = ss_c[s], sdf = sd_c[s];
     const double ss = ssf, sd = sdf;
@@ -281,15 +317,12 @@ extern "C" int nerfca_composite_loss(const float* raw_s, const float* raw_d, con
     NERFCA_LAUNCH_OK();
     return NERFCA_OK;
   }
-  int warps = 4;
-  while (warps > 1 && (size_t)warps * 2 * n_depth * sizeof(float) > 48 * 1024) warps >>= 1;
-  const size_t smem = (size_t)warps * 2 * n_depth * sizeof(float);
+  const size_t smem = 8 * (LOSS_THREADS / 32) * sizeof(double) + (size_t)2 * n_depth * sizeof(float);
   NERFCA_REQUIRE(smem <= 200 * 1024, NERFCA_E_UNSUPPORTED, "n_depth too large for the fused loss kernel");
   if (smem > 48 * 1024)
     NERFCA_CUDA_OK(cudaFuncSetAttribute(composite_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  composite_loss_kernel<<<div_up(n_rays, warps), warps * 32, smem, st>>>(raw_s, raw_d, depth, i0, gt, wpix, gw_stride, n_rays,
-                                                                       n_depth, activation, c, pix_out, terms_out, d_raw_s,
-                                                                       d_raw_d);
+  composite_loss_kernel<<<n_rays, LOSS_THREADS, smem, st>>>(raw_s, raw_d, depth, i0, gt, wpix, gw_stride, n_rays, n_depth, activation, c,
+                                                         pix_out, terms_out, d_raw_s, d_raw_d);
   NERFCA_LAUNCH_OK();
   return NERFCA_OK;
 }

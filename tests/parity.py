@@ -117,18 +117,18 @@ def compare_grads(got: dict, want: dict, tol: dict, prefix=""):
 
 
 def run_composite_step_parity(n_rays=64, n_depth=40, precision="bf16", seed=0, hidden=128, n_early=4, n_freq=12, n_latent=8,
-                              it=50000, fused=True, device="cuda:0"):
+                              it=50000, fused=True, device="cuda:0", n_phases=10):
     """One composite training step on the GPU (fused path or autograd drop-in path) against the oracle."""
     from nerfca import ops
     import model_helpers as mh
     tol = TOL[precision]
     enc_dim = 3 + 6 * n_freq
     sd_s = orc.init_field_state(enc_dim, hidden, n_early, seed=seed + 1)
-    sd_d = orc.init_field_state(enc_dim + n_latent, hidden, n_early, 10, n_latent, seed=seed + 2)
+    sd_d = orc.init_field_state(enc_dim + n_latent, hidden, n_early, n_phases, n_latent, seed=seed + 2)
     sd_d["output_linear.0.bias"] = sd_d["output_linear.0.bias"] + 0.5
     mask, _ = orc.freq_mask(n_freq, it, 150000, 1)
     cfg = {"n_freq": n_freq, "n_hidden": n_early, "pos_enc": "free_windowed", "window": mask}
-    rays, phases, z = synthetic_batch(n_rays, n_depth, seed)
+    rays, phases, z = synthetic_batch(n_rays, n_depth, seed, n_phases=n_phases)
     hp = orc.COMPOSITE_HP
     loss_o, out_o, gs_o, gd_o = oracle_composite_step(sd_s, sd_d, cfg, cfg, rays, phases, z, hp, it)
 

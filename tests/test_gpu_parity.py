@@ -334,6 +334,14 @@ def test_composite_step_vs_oracle(precision, fused):
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
+def test_composite_step_30_phases(precision):
+    """BASELINE config 3: 30 cardiac phases (time_latents [30, 8]).  On the tensor-core path the latent gradient then takes the
+    explicit latent-dgrad + scatter-by-phase route (30 one-hot columns do not fit the padded first layer)."""
+    res = parity.run_composite_step_parity(n_rays=120, n_depth=50, precision=precision, seed=7, fused=True, n_phases=30)
+    assert res["grad_cos_min"] >= parity.TOL[precision]["grad_cos"]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
 def test_full_size_step_properties(precision):
     """Config-2 batch (1024 rays x 500 samples): determinism of the forward, and ray-shard additivity of the gradients
     (the multi-GPU contract: sum of shard gradients with the global 1/B == single-device gradients)."""
