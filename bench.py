@@ -221,7 +221,7 @@ def workload_config(extra=None):
          "rays_per_step_per_gpu": N_RAYS, "samples_per_ray": N_DEPTH, "hidden": HIDDEN, "n_freq": N_FREQ,
          "step": "zero_grad + fields fwd + line integral + 11 loss terms + closed-form dL/draw + fields bwd (wgrad/dgrad/latent) "
                  "+ grad all-reduce (N>1) + Adam",
-         "l2": "per-step working set (activation stash, ~1.5 GB) exceeds the 126 MB L2 and every step uses a distinct ray batch; no explicit flush"}
+         "l2": "per-step working set (activation stash + hand-off, ~1.4 GB) exceeds the 126 MB L2 and every step uses a distinct ray batch; no explicit flush"}
     if extra:
         c.update(extra)
     return c
@@ -237,6 +237,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("NERFCA_PRECISION", "bf16"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -320,9 +321,14 @@ def main():
         trainer.step_host(rays_host[k], phases_host[k], trand_host[k])
     barrier()
     e0.record()
-    losses = []
+    losses, pending = [], []
     for k in range(args.warmup, n_total):
-        losses.append(trainer.step_host(rays_host[k], phases_host[k], trand_host[k]))
+        # every step: H2D of its batch rows, the step, D2H of its loss sums -- all enqueued; the loss of step k is read (host wait
+        # on that step's event only) while step k + 1 is already queued, as a driver that logs one iteration late would
+        pending.append(trainer.step_host_async(rays_host[k], phases_host[k], trand_host[k]))
+        if len(pending) > 1:
+            losses.append(pending.pop(0).loss())
+    losses.extend(h.loss() for h in pending)
     e1.record()
     barrier()
     ms2 = e0.elapsed_time(e1)
@@ -353,6 +359,30 @@ def main():
                 "whole_step_frac": (N_RAYS * N_DEPTH * FLOP_PER_SAMPLE / (ms_per_step * 1e-3) / 1e12) / pk["bf16_sustained"],
                 "kernels": {k: {"ms_per_step": v["ms_per_step"], "launches_per_step": v["launches_per_step"]} for k, v in kt.items()}}
 
+    # ---------------- secondary metric (BASELINE.json): render ms/frame, config 4 (1024^2 frame, static + dynamic, no grad) ------
+    render = None
+    if world == 1 and not args.no_render:
+        import proj_helpers as ph
+        from nerfca import ops
+        geo_r = dict(GEO, nDetector=[1024, 1024], dDetector=[200 * 0.01 / 1024] * 2)
+        o_r, d_r = ph.ray_values_tigre_device(VIEWS[0][0], VIEWS[0][1], 0, geo_r, dev)
+        z_r = trainer.depth_uniform
+        with torch.no_grad():
+            ops.render_frame(trainer.static, trainer.temp, o_r, d_r, z_r, 3, I0)        # warm-up frame
+            torch.cuda.synchronize()
+            e0.record()
+            n_frames = 3
+            for ph_id in range(n_frames):
+                pix_r, _, _ = ops.render_frame(trainer.static, trainer.temp, o_r, d_r, z_r, ph_id, I0)
+            e1.record()
+            torch.cuda.synchronize()
+        ms_frame = e0.elapsed_time(e1) / n_frames
+        flop_frame = 1024 * 1024 * N_DEPTH * FLOP_PER_SAMPLE_FWD
+        render = {"ms_per_frame": ms_frame, "frame": "1024x1024 rays x 500 samples, static + dynamic composite + both component images",
+                  "rays_per_s": 1024 * 1024 / (ms_frame * 1e-3), "tflops": flop_frame / (ms_frame * 1e-3) / 1e12,
+                  "frac_of_tensor_peak": flop_frame / (ms_frame * 1e-3) / 1e12 / peaks()["bf16_sustained"],
+                  "finite": bool(torch.isfinite(pix_r).all().item())}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         n_cpu = 128
@@ -369,7 +399,7 @@ def main():
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "loss_last_step": losses[-1] if losses else None},
-            "roofline": roof, "cpu_baseline": cpu}
+            "roofline": roof, "render": render, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -61,6 +61,22 @@ def flatten_parameters(modules, device):
     return flat_p, flat_g
 
 
+class PendingLoss:
+    """Loss sums of one enqueued step: a pinned host slot + the event recorded behind its D2H copy (a ring of 8 per trainer, so a
+    handle must be read before 8 further steps are enqueued)."""
+
+    def __init__(self, trainer):
+        self.trainer = trainer
+        self.host = torch.zeros(L.N_LOSS_TERMS, dtype=torch.float64).pin_memory()
+        self.event = torch.cuda.Event()
+        self.n_rays_global = 0
+        self.cfg = None
+
+    def loss(self) -> float:
+        self.event.synchronize()
+        return float(ops.loss_from_terms(self.host, self.cfg, self.n_rays_global, self.trainer.n_depth))
+
+
 class CompositeTrainer:
     def __init__(self, static_model, temp_model, device, lr=1e-3, lr_end_factor=0.01, lr_decay_steps=150000, betas=(0.9, 0.999),
                  eps=1e-8, i0=float(np.log(8.670397)), near=3.2, far=8.8, n_depth=500, output_activation="softplus", hp=None,
@@ -82,6 +98,8 @@ class CompositeTrainer:
         self.last_terms = self.terms
         self._terms_host = torch.zeros(L.N_LOSS_TERMS, dtype=torch.float64).pin_memory() if self.device.type == "cuda" else None
         self._i0_cache = {}
+        self._pending_slots = [PendingLoss(self) for _ in range(8)] if self.device.type == "cuda" else []
+        self._pending_next = 0
         self.iteration = 0
         self.loss_cfg = ops.LossConfig()
         self.set_iteration(0)
@@ -156,15 +174,26 @@ class CompositeTrainer:
     def step_host(self, rays_host: torch.Tensor, phases_host: torch.Tensor, t_rand_host: torch.Tensor) -> float:
         """The call a user of the drop-in makes per iteration with HOST batch rows (run_composite.py:262-308):
         H2D of rays / phases / the jitter draw, the step, D2H of the loss sums; returns the total loss (python float)."""
+        return self.step_host_async(rays_host, phases_host, t_rand_host).loss()
+
+    def step_host_async(self, rays_host: torch.Tensor, phases_host: torch.Tensor, t_rand_host: torch.Tensor) -> "PendingLoss":
+        """step_host without the host-side wait: everything (H2D copies, the step, the D2H copy of the loss sums into a pinned
+        slot) is enqueued on the current stream and a handle is returned; `.loss()` waits for that step only.  A driver that
+        reads the loss one iteration late (logging, early-stop checks) keeps the GPU busy back to back."""
         rays = rays_host.to(self.device, non_blocking=True)
         phases = phases_host.to(self.device, non_blocking=True)
         depth = self.jitter(t_rand_host)
         terms = self.step_device(rays, phases, depth)
         if self.world_size > 1:
+            terms = terms.clone()
             self.dist.all_reduce(terms)          # sums; the two maxima are per-rank diagnostics
-        self._terms_host.copy_(terms, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(self.loss_from(self._terms_host, rays.shape[0] * self.world_size))
+        slot = self._pending_slots[self._pending_next % len(self._pending_slots)]
+        self._pending_next += 1
+        slot.host.copy_(terms, non_blocking=True)
+        slot.event.record(torch.cuda.current_stream())
+        slot.n_rays_global = rays.shape[0] * self.world_size
+        slot.cfg = self.loss_cfg
+        return slot
 
     def loss_from(self, terms: torch.Tensor, n_rays_global: Optional[int] = None) -> torch.Tensor:
         n = n_rays_global or (self.loss_cfg.n_rays_global or 1)
