@@ -293,11 +293,16 @@ def main():
     barrier()
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cuprof = os.environ.get("NERFCA_CUPROF") == "1"      # ncu --profile-from-start off: list exactly the timed region's launches
+    if cuprof:
+        torch.cuda.profiler.start()
     e0.record()
     for k in range(args.warmup, n_total):
         trainer.step_device(*batches[k])
     e1.record()
     barrier()
+    if cuprof:
+        torch.cuda.profiler.stop()
     clk = clocks.stop()
     ms = e0.elapsed_time(e1)
     launches = trainer.launch_count - launches0

@@ -12,8 +12,9 @@ timeout 600 python bench.py --steps 100 --warmup 5 > $OUT/bench.json 2> $OUT/ben
 cat $OUT/bench.json; tail -5 $OUT/bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
 cat $OUT/bench_ref.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1
+NERFCA_CUPROF=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv \
+    --log-file $OUT/launches.csv python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-render > $OUT/ncu_bench.log 2>&1
+python tools/launch_shares.py $OUT/launches.csv > $OUT/launch_shares.txt 2>&1; cat $OUT/launch_shares.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_(forward|bwd_top|bwd_bot)_kernel|composite_loss' -s 8 -c 4 \
     -o $OUT/prof -f python tools/profile_step.py 1024 500 3 > $OUT/ncu_full.log 2>&1
 tail -3 $OUT/ncu_full.log
