@@ -56,6 +56,19 @@ def peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
 
 
+def measured_traffic(family: str):
+    """DRAM bytes per launch of a kernel family from the newest committed ncu capture (profiles/*/traffic.json), or None."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*", "traffic.json")), reverse=True):
+        try:
+            with open(path) as f:
+                t = json.load(f)
+            return {"dram_bytes_per_launch": t["per_launch"][family]["dram_bytes"], "source": os.path.relpath(path, ROOT)}
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
+
+
 # ---- synthetic phantom: a chain of Gaussian blobs (closed-form line integrals) ---------------------------------------
 
 def phantom_blobs(phase: int):
@@ -221,7 +234,7 @@ def workload_config(extra=None):
          "rays_per_step_per_gpu": N_RAYS, "samples_per_ray": N_DEPTH, "hidden": HIDDEN, "n_freq": N_FREQ,
          "step": "zero_grad + fields fwd + line integral + 11 loss terms + closed-form dL/draw + fields bwd (wgrad/dgrad/latent) "
                  "+ grad all-reduce (N>1) + Adam",
-         "l2": "per-step working set (activation stash + hand-off, ~1.4 GB) exceeds the 126 MB L2 and every step uses a distinct ray batch; no explicit flush"}
+         "l2": "per-step working set (activation stash, ~1.0 GB written by the forward and read back by the backward) exceeds the 126 MB L2 and every step uses a distinct ray batch; no explicit flush"}
     if extra:
         c.update(extra)
     return c
@@ -357,8 +370,10 @@ def main():
         fam_flop = {"field_forward": FLOP_PER_SAMPLE_FWD, "field_backward": FLOP_PER_SAMPLE - FLOP_PER_SAMPLE_FWD}.get(dom, 0) * N_RAYS * N_DEPTH
         d["flop_per_launch"] = fam_flop / d["launches_per_step"]
         achieved = d["flop_per_launch"] / (d["ms_per_launch"] * 1e-3) / 1e12
+        tr = measured_traffic(dom)
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
+                "frac": achieved / pk["bf16_sustained"], "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                "traffic_source": tr["source"] if tr else None, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                 "ms_per_launch": d["ms_per_launch"], "launches_per_step": d["launches_per_step"],
                 "share_of_step": d["ms_per_step"] / ms_per_step,
                 "whole_step_frac": (N_RAYS * N_DEPTH * FLOP_PER_SAMPLE / (ms_per_step * 1e-3) / 1e12) / pk["bf16_sustained"],

@@ -38,7 +38,8 @@ constexpr int TC_H = 128;
 constexpr uint32_t TILE_BYTES = 32768;           // one [128 x 128] bf16 tile
 constexpr int TC_N_RELU = 5;
 constexpr int STASH_TILES = 4;                   // H0 .. H3 of every tile (bf16, tile-canonical bytes)
-constexpr uint32_t MASK_BYTES = 16384;           // + the high bytes of H4 (nonzero <=> Z4 + b4 > 0): chunk c (16 columns) at c * 2048 + row * 16
+constexpr uint32_t MASK_BYTES = 2048;            // + the ReLU pattern of H4, one BIT per element: row r owns 16 bytes = 4 words, word 2 ch + g covers
+                                                 // columns [64 ch + 32 g, + 32): bit i = column 2i, bit 16 + i = column 2i + 1 (i < 16)
 constexpr size_t STASH_STRIDE = (size_t)STASH_TILES * 32768 + MASK_BYTES;   // bytes per tile and net
 constexpr int FWD_THREADS = 20 * 32;             // 16 epilogue / issue warps + 4 X0 producer warps
 constexpr int FAST_FREQ = 12;                    // band count the register-resident encoder is specialised for
@@ -289,6 +290,21 @@ __device__ __forceinline__ void emit_x0_row(const X0Desc& xd, const RowIn& in, c
   }
 }
 
+// ---- shared-memory access by 32-bit shared-space address ------------------------------------------------------
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---- accumulator (this thread's lane, 64 columns) -> registers ---------------------------------------------------
 __device__ __forceinline__ void ld_acc64(uint32_t taddr, uint32_t (&a)[32], uint32_t (&b)[32]) {
   tmem_ld32(taddr, a);
@@ -425,6 +441,9 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
 //     MUFU + double-angle steps) into its own TMEM region while the slot's previous tile is still in the layer chain.
 //   * The 128 -> 1 output layer is a sixth MMA (N = 16) against a (hi, lo) bf16 split of w_out into its own accumulator, so
 //     layer 0 of the slot's next tile is issued right behind it.
+//   * The stash (130 KB per tile) leaves as 16-byte streaming stores straight from the epilogue registers.  That path tops out near
+//     16 B/clk per SM (~4.7 TB/s over the chip) and is what bounds the training forward (the same kernel without a stash runs 3x
+//     faster); routing it through shared-memory staging + bulk stores was measured slower (294 vs 227 us per step).
 // smem: [packed block][barriers][band weights 32 f32][latent table 256 f32]
 __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -533,7 +552,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
     // shared-window base, ~25-cycle S2R reads on the critical path of every layer)
     uint32_t k_acc = t_acc, k_a = t_a, k_bias = smem_u32(s_f) + (uint32_t)(ch * 64) * 4u, k_bar_acc = bar_acc;
     uint32_t k_stash_off = (uint32_t)(ch * 8) * CHUNK_BYTES + (uint32_t)row * 16u;
-    uint32_t k_mask_off = (uint32_t)(ch * 4) * CHUNK_BYTES + (uint32_t)row * 16u;
+    uint32_t k_mask_off = (uint32_t)row * 16u + (uint32_t)ch * 8u;
     pin(k_acc); pin(k_a); pin(k_bias); pin(k_bar_acc); pin(k_stash_off); pin(k_mask_off);
 
     auto issue_layer0 = [&]() {      // whole warp; the X0 region of the slot's next tile feeds layer 0
@@ -562,7 +581,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
         // groups of 32 columns; the bias of the first group is fetched before the accumulator wait
         const uint32_t bias = k_bias + (uint32_t)l * 512u;
         // tile-canonical stash bytes: chunk c of the row at c * 2048 + row * 16 (a warp writes 512 contiguous bytes per chunk);
-        // layer 4 leaves only the high byte of every H4 element (the ReLU pattern the backward needs), 16 columns per chunk
+        // layer 4 leaves only the ReLU pattern of H4 (what the backward needs), one bit per element
         uint8_t* dst = nt.stash + (size_t)tile * STASH_STRIDE + (size_t)(l < 4 ? l : STASH_TILES) * TILE_BYTES + ((l < 4) ? k_stash_off : k_mask_off);
         mbar_wait(k_bar_acc, ph_acc);
         ph_acc ^= 1;
@@ -574,6 +593,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
         tmem_ld32(k_acc + 32, v1);
         tmem_ld_wait();
         NERFCA_TL(lane == 0 && (warp & 7) == 1, 1012 + slot * 1000 + l * 10);
+        uint32_t mbits[2] = {0u, 0u};
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           uint32_t w[16];
@@ -591,14 +611,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
               for (int c = 0; c < 4; ++c)
                 __stcs(reinterpret_cast<uint4*>(dst + (4 * g + c) * CHUNK_BYTES), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
             } else {
+              // every half of w is a non-negative bf16: adding 0x7FFF carries into the half's top bit exactly when it is nonzero (and
+              // never beyond: the largest half is 0x7F80); word i's two flags end up at bits i and 16 + i
+              uint32_t m = 0;
 #pragma unroll
-              for (int c = 0; c < 2; ++c)
-                __stcs(reinterpret_cast<uint4*>(dst + (2 * g + c) * CHUNK_BYTES),
-                       make_uint4(__byte_perm(w[8 * c], w[8 * c + 1], 0x7531), __byte_perm(w[8 * c + 2], w[8 * c + 3], 0x7531),
-                                  __byte_perm(w[8 * c + 4], w[8 * c + 5], 0x7531), __byte_perm(w[8 * c + 6], w[8 * c + 7], 0x7531)));
+              for (int i2 = 0; i2 < 16; ++i2) m = (m >> 1) | ((w[i2] + 0x7FFF7FFFu) & 0x80008000u);
+              mbits[g] = m;
             }
           }
         }
+        if (stash_on && l == 4) __stcs(reinterpret_cast<uint2*>(dst), make_uint2(mbits[0], mbits[1]));
         tmem_st_wait();
         NERFCA_TL(lane == 0 && (warp & 7) == 1, 1011 + slot * 1000 + l * 10);
         tc_fence_before();
@@ -670,7 +692,9 @@ __device__ __forceinline__ void flush_wgrad(uint32_t t_lane, uint32_t col0, floa
 struct BwdNet {
   const uint8_t* pack;
   const uint8_t* stash;
-  uint8_t* handoff;          // [n_tiles][TILE_BYTES]  dZ2
+  uint8_t* handoff;          // [ring][TILE_BYTES]  dZ2 of tile t sits in slot t % ring (top role -> bottom role, through L2)
+  uint32_t* produced;        // [n_tiles] 8 once the top role's dZ2 of the tile is visible GPU-wide
+  uint32_t* consumed;        // [n_tiles] 1 once the bottom role's copy of the slot has landed in its shared memory
   const float* d_raw;
   float* g_w[NERFCA_MAX_LAYERS];
   float* g_b[NERFCA_MAX_LAYERS];   // may be null
@@ -686,9 +710,36 @@ struct BwdArgs {
   BwdNet net[2];
   int n_nets;
   long long n_tiles;
-  long long* dbg;   // optional event timeline of one CTA (NERFCA_TIMELINE=bot, NERFCA_TIMELINE_CTA=n)
+  int n_top, n_bot;          // CTAs per net in the top / bottom role (grid = n_nets * (n_top + n_bot))
+  int ring;                  // hand-off slots per net
+  int role;                  // 0: both roles in this launch, 1: every CTA runs the top role, 2: every CTA runs the bottom role
+  long long* dbg;   // optional event timeline of one CTA (NERFCA_TIMELINE=top|bot, NERFCA_TIMELINE_CTA=n)
   int dbg_cta;
 };
+
+// ---- hand-off flags in global memory (top role -> bottom role, both resident in the same launch) ------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// generic-proxy global writes <-> async-proxy (bulk copy) reads of the same bytes
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Bounded spin on a flag: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t want) {
+  if (ld_acquire_gpu(p) >= want) return;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(p) < want) {
+    __nanosleep(64);
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
 
 // =====================================================================================================================
 // backward, top pass: output layer, layers 4 and 3
@@ -709,16 +760,9 @@ struct BwdArgs {
 //     tile i + 1 go into the buffers H3 / R of tile i vacate when weight gradient 4 completes.
 // TMEM: ACC [0,128) | WG4 [128,256) | WG3 [256,384) | BG4 [384,400) | BG3 [400,416) | A [416,480)
 constexpr uint32_t TOP_ACC = 0, TOP_WG4 = 128, TOP_WG3 = 256, TOP_BG4 = 384, TOP_BG3 = 400, TOP_A = 416;
-constexpr int TOP_THREADS = 9 * 32;                  // 8 epilogue warps (warp 0 holds the issuing lane) + load warp
+constexpr int BWD_THREADS = 16 * 32;   // both roles: warps 0-7 epilogue (warp 0 holds the issuing lane); top: 8 loader; bottom: 8-11 X0, 12 loader
+constexpr int BWD_RING = 128;          // hand-off slots per net (4 MB: lives in L2)
 
-__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
 // 32 packed words (64 bf16 columns of one row) -> the row's 8 chunks of a tile-canonical shared-memory tile
 __device__ __forceinline__ void sts_row64(uint32_t tile_row_addr, const uint32_t (&w)[32]) {
 #pragma unroll
@@ -751,13 +795,10 @@ __device__ __forceinline__ void flush_wgrad_scaled(uint32_t t_lane, uint32_t col
   }
 }
 
-// smem: [W3][W4][4 tile buffers][ones tile 4 KB][H4 pattern 16 KB][fp32: w_out (128)][bf16x2 w_out pairs (64 words)][d_raw 2 x 128][barriers]
-__global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
+// smem: [W3][W4][4 tile buffers][ones tile 4 KB][H4 pattern 2 KB][fp32: w_out (128)][bf16x2 w_out pairs (64 words)][d_raw 2 x 128][barriers]
+__device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt, const long long worker, const long long n_workers) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int net_id = blockIdx.x % a.n_nets;
-  const BwdNet& nt = a.net[net_id];
-  const long long worker = blockIdx.x / a.n_nets, n_workers = gridDim.x / a.n_nets;
   uint8_t* s_w3 = smem;
   uint8_t* s_w4 = smem + TILE_BYTES;
   uint8_t* s_buf = smem + 2 * TILE_BYTES;            // 4 rotating tile buffers
@@ -768,14 +809,15 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
   float* s_g = reinterpret_cast<float*>(s_wo2 + 64);           // d_raw of the tile's rows, two tiles deep (filled by the load warp)
   float* s_gbout = s_g + 256;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_gbout + 4);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 12);
   const uint32_t bar_w = smem_u32(s_bar), bar_ldh = bar_w + 8, bar_ldm = bar_w + 16, bar_acc = bar_w + 24, bar_half = bar_w + 32,
-                 bar_mfree = bar_w + 40, bar_tile = bar_w + 48, bar_done = bar_w + 56;
+                 bar_mfree = bar_w + 40, bar_tile = bar_w + 48, bar_slot = bar_w + 56, bar_pub = bar_w + 64;
 
   if (warp == 8) {
     if (lane == 0) {
       mbar_init(bar_w, 1); mbar_init(bar_ldh, 1); mbar_init(bar_ldm, 1); mbar_init(bar_acc, 1); mbar_init(bar_half, 1);
-      mbar_init(bar_mfree, 8); mbar_init(bar_tile, 1); mbar_init(bar_done, 1);
+      mbar_init(bar_mfree, 8); mbar_init(bar_tile, 1);
+      mbar_init(bar_slot, 1); mbar_init(bar_pub, 8);
       mbar_init_fence();
     }
     __syncwarp();
@@ -797,6 +839,9 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
   const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
   [[maybe_unused]] int tl_n = 0;
 
+  if (warp >= 8) {
+    if (warp >= 12) reg_dealloc<24>(); else reg_dealloc<64>();      // per warpgroup; warps 9-15 only hand their registers over
+  }
   if (warp == 8) {
     // ================= load warp =================
     if (lane == 0) {
@@ -805,9 +850,19 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
       bulk_g2s(smem_u32(s_w4), nt.pack + nt.w0_bytes + 3 * (size_t)TILE_BYTES, TILE_BYTES, bar_w);
     }
     uint32_t ph_half = 0, ph_mfree = 0;
+    // hand-off slot of tile j: free once the bottom role has copied out the tile that used it `ring` tiles earlier.  The slot
+    // barrier gets its arrival for tile j only after step A of tile j has been passed (bar_mfree), i.e. after the epilogue
+    // has consumed the arrival for tile j - 1: never more than one phase ahead of its only waiter.
+    auto release_slot = [&](long long tile_j, uint32_t seen) {
+      if (tile_j >= a.ring && seen == 0u) wait_flag_ge(nt.consumed + (tile_j - a.ring), 1u);
+      mbar_arrive(bar_slot);
+    };
     for (long long i = 0; i < n_my; ++i) {
       const long long tile = worker + i * n_workers;
       const uint8_t* st = nt.stash + (size_t)tile * STASH_STRIDE;
+      // the flag of the previous tile's slot is requested now and looked at after this tile's loads have been issued
+      uint32_t seen = 1u;
+      if (lane == 0 && i > 0 && tile - n_workers >= a.ring) seen = ld_acquire_gpu(nt.consumed + (tile - n_workers - a.ring));
       // H4 pattern + d_raw of tile i: as soon as step A of tile i - 1 has consumed its own (plain loads for d_raw: the last tile
       // may be ragged; they are published by the arrival on bar_ldm below)
       float gv[4];
@@ -820,28 +875,58 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
       __syncwarp();
       if (lane == 0) {
         if (i > 0) mbar_wait(bar_mfree, ph_mfree);
+        NERFCA_TL(true, 2001);
         mbar_expect_tx(bar_ldm, MASK_BYTES);
         bulk_g2s(smem_u32(s_m4), st + (size_t)STASH_TILES * TILE_BYTES, MASK_BYTES, bar_ldm);
         // H2, H3 of tile i: into the buffers that H3 / R of tile i - 1 leave when its weight gradient 4 is complete
         if (i > 0) mbar_wait(bar_half, ph_half);
+        NERFCA_TL(true, 2003);
         mbar_expect_tx(bar_ldh, 2 * TILE_BYTES);
         bulk_g2s(smem_u32(s_buf + (size_t)(i & 3) * TILE_BYTES), st + 2 * (size_t)TILE_BYTES, TILE_BYTES, bar_ldh);
         bulk_g2s(smem_u32(s_buf + (size_t)((i + 1) & 3) * TILE_BYTES), st + 3 * (size_t)TILE_BYTES, TILE_BYTES, bar_ldh);
+        if (i > 0) release_slot(tile - n_workers, seen);
+        NERFCA_TL(true, 2005);
       }
       if (i > 0) { ph_half ^= 1; ph_mfree ^= 1; }
       __syncwarp();
     }
-  } else {
-    // ================= 8 epilogue warps: thread = (row, column half); the elected lane of warp 0 issues =================
+    if (lane == 0 && n_my > 0) {
+      mbar_wait(bar_mfree, ph_mfree);                   // step A of the last tile
+      release_slot(worker + (n_my - 1) * n_workers, 0u);
+    }
+  } else if (warp == 10) {
+    // ================= publisher: the epilogue warps only arrive on bar_pub behind their dZ2 stores (a CTA-scope release costs them
+    // nothing); the GPU-scope release -- which has to wait until those stores have reached L2 -- is paid here, off the tile's path ====
+    if (lane == 0) {                // one polling lane that sleeps between probes: the epilogue warps of its scheduler keep their issue slots
+      for (long long i = 0; i < n_my; ++i) {
+        const long long t0 = clock64();
+        while (!mbar_try_wait(bar_pub, (uint32_t)(i & 1))) {
+          __nanosleep(500);
+          if (clock64() - t0 > 4000000000LL) __trap();
+        }
+        red_release_gpu_add(nt.produced + (worker + i * n_workers), 8u);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 8) {
+    reg_alloc<200>();
+    // ================= 8 epilogue warps: thread = (row, column half); the elected lane of warp 0 issues the dgrad GEMMs =================
     const int q = warp & 3, ch = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t k_acc = t_lane + TOP_ACC + ch * 64, k_a = t_lane + TOP_A + ch * 32;
     uint32_t k_wo2 = smem_u32(s_wo2) + (uint32_t)(ch * 32) * 4u;
     uint32_t k_rowoff = (uint32_t)(ch * 8) * CHUNK_BYTES + (uint32_t)row * 16u;     // this thread's first chunk inside a tile
-    uint32_t k_m4 = smem_u32(s_m4) + (uint32_t)(ch * 4) * CHUNK_BYTES + (uint32_t)row * 16u;
+    uint32_t k_m4 = smem_u32(s_m4) + (uint32_t)row * 16u + (uint32_t)ch * 8u;
     uint32_t k_buf = smem_u32(s_buf);
     pin(k_acc); pin(k_a); pin(k_wo2); pin(k_rowoff); pin(k_m4); pin(k_buf);
+    // publish the previous tile's dZ2 (stored a whole step ago): one arrival per warp; the publisher warp raises the GPU-scope flag
+    auto publish = [&]() {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pub);
+    };
+    uint32_t slot = (uint32_t)(worker % a.ring);      // hand-off slot of the current tile, advanced without a division per tile
+    const uint32_t slot_step = (uint32_t)(n_workers % a.ring);
     const uint32_t w3 = smem_u32(s_w3), w4 = smem_u32(s_w4), ones = smem_u32(s_ones);
     constexpr uint32_t KM = KSTEP_MNMAJOR;
     constexpr uint32_t id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1), id_side = instr_desc(128, 16, 1, 1);
@@ -850,7 +935,6 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
     float gb_sum = 0.f;
     mbar_wait(bar_w, 0);
     for (long long i = 0; i < n_my; ++i) {
-      const long long tile = worker + i * n_workers;
       const uint32_t par = (uint32_t)(i & 1);
       const uint32_t h2 = k_buf + (uint32_t)(i & 3) * TILE_BYTES, h3 = k_buf + (uint32_t)((i + 1) & 3) * TILE_BYTES,
                      R = k_buf + (uint32_t)((i + 2) & 3) * TILE_BYTES, S = k_buf + (uint32_t)((i + 3) & 3) * TILE_BYTES;
@@ -858,22 +942,21 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
       uint32_t va[32], vb[32], w[32];
       // ---- step A: R = dZ4' = d_raw 1[H4 > 0] (shared memory, A of wgrad 4), A = dZ4 = dZ4' w_out (tensor memory, A of dgrad 4)
       mbar_wait(bar_ldm, par);
+      NERFCA_TL(warp == 1 && lane == 0, 1009);
       if (i > 0) mbar_wait(bar_tile, par ^ 1);      // weight gradient 3 of the previous tile has released the R / S buffers
       NERFCA_TL(warp == 1 && lane == 0, 1010);
       {
         const float g_cur = s_g[par * 128 + row];
         const uint32_t gb = pack_bf16x2(g_cur, g_cur);
         if (ch == 0) gb_sum += g_cur;
+        // pattern word g covers this thread's columns [32 g, 32 g + 32): bit i / 16 + i = columns 2i / 2i + 1.  (0 or 1 in each half) times
+        // the 16 bf16 bits of d_raw gives the packed pair without a carry between the halves.
+        const uint2 mb = lds_u2(k_m4);
+        const uint32_t gbits = gb & 0xFFFFu;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint4 mb = lds_u4(k_m4 + (uint32_t)c * CHUNK_BYTES);      // 16 pattern bytes = 16 columns
-          const uint32_t m[4] = {mb.x, mb.y, mb.z, mb.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            // byte b of the word -> bf16 halfword b << 8 (> 0 exactly when H4 was): columns (4e, 4e+1) and (4e+2, 4e+3) of the chunk
-            w[8 * c + 2 * e] = mul_bf16x2(relu_mask_bf16x2(__byte_perm(m[e], 0u, 0x1404)), gb);
-            w[8 * c + 2 * e + 1] = mul_bf16x2(relu_mask_bf16x2(__byte_perm(m[e], 0u, 0x3424)), gb);
-          }
+        for (int i2 = 0; i2 < 16; ++i2) {
+          w[i2] = ((mb.x >> i2) & 0x00010001u) * gbits;
+          w[16 + i2] = ((mb.y >> i2) & 0x00010001u) * gbits;
         }
         sts_row64(R + k_rowoff, w);
 #pragma unroll
@@ -894,6 +977,10 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
       NERFCA_TL(warp == 1 && lane == 0, 1013);
       named_bar_sync(1, 256);
       NERFCA_TL(warp == 1 && lane == 0, 1014);
+      // One lane issues everything in the order the results are needed: the dgrad GEMM first, then the weight / bias gradient GEMMs
+      // nobody waits for.  (The tensor pipe executes MMAs in issue order at ~68 cycles per 128x128x16 step and the issuing lane stalls
+      // while the queue is full, so the ~1300 cycles spent here are tensor-pipe time; issuing from three lanes at once, or from a
+      // dedicated warp behind an mbarrier hand-over, were both measured slower.)
       if (warp == 0) {
         tc_fence_after();
         if (elect_one()) {
@@ -913,6 +1000,7 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
       mbar_wait(bar_ldh, par);
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
+      if (i > 0) publish();                           // (the stores were issued a whole step ago)
       NERFCA_TL(warp == 1 && lane == 0, 1020);
       ld_acc64(k_acc, va, vb);
       masked_grad_pack64(va, vb, h3 + k_rowoff, w);
@@ -943,16 +1031,22 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
       tc_fence_after();
       NERFCA_TL(warp == 1 && lane == 0, 1030);
       ld_acc64(k_acc, va, vb);
-      masked_grad_pack64(va, vb, h2 + k_rowoff, w);
       {
-        uint8_t* dst = nt.handoff + (size_t)tile * TILE_BYTES + k_rowoff;
+        masked_grad_pack64(va, vb, h2 + k_rowoff, w);
+        mbar_wait(bar_slot, par);
+        NERFCA_TL(warp == 1 && lane == 0, 1031);
+        uint8_t* dst = nt.handoff + (size_t)slot * TILE_BYTES + k_rowoff;
+        slot += slot_step;
+        if (slot >= (uint32_t)a.ring) slot -= (uint32_t)a.ring;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < 8; ++c)      // .cg: straight to L2 (a plain store also goes through the L1 path and takes ~2x as long to drain)
           __stcs(reinterpret_cast<uint4*>(dst + c * CHUNK_BYTES), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+        __syncwarp();
       }
       tc_fence_before();
       NERFCA_TL(warp == 1 && lane == 0, 1033);
     }
+    if (n_my > 0) publish();                          // the last tile's dZ2
     // ---- flush the TMEM-resident accumulators
     if (ch == 0) {
 #pragma unroll
@@ -960,12 +1054,7 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
       if (lane == 0 && nt.g_b[5]) atomicAdd(s_gbout, gb_sum);
     }
     if (n_my > 0) {
-      named_bar_sync(1, 256);
-      if (warp == 0) {
-        if (elect_one()) umma_commit(bar_done);
-        __syncwarp();
-      }
-      mbar_wait(bar_done, 0);
+      mbar_wait(bar_tile, (uint32_t)((n_my - 1) & 1));   // the last commit of the issuing lane: every MMA has completed
       tc_fence_after();
       const float* fb = reinterpret_cast<const float*>(nt.pack + nt.f32_off);
       const float wo_row = s_wo[row], b4_row = __ldg(fb + 4 * 128 + row);
@@ -1019,15 +1108,11 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
 // loads of H1 / H0 into the H0 / dZ1 buffers when weight gradient 1 is complete.
 // TMEM: ACC [0,128) | WG2 [128,256) | WG1 [256,384) | WG0 [384,480) | BG2 [480,496) | BG1 [496,512)
 constexpr uint32_t BOT_ACC = 0, BOT_WG2 = 128, BOT_WG1 = 256, BOT_WG0 = 384, BOT_BG2 = 480, BOT_BG1 = 496;
-constexpr int BOT_THREADS = 16 * 32;   // warps 0-7 epilogue (warp 0 holds the issuing lane), 8-11 X0 producers, 12 loader, 13-15 idle
 
 // smem: [W1][W2][4 tile buffers][X0: 96 * 256][W0 latent chunks 4 KB][ones tile 4 KB][latent acc 256 f32][barriers]
-__global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
+__device__ __forceinline__ void bwd_bot_role(const BwdArgs& a, const BwdNet& nt, const long long worker, const long long n_workers) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int net_id = blockIdx.x % a.n_nets;
-  const BwdNet& nt = a.net[net_id];
-  const long long worker = blockIdx.x / a.n_nets, n_workers = gridDim.x / a.n_nets;
   const bool onehot = nt.n_latent > 0 && nt.x0.onehot > 0;    // latent gradient through the one-hot columns of X0
   const bool has_lat = nt.n_latent > 0 && !onehot;            // fallback: explicit latent dgrad + scatter by phase
   const int kpad0 = nt.x0.kpad0;
@@ -1042,14 +1127,14 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
   float* s_lat = reinterpret_cast<float*>(s_ones + 4096);
   const int n_lat_acc = has_lat ? nt.n_phases * nt.n_latent : 0;            // <= 256 checked on the host
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_lat + 256);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 10);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 12);
   const uint32_t bar_w = smem_u32(s_bar), bar_ld_dz = bar_w + 8, bar_ld_h1 = bar_w + 16, bar_ld_h0 = bar_w + 24, bar_acc = bar_w + 32,
-                 bar_free1 = bar_w + 40, bar_free2 = bar_w + 48, bar_x0 = bar_w + 56, bar_x0free = bar_w + 64, bar_done = bar_w + 72;
+                 bar_free1 = bar_w + 40, bar_free2 = bar_w + 48, bar_x0 = bar_w + 56, bar_x0free = bar_w + 64;
 
   if (warp == 12) {
     if (lane == 0) {
       mbar_init(bar_w, 1); mbar_init(bar_ld_dz, 1); mbar_init(bar_ld_h1, 1); mbar_init(bar_ld_h0, 1); mbar_init(bar_acc, 1);
-      mbar_init(bar_free1, 1); mbar_init(bar_free2, 1); mbar_init(bar_x0, 4); mbar_init(bar_x0free, 1); mbar_init(bar_done, 1);
+      mbar_init(bar_free1, 1); mbar_init(bar_free2, 1); mbar_init(bar_x0, 4); mbar_init(bar_x0free, 1);
       mbar_init_fence();
     }
     __syncwarp();
@@ -1079,17 +1164,32 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
       bulk_g2s(smem_u32(s_w2), nt.pack + nt.w0_bytes + (size_t)TILE_BYTES, TILE_BYTES, bar_w);
       if (has_lat) bulk_g2s(smem_u32(s_w0lat), nt.pack + (size_t)lat_c0 * CHUNK_BYTES, lat_bytes, bar_w);
       uint32_t ph1 = 0, ph2 = 0;
+      uint32_t slot = (uint32_t)(worker % a.ring);    // hand-off slot of the current tile, advanced without a division per tile
+      const uint32_t slot_step = (uint32_t)(n_workers % a.ring);
       for (long long i = 0; i < n_my; ++i) {
         const long long tile = worker + i * n_workers;
         const uint8_t* st = nt.stash + (size_t)tile * STASH_STRIDE;
-        if (i > 0) { mbar_wait(bar_free1, ph1); ph1 ^= 1; }     // H1's buffer of tile i - 1
+        const uint32_t seen = ld_acquire_gpu(nt.produced + tile);   // requested now, looked at once the buffer is free
+        if (i > 0) {
+          mbar_wait(bar_free1, ph1); ph1 ^= 1;                  // H1's buffer of tile i - 1
+          mbar_wait(bar_ld_dz, (uint32_t)((i - 1) & 1));        // (long complete) dZ2 of tile i - 1 has left its hand-off slot
+          st_release_gpu(nt.consumed + (tile - n_workers), 1u);
+        }
+        if (seen < 8u) wait_flag_ge(nt.produced + tile, 8u);    // all 8 epilogue warps of the top role have written the tile
+        fence_proxy_async_all();
         mbar_expect_tx(bar_ld_dz, TILE_BYTES);
-        bulk_g2s(smem_u32(s_buf + (size_t)(i & 3) * TILE_BYTES), nt.handoff + (size_t)tile * TILE_BYTES, TILE_BYTES, bar_ld_dz);
+        bulk_g2s(smem_u32(s_buf + (size_t)(i & 3) * TILE_BYTES), nt.handoff + (size_t)slot * TILE_BYTES, TILE_BYTES, bar_ld_dz);
+        slot += slot_step;
+        if (slot >= (uint32_t)a.ring) slot -= (uint32_t)a.ring;
         if (i > 0) { mbar_wait(bar_free2, ph2); ph2 ^= 1; }     // H0's and dZ1's buffers of tile i - 1
         mbar_expect_tx(bar_ld_h1, TILE_BYTES);
         bulk_g2s(smem_u32(s_buf + (size_t)((i + 1) & 3) * TILE_BYTES), st + (size_t)TILE_BYTES, TILE_BYTES, bar_ld_h1);
         mbar_expect_tx(bar_ld_h0, TILE_BYTES);
         bulk_g2s(smem_u32(s_buf + (size_t)((i + 2) & 3) * TILE_BYTES), st, TILE_BYTES, bar_ld_h0);
+      }
+      if (n_my > 0) {
+        mbar_wait(bar_ld_dz, (uint32_t)((n_my - 1) & 1));
+        st_release_gpu(nt.consumed + (worker + (n_my - 1) * n_workers), 1u);
       }
     }
     __syncwarp();
@@ -1206,8 +1306,8 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
           umma_commit(bar_free2);      // wgrad 1 complete and H0's pattern read: the H0 / dZ1 buffers may be reloaded
           mbar_wait(bar_x0, par);
           tc_fence_after();
-          umma_k<8, KM, KM>(tmem + BOT_WG0, mnmajor(dz0), mnmajor(x0), id_wg0, first);               // WG0 += dZ0^T X0
-          umma_commit(bar_x0free);
+          umma_k<8, KM, KM>(tmem + BOT_WG0, mnmajor(dz0), mnmajor(x0), id_wg0, first);               // WG0 += dZ0^T X0 (same thread as the next
+          umma_commit(bar_x0free);                                                                    // dgrad 2: its commit covers this read of dZ0)
           if (has_lat) {
             umma_k<8, KK, KM>(td_acc, kmajor(dz0), mnmajor(w0lat), id_lat, 0);                       // latent columns of dX0
             umma_commit(bar_acc);
@@ -1252,11 +1352,7 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
       // (without the fallback the accumulator was last read before the barrier of step C)
     }
     if (n_my > 0) {
-      if (warp == 0) {
-        if (elect_one()) umma_commit(bar_done);
-        __syncwarp();
-      }
-      mbar_wait(bar_done, 0);
+      mbar_wait(bar_x0free, (uint32_t)((n_my - 1) & 1));   // the last commit of the issuing lane: every weight-gradient MMA has completed
       tc_fence_after();
       flush_wgrad(t_lane, BOT_WG2, nt.g_w[2], row, ch, 128, 128);
       flush_wgrad(t_lane, BOT_WG1, nt.g_w[1], row, ch, 128, 128);
@@ -1318,18 +1414,38 @@ __global__ void __launch_bounds__(BOT_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
   if (warp == 12) tmem_dealloc(tmem, 512);
 }
 
+// One launch, two roles: of the n_top + n_bot CTAs of a net the first n_top run the top pass and hand every tile's dZ2 to the rest
+// through a ring of slots that stays in L2 (flags: `produced` / `consumed` per tile).  Both roles walk the tiles in increasing
+// order (worker, worker + n_workers, ...), and all CTAs are resident at once (grid <= #SMs, one CTA per SM), so the smallest
+// tile not yet produced is always being worked on: the hand-off cannot deadlock for any ring size >= 1.
+__global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
+  const int net_id = blockIdx.x % a.n_nets;
+  const int r = blockIdx.x / a.n_nets;
+  if (a.role == 1 || (a.role == 0 && r < a.n_top)) bwd_top_role(a, a.net[net_id], r, a.n_top);
+  else bwd_bot_role(a, a.net[net_id], a.role == 2 ? r : r - a.n_top, a.n_bot);
+}
+// single-role launches (two-launch mode)
+__global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_top_kernel(BwdArgs a) {
+  bwd_top_role(a, a.net[blockIdx.x % a.n_nets], blockIdx.x / a.n_nets, a.n_top);
+}
+__global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
+  bwd_bot_role(a, a.net[blockIdx.x % a.n_nets], blockIdx.x / a.n_nets, a.n_bot);
+}
+
 // =====================================================================================================================
 // host side
 // =====================================================================================================================
 static size_t fwd_smem_bytes(const NetDims& d) { return (((size_t)d.pack_bytes + 127) & ~(size_t)127) + 10 * 8 + (32 + 256) * 4; }
-constexpr size_t TOP_SMEM = 6 * (size_t)TILE_BYTES + 4096 + MASK_BYTES + 128 * 4 + 64 * 4 + 256 * 4 + 16 + 8 * 8 + 16;
-constexpr size_t BOT_SMEM = 6 * (size_t)TILE_BYTES + 96 * 256 + 4096 + 4096 + 256 * 4 + 10 * 8 + 16;
+constexpr size_t TOP_SMEM = 6 * (size_t)TILE_BYTES + 4096 + MASK_BYTES + 128 * 4 + 64 * 4 + 256 * 4 + 16 + 12 * 8 + 16;
+constexpr size_t BOT_SMEM = 6 * (size_t)TILE_BYTES + 96 * 256 + 4096 + 4096 + 256 * 4 + 12 * 8 + 16;
+constexpr size_t BWD_SMEM = TOP_SMEM > BOT_SMEM ? TOP_SMEM : BOT_SMEM;
+static_assert(BWD_SMEM <= 227 * 1024, "backward kernel exceeds the shared memory of an SM");
 
 static size_t n_tiles_of(long long P) { return (size_t)((P + TILE_M - 1) / TILE_M); }
 
 // stash: [net][tile][2][32 KB]
 size_t tc_stash_bytes_n(int n_nets, long long P) { return (size_t)n_nets * n_tiles_of(P) * STASH_STRIDE; }
-// workspace: [packed blocks][hand-off: net, tile, 32 KB (backward only)]
+// workspace: [packed blocks][hand-off ring: net, slot, 32 KB][hand-off flags: net, {produced, consumed}, tile]   (the last two: backward only)
 static size_t tc_pack_bytes_n(const nerfca_field_t* const* f, int n_nets) {
   size_t n = 0;
   for (int i = 0; i < n_nets; ++i) n += pack_stride(net_dims(*f[i]));
@@ -1337,10 +1453,16 @@ static size_t tc_pack_bytes_n(const nerfca_field_t* const* f, int n_nets) {
 }
 size_t tc_workspace_bytes_n(const nerfca_field_t* const* f, int n_nets, long long P, int backward) {
   size_t n = tc_pack_bytes_n(f, n_nets);
-  if (backward) n += (size_t)n_nets * n_tiles_of(P) * TILE_BYTES;
+  // (sized for the two-launch mode, NERFCA_BWD_MERGED=0, whose hand-off holds every tile; the one-launch mode uses BWD_RING slots per net)
+  if (backward) n += (size_t)n_nets * (n_tiles_of(P) > (size_t)BWD_RING ? n_tiles_of(P) : (size_t)BWD_RING) * TILE_BYTES +
+                     (size_t)n_nets * 2 * n_tiles_of(P) * sizeof(uint32_t);
   return n;
 }
 
+static int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 static bool timeline_wanted(const char* which) {
   const char* e = getenv("NERFCA_TIMELINE");
   return e && strcmp(e, which) == 0;
@@ -1429,13 +1551,19 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
   a.n_tiles = (long long)n_tiles_of(s.n_points);
   size_t off = 0;
   uint8_t* handoff = (uint8_t*)workspace + tc_pack_bytes_n(f, n_nets);
+  const int merged = env_flag("NERFCA_BWD_MERGED", 1);
+  const size_t ring = merged ? (size_t)BWD_RING : ((size_t)a.n_tiles > (size_t)BWD_RING ? (size_t)a.n_tiles : (size_t)BWD_RING);
+  const size_t ring_alloc = (size_t)a.n_tiles > (size_t)BWD_RING ? (size_t)a.n_tiles : (size_t)BWD_RING;
+  uint32_t* flags = reinterpret_cast<uint32_t*>(handoff + (size_t)n_nets * ring_alloc * TILE_BYTES);
   for (int i = 0; i < n_nets; ++i) {
     const NetDims d = net_dims(*f[i]);
     BwdNet& n = a.net[i];
     n.pack = (const uint8_t*)workspace + off;
     off += pack_stride(d);
     n.stash = (const uint8_t*)stash + (size_t)i * a.n_tiles * STASH_STRIDE;
-    n.handoff = handoff + (size_t)i * a.n_tiles * TILE_BYTES;
+    n.handoff = handoff + (size_t)i * ring * TILE_BYTES;
+    n.produced = flags + (size_t)(2 * i) * a.n_tiles;
+    n.consumed = flags + (size_t)(2 * i + 1) * a.n_tiles;
     n.d_raw = d_raw[i];
     for (int l = 0; l < NERFCA_MAX_LAYERS; ++l) { n.g_w[l] = gr[i]->weight[l]; n.g_b[l] = gr[i]->bias[l]; }
     n.g_lat = gr[i]->latents;
@@ -1450,36 +1578,50 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
     NERFCA_REQUIRE(f[i]->n_latent == 0 || (size_t)f[i]->n_phases * f[i]->n_latent <= 256, NERFCA_E_UNSUPPORTED,
                    "tcgen05 backward: latent table larger than 256 floats (use precision fp32)");
   }
+  // role split: n_top + n_bot CTAs per net, all resident at once (one CTA per SM).  NERFCA_BWD_SPLIT="n_top,n_bot" overrides it.
+  const int per_net = sm_count() / n_nets;
+  int n_top = per_net / 2, n_bot = per_net - per_net / 2;
+  if (!merged) n_top = n_bot = per_net;          // two launches: every SM runs the top role, then every SM the bottom role
+  else if (const char* e = getenv("NERFCA_BWD_SPLIT")) {
+    int t = 0, b = 0;
+    if (sscanf(e, "%d,%d", &t, &b) == 2 && t > 0 && b > 0 && t + b <= per_net) { n_top = t; n_bot = b; }
+  }
+  if (n_top > a.n_tiles) n_top = (int)a.n_tiles;
+  if (n_bot > a.n_tiles) n_bot = (int)a.n_tiles;
+  NERFCA_REQUIRE(n_top >= 1 && n_bot >= 1, NERFCA_E_UNSUPPORTED, "tcgen05 backward needs at least two SMs per net");
+  a.n_top = n_top; a.n_bot = n_bot; a.ring = (int)ring;
+  NERFCA_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)n_nets * 2 * a.n_tiles * sizeof(uint32_t), st));
+  NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
   NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_bwd_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOP_SMEM));
   NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_bwd_bot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BOT_SMEM));
-  const unsigned grid = grid_for(n_nets, a.n_tiles);
+  const bool tl_top = timeline_wanted("top"), tl_bot = timeline_wanted("bot");   // NERFCA_TIMELINE_CTA picks a CTA of that role
   a.dbg = nullptr;
   a.dbg_cta = getenv("NERFCA_TIMELINE_CTA") ? atoi(getenv("NERFCA_TIMELINE_CTA")) : 0;
-  if (timeline_wanted("top")) {
+  if (tl_top || tl_bot) {
     NERFCA_CUDA_OK(cudaMalloc(&a.dbg, 8008 * sizeof(long long)));
     NERFCA_CUDA_OK(cudaMemsetAsync(a.dbg, 0, 8008 * sizeof(long long), st));
+    if (merged && tl_bot && !getenv("NERFCA_TIMELINE_CTA")) a.dbg_cta = n_nets * n_top;
   }
   {
     ProfScope prof(NERFCA_K_FIELD_BWD, st);
-    tc_bwd_top_kernel<<<grid, TOP_THREADS, TOP_SMEM, st>>>(a);
-    NERFCA_LAUNCH_OK();
+    if (merged) {
+      a.role = 0;
+      tc_bwd_kernel<<<(unsigned)(n_nets * (n_top + n_bot)), BWD_THREADS, BWD_SMEM, st>>>(a);
+      NERFCA_LAUNCH_OK();
+    } else {
+      BwdArgs b = a;
+      if (!tl_top) b.dbg = nullptr;
+      b.role = 1;
+      tc_bwd_top_kernel<<<(unsigned)(n_nets * n_top), BWD_THREADS, TOP_SMEM, st>>>(b);
+      NERFCA_LAUNCH_OK();
+      b = a;
+      if (!tl_bot) b.dbg = nullptr;
+      b.role = 2;
+      tc_bwd_bot_kernel<<<(unsigned)(n_nets * n_bot), BWD_THREADS, BOT_SMEM, st>>>(b);
+      NERFCA_LAUNCH_OK();
+    }
   }
-  if (timeline_wanted("top")) {
-    int rc = timeline_dump(a.dbg, st);
-    if (rc) return rc;
-    a.dbg = nullptr;
-  }
-  const bool timeline = timeline_wanted("bot");
-  if (timeline) {
-    NERFCA_CUDA_OK(cudaMalloc(&a.dbg, 8008 * sizeof(long long)));
-    NERFCA_CUDA_OK(cudaMemsetAsync(a.dbg, 0, 8008 * sizeof(long long), st));
-  }
-  {
-    ProfScope prof(NERFCA_K_FIELD_BWD, st);
-    tc_bwd_bot_kernel<<<grid, BOT_THREADS, BOT_SMEM, st>>>(a);
-    NERFCA_LAUNCH_OK();
-  }
-  if (timeline) return timeline_dump(a.dbg, st);
+  if (tl_top || tl_bot) return timeline_dump(a.dbg, st);
   return NERFCA_OK;
 }
 

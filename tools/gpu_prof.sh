@@ -7,7 +7,7 @@ mkdir -p $OUT
 timeout 600 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest exit $?" >> $OUT/pytest.log
 tail -4 $OUT/pytest.log
 python tools/profile_step.py 1024 500 4
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_(forward|bwd_top|bwd_bot)_kernel|composite_loss' -s 4 -c 4 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_(forward|bwd)_kernel|composite_loss' -s 3 -c 3 \
     -o $OUT/prof -f python tools/profile_step.py 1024 500 2 > $OUT/ncu_full.log 2>&1
 tail -3 $OUT/ncu_full.log
 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
