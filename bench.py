@@ -284,7 +284,7 @@ def main():
 
     n_total = args.steps + args.warmup
     # same host RNG stream on every rank; each rank takes its contiguous slice of the global batch
-    ids_all = np.random.randint(0, R, size=(n_total, world * N_RAYS))[:, rank * N_RAYS:(rank + 1) * N_RAYS]
+    ids_all = np.random.randint(0, R, size=(n_total, world * N_RAYS))[:, tr.shard_slice(world * N_RAYS, rank, world)]
     ids_dev = torch.from_numpy(ids_all).to(dev)
     gen = torch.Generator().manual_seed(1234)
     t_rand = torch.rand((n_total, N_DEPTH), generator=gen)

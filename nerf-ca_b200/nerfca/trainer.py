@@ -61,6 +61,22 @@ def flatten_parameters(modules, device):
     return flat_p, flat_g
 
 
+def shard_slice(n_global: int, rank: int, world_size: int) -> slice:
+    """Contiguous slice of a global batch of n_global rays owned by `rank` (every rank draws the same global ray ids
+    from the same host RNG stream and keeps its slice; the remainder goes to the first ranks)."""
+    base, rem = divmod(int(n_global), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return slice(lo, lo + base + (1 if rank < rem else 0))
+
+
+def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """The step's only collective: in-place sum of one flat buffer (gradients, or the loss sums) over the ranks."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
 class PendingLoss:
     """Loss sums of one enqueued step: a pinned host slot + the event recorded behind its D2H copy (a ring of 8 per trainer, so a
     handle must be read before 8 further steps are enqueued)."""
@@ -162,7 +178,7 @@ class CompositeTrainer:
         self.terms.zero_()
         ops.train_step_composite(self.static, self.temp, rays, phases, self._i0(B), depth, self.output_activation, cfg, self.terms)
         if self.world_size > 1:
-            self.dist.all_reduce(self.flat_g)
+            allreduce_sum_(self.flat_g)
         L.check(L.load().nerfca_adam_step(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
                                           self.flat_p.numel(), L.ptr(self.step_dev), C.byref(self.adam), 1.0, 1, L.stream_ptr()),
                 "nerfca_adam_step")
@@ -185,8 +201,7 @@ class CompositeTrainer:
         depth = self.jitter(t_rand_host)
         terms = self.step_device(rays, phases, depth)
         if self.world_size > 1:
-            terms = terms.clone()
-            self.dist.all_reduce(terms)          # sums; the two maxima are per-rank diagnostics
+            terms = allreduce_sum_(terms.clone())    # sums; the two maxima are per-rank diagnostics
         slot = self._pending_slots[self._pending_next % len(self._pending_slots)]
         self._pending_next += 1
         slot.host.copy_(terms, non_blocking=True)
