@@ -356,6 +356,28 @@ def main():
     e2e_value = world * N_RAYS * args.steps / (float(t.item()) * 1e-3)
     d2h = trainer.d2h_bytes_per_step
 
+    # ---------------- e2e, N1 path: ray table resident in HBM, only the step's ray ids + the jitter draw cross PCIe ----------------
+    trainer.attach_ray_table(rays_tab, phases_tab)
+    ids_host = [torch.from_numpy(ids_all[k]).pin_memory() for k in range(n_total)]
+    for k in range(args.warmup):
+        trainer.step_ids_async(ids_host[k], trand_host[k]).loss()
+    barrier()
+    e0.record()
+    pending = []
+    for k in range(args.warmup, n_total):
+        pending.append(trainer.step_ids_async(ids_host[k], trand_host[k]))
+        if len(pending) > 1:
+            pending.pop(0).loss()
+    for h in pending:
+        h.loss()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ids_value = world * N_RAYS * args.steps / (float(t.item()) * 1e-3)
+    h2d_ids = ids_host[0].numel() * 8 + trand_host[0].numel() * 4
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -418,7 +440,11 @@ def main():
                                        "loss_last_step": float(trainer.loss_from(last_terms))}),
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "loss_last_step": losses[-1] if losses else None},
+                    "loss_last_step": losses[-1] if losses else None,
+                    "api": "CompositeTrainer.step_host_async(rays[B,4,3] f64, phases[B], t_rand[N]) -- the host rows upstream feeds per iteration",
+                    "device_ray_table": {"value": e2e_ids_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_ids, "d2h_bytes_per_step": d2h,
+                                         "api": "CompositeTrainer.step_ids_async(ids[B] i64, t_rand[N]) -- ray table resident in HBM, "
+                                                "batch rows gathered by nerfca_gather_batch"}},
             "roofline": roof, "render": render, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -150,6 +150,16 @@ NERFCA_API int nerfca_gen_rays(const float* pose_host, int32_t width, int32_t he
  * (t_rand device [n]); out device [n].  Bit-identical fp32.                                           */
 NERFCA_API int nerfca_jitter_depth(const float* z, const float* t_rand, int32_t n, float* out, void* stream);
 
+/* N1  train/run_composite.py:250-273: assemble a training batch ON THE DEVICE from the device-resident ray table
+ * rays_train [R,4,3] float64 / phases_train [R] int64 (train/data_helpers.py:157-163) and the step's ray ids
+ * (int64 [B], drawn by the host RNG exactly as upstream): rays_out [B,4,3] float64 = rays_train[ids] (bit copy),
+ * phases_out [B] int32 = phases_train[ids] (run_composite.py:265 `.int()`).  An id outside [0, R) is an argument
+ * error reported through err_flag (device int32, set to 1; may be null).  Replaces the host-side fancy index of a
+ * multi-GB float64 array plus a 96 B/ray H2D copy by an 8 B/ray copy of the ids.                          */
+NERFCA_API int nerfca_gather_batch(const double* rays_table, const int64_t* phases_table, int64_t n_table,
+                        const int64_t* ids, int32_t n_batch, double* rays_out, int32_t* phases_out,
+                        int32_t* err_flag, void* stream);
+
 /* A4  train/model_helpers.py:118-121 / run_composite.py:351-352: materialise the sample points
  * [P,3] float32 (device) of a ray-generated sample set.  Bit-identical.                               */
 NERFCA_API int nerfca_sample_points(const nerfca_samples_t* samples, float* points_out, void* stream);

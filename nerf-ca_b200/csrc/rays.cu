@@ -97,6 +97,35 @@ extern "C" int nerfca_jitter_depth(const float* z, const float* t_rand, int32_t 
   return NERFCA_OK;
 }
 
+// one thread per (ray, 16-byte half-row pair): a ray-table row is 12 doubles = 96 bytes = 6 x 16 B
+__global__ void gather_batch_kernel(const double* __restrict__ table, const long long* __restrict__ phases, long long n_table,
+                                    const long long* __restrict__ ids, int n_batch, double* __restrict__ rays_out,
+                                    int* __restrict__ phases_out, int* __restrict__ err_flag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = t / 6, part = t - r * 6;
+  if (r >= n_batch) return;
+  const long long id = __ldg(ids + r);
+  if (id < 0 || id >= n_table) {
+    if (err_flag && part == 0) *err_flag = 1;
+    return;
+  }
+  const double2 v = __ldg(reinterpret_cast<const double2*>(table + id * 12) + part);
+  reinterpret_cast<double2*>(rays_out + (long long)r * 12)[part] = v;
+  if (part == 0 && phases_out) phases_out[r] = phases ? (int)__ldg(phases + id) : 0;
+}
+
+extern "C" int nerfca_gather_batch(const double* rays_table, const int64_t* phases_table, int64_t n_table, const int64_t* ids,
+                                   int32_t n_batch, double* rays_out, int32_t* phases_out, int32_t* err_flag, void* stream) {
+  NERFCA_REQUIRE(rays_table && ids && rays_out, NERFCA_E_ARG, "null pointer");
+  NERFCA_REQUIRE(n_table > 0 && n_batch >= 0, NERFCA_E_ARG, "empty ray table or negative batch size");
+  NERFCA_REQUIRE(((uintptr_t)rays_table & 15) == 0 && ((uintptr_t)rays_out & 15) == 0, NERFCA_E_ARG, "ray rows must be 16-byte aligned");
+  if (n_batch == 0) return NERFCA_OK;
+  gather_batch_kernel<<<div_up((long long)n_batch * 6, 256), 256, 0, (cudaStream_t)stream>>>(
+      rays_table, (const long long*)phases_table, (long long)n_table, (const long long*)ids, n_batch, rays_out, phases_out, err_flag);
+  NERFCA_LAUNCH_OK();
+  return NERFCA_OK;
+}
+
 extern "C" int nerfca_sample_points(const nerfca_samples_t* samples, float* points_out, void* stream) {
   NERFCA_REQUIRE(samples && points_out, NERFCA_E_ARG, "null pointer");
   int rc = validate_samples(samples, false);

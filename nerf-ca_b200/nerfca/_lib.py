@@ -79,6 +79,7 @@ _SIGNATURES = {
     "nerfca_abi_version": (C.c_int, []),
     "nerfca_gen_rays": (C.c_int, [_P, _I32, _I32, _F, _F, _F, _F, _F, _P, _P, _P]),
     "nerfca_jitter_depth": (C.c_int, [_P, _P, _I32, _P, _P]),
+    "nerfca_gather_batch": (C.c_int, [_P, _P, _I64, _P, _I32, _P, _P, _P, _P]),
     "nerfca_sample_points": (C.c_int, [C.POINTER(SamplesStruct), _P, _P]),
     "nerfca_encode": (C.c_int, [C.POINTER(FieldStruct), C.POINTER(SamplesStruct), _P, _P]),
     "nerfca_field_stash_bytes": (C.c_size_t, [C.POINTER(FieldStruct), _I64, _I32]),

@@ -121,6 +121,24 @@ def jitter_depth(z: torch.Tensor, t_rand: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gather_batch(rays_table: torch.Tensor, phases_table: Optional[torch.Tensor], ids: torch.Tensor,
+                 err_flag: Optional[torch.Tensor] = None):
+    """N1 (train/run_composite.py:250-273): rays_table[ids] / phases_table[ids].int() assembled on the device from the
+    device-resident ray table [R,4,3] float64 (+ phases [R] int64) and int64 ray ids [B].  Bit copy of the rows.
+    `err_flag` (device int32 [1]) is set to 1 by an id outside [0, R); the caller decides when to read it."""
+    assert rays_table.dtype == torch.float64 and rays_table.is_contiguous() and tuple(rays_table.shape[1:]) == (4, 3)
+    ids = ids.to(device=rays_table.device, dtype=torch.int64).contiguous()
+    B = ids.numel()
+    rays = torch.empty((B, 4, 3), dtype=torch.float64, device=rays_table.device)
+    phases = torch.empty((B,), dtype=torch.int32, device=rays_table.device)
+    if phases_table is not None:
+        assert phases_table.dtype == torch.int64 and phases_table.is_contiguous() and phases_table.numel() == rays_table.shape[0]
+    L.check(L.load().nerfca_gather_batch(L.ptr(rays_table), L.ptr(phases_table) if phases_table is not None else None,
+                                         rays_table.shape[0], L.ptr(ids), B, L.ptr(rays), L.ptr(phases),
+                                         L.ptr(err_flag) if err_flag is not None else None, L.stream_ptr()), "nerfca_gather_batch")
+    return rays, phases
+
+
 # ------------------------------------------------------------------------------------------------
 # fields
 # ------------------------------------------------------------------------------------------------

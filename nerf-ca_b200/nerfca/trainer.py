@@ -90,6 +90,8 @@ class PendingLoss:
 
     def loss(self) -> float:
         self.event.synchronize()
+        if self.host[L.N_LOSS_TERMS - 1] != 0:      # last (otherwise unused) slot: the batch gather saw a ray id outside the table
+            raise ValueError("ray id outside the ray table (nerfca_gather_batch)")
         return float(ops.loss_from_terms(self.host, self.cfg, self.n_rays_global, self.trainer.n_depth))
 
 
@@ -116,6 +118,8 @@ class CompositeTrainer:
         self._i0_cache = {}
         self._pending_slots = [PendingLoss(self) for _ in range(8)] if self.device.type == "cuda" else []
         self._pending_next = 0
+        self.rays_table = self.phases_table = None       # device-resident ray table (attach_ray_table)
+        self._gather_err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.iteration = 0
         self.loss_cfg = ops.LossConfig()
         self.set_iteration(0)
@@ -205,6 +209,34 @@ class CompositeTrainer:
         slot = self._pending_slots[self._pending_next % len(self._pending_slots)]
         self._pending_next += 1
         slot.host.copy_(terms, non_blocking=True)
+        slot.event.record(torch.cuda.current_stream())
+        slot.n_rays_global = rays.shape[0] * self.world_size
+        slot.cfg = self.loss_cfg
+        return slot
+
+    # ---- N1: device-resident ray table, batches assembled on the device --------------------------------------------------
+    def attach_ray_table(self, rays_train, phases_train):
+        """Keep `rays_train [R,4,3] float64` / `phases_train [R] int64` (train/data_helpers.py:157-163; numpy or torch) in HBM.
+        96 B + 8 B per ray: config 2 = 166 MB, config 3 = 6.5 GB of the 180 GB."""
+        self.rays_table = torch.as_tensor(rays_train, dtype=torch.float64).to(self.device).contiguous()
+        self.phases_table = torch.as_tensor(phases_train).to(device=self.device, dtype=torch.int64).contiguous()
+        assert tuple(self.rays_table.shape[1:]) == (4, 3) and self.phases_table.numel() == self.rays_table.shape[0]
+
+    def step_ids_async(self, ids_host: torch.Tensor, t_rand_host: torch.Tensor) -> "PendingLoss":
+        """One iteration of run_composite.py:250-308 from the step's ray ids (int64 [B], host, drawn by the caller's RNG as
+        upstream does): H2D of 8 B per ray instead of 96, the batch rows are gathered from the resident table by
+        nerfca_gather_batch, then the step; returns the loss handle like step_host_async."""
+        assert self.rays_table is not None, "attach_ray_table() first"
+        ids = ids_host.to(self.device, non_blocking=True)
+        rays, phases = ops.gather_batch(self.rays_table, self.phases_table, ids, self._gather_err)
+        depth = self.jitter(t_rand_host)
+        terms = self.step_device(rays, phases, depth)
+        if self.world_size > 1:
+            terms = allreduce_sum_(terms.clone())
+        slot = self._pending_slots[self._pending_next % len(self._pending_slots)]
+        self._pending_next += 1
+        slot.host.copy_(terms, non_blocking=True)
+        slot.host[L.N_LOSS_TERMS - 1:].copy_(self._gather_err, non_blocking=True)
         slot.event.record(torch.cuda.current_stream())
         slot.n_rays_global = rays.shape[0] * self.world_size
         slot.cfg = self.loss_cfg

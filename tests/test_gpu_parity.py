@@ -372,3 +372,52 @@ def test_full_size_step_properties(precision):
     np.testing.assert_allclose(both.cpu().numpy(), tv.cpu().numpy(), rtol=1e-9)
     for a, b, c in zip(g1, g2, gr):
         assert parity.rel_l2((a + b).cpu().numpy(), c.cpu().numpy()) <= 2e-3   # fp32 atomics: order-dependent rounding only
+
+
+# ---- N1: device-resident ray table, batches gathered on the device ---------------------------------------------------------
+
+def test_gather_batch_bit_exact_and_flags_bad_ids():
+    from nerfca import ops
+    g = torch.Generator().manual_seed(11)
+    table = torch.rand((5000, 4, 3), dtype=torch.float64, generator=g).to(DEV)
+    ph_tab = torch.randint(0, 30, (5000,), generator=g).to(DEV)
+    for n in (0, 1, 7, 1024, 4099):                              # empty, ragged and > one block
+        ids = torch.randint(0, 5000, (n,), generator=g)
+        err = torch.zeros(1, dtype=torch.int32, device=DEV)
+        rays, phases = ops.gather_batch(table, ph_tab, ids, err)
+        assert torch.equal(rays, table[ids.to(DEV)]) and torch.equal(phases, ph_tab[ids.to(DEV)].int())
+        assert rays.dtype == torch.float64 and phases.dtype == torch.int32 and int(err.item()) == 0
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.gather_batch(table, ph_tab, torch.tensor([3, 5000, 4]), err)     # id == R is outside the table
+    assert int(err.item()) == 1
+    err.zero_()
+    ops.gather_batch(table, ph_tab, torch.tensor([-1]), err)
+    assert int(err.item()) == 1
+
+
+def test_trainer_step_from_ids_equals_step_from_host_rows():
+    """run_composite.py:250-308 driven by ray ids against the resident table == driven by host batch rows."""
+    from nerfca import trainer as tr
+    rays, phases, _ = parity.synthetic_batch(600, 16, seed=21)
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, 600, (3, 64), generator=g)
+    t_rand = torch.rand((3, 16), generator=g)
+    losses = []
+    for mode in ("rows", "ids"):
+        torch.manual_seed(0)
+        t = tr.CompositeTrainer.from_config(device=DEV, precision="bf16", n_depth=16)
+        t.set_iteration(50000)
+        if mode == "ids":
+            t.attach_ray_table(rays, phases)
+        out = []
+        for k in range(3):
+            if mode == "rows":
+                out.append(t.step_host(rays[ids[k]].pin_memory(), phases[ids[k]].pin_memory(), t_rand[k].pin_memory()))
+            else:
+                out.append(t.step_ids_async(ids[k].pin_memory(), t_rand[k].pin_memory()).loss())
+        losses.append((out, t.flat_p.clone()))
+    assert losses[0][0] == pytest.approx(losses[1][0], rel=1e-6)
+    assert parity.rel_l2(losses[0][1].cpu().numpy(), losses[1][1].cpu().numpy()) <= 1e-5     # fp32 atomics order only
+    t.attach_ray_table(rays, phases)
+    with pytest.raises(ValueError):
+        t.step_ids_async(torch.tensor([0, 600]).pin_memory(), t_rand[0].pin_memory()).loss()
