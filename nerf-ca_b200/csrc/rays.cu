@@ -116,10 +116,10 @@ __global__ void gather_batch_kernel(const double* __restrict__ table, const long
 
 extern "C" int nerfca_gather_batch(const double* rays_table, const int64_t* phases_table, int64_t n_table, const int64_t* ids,
                                    int32_t n_batch, double* rays_out, int32_t* phases_out, int32_t* err_flag, void* stream) {
-  NERFCA_REQUIRE(rays_table && ids && rays_out, NERFCA_E_ARG, "null pointer");
   NERFCA_REQUIRE(n_table > 0 && n_batch >= 0, NERFCA_E_ARG, "empty ray table or negative batch size");
-  NERFCA_REQUIRE(((uintptr_t)rays_table & 15) == 0 && ((uintptr_t)rays_out & 15) == 0, NERFCA_E_ARG, "ray rows must be 16-byte aligned");
   if (n_batch == 0) return NERFCA_OK;
+  NERFCA_REQUIRE(rays_table && ids && rays_out, NERFCA_E_ARG, "null pointer");
+  NERFCA_REQUIRE(((uintptr_t)rays_table & 15) == 0 && ((uintptr_t)rays_out & 15) == 0, NERFCA_E_ARG, "ray rows must be 16-byte aligned");
   gather_batch_kernel<<<div_up((long long)n_batch * 6, 256), 256, 0, (cudaStream_t)stream>>>(
       rays_table, (const long long*)phases_table, (long long)n_table, (const long long*)ids, n_batch, rays_out, phases_out, err_flag);
   NERFCA_LAUNCH_OK();

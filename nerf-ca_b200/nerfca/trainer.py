@@ -84,13 +84,16 @@ class PendingLoss:
     def __init__(self, trainer):
         self.trainer = trainer
         self.host = torch.zeros(L.N_LOSS_TERMS, dtype=torch.float64).pin_memory()
+        self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()     # set by the batch gather for a ray id outside the table
         self.event = torch.cuda.Event()
         self.n_rays_global = 0
         self.cfg = None
 
     def loss(self) -> float:
         self.event.synchronize()
-        if self.host[L.N_LOSS_TERMS - 1] != 0:      # last (otherwise unused) slot: the batch gather saw a ray id outside the table
+        if int(self.err_host[0]) != 0:
+            self.err_host.zero_()
+            self.trainer._gather_err.zero_()
             raise ValueError("ray id outside the ray table (nerfca_gather_batch)")
         return float(ops.loss_from_terms(self.host, self.cfg, self.n_rays_global, self.trainer.n_depth))
 
@@ -236,7 +239,7 @@ class CompositeTrainer:
         slot = self._pending_slots[self._pending_next % len(self._pending_slots)]
         self._pending_next += 1
         slot.host.copy_(terms, non_blocking=True)
-        slot.host[L.N_LOSS_TERMS - 1:].copy_(self._gather_err, non_blocking=True)
+        slot.err_host.copy_(self._gather_err, non_blocking=True)
         slot.event.record(torch.cuda.current_stream())
         slot.n_rays_global = rays.shape[0] * self.world_size
         slot.cfg = self.loss_cfg
