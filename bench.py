@@ -46,6 +46,16 @@ FLOP_PER_SAMPLE_FWD = 303104
 LR, LR_END_FACTOR, LR_DECAY_STEPS = 1e-3, 0.01, 150000   # composite.txt:33-35
 
 
+# The driver reads ONE JSON line from stdout: everything else that libraries print there (e.g. NCCL's version banner) is sent to
+# stderr by pointing fd 1 at fd 2 for the whole run; emit() writes the line to the saved original stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -224,7 +234,7 @@ def run_reference_arm(args):
                              "sample": f"{n} rays x {N_DEPTH} samples per step, {args.steps} steps, oracle port of the reference step "
                                        f"(CPU torch {torch.__version__}, {cores} threads)"},
             "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(extra=None):
@@ -446,7 +456,7 @@ def main():
                                          "api": "CompositeTrainer.step_ids_async(ids[B] i64, t_rand[N]) -- ray table resident in HBM, "
                                                 "batch rows gathered by nerfca_gather_batch"}},
             "roofline": roof, "render": render, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
