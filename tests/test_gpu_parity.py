@@ -421,3 +421,14 @@ def test_trainer_step_from_ids_equals_step_from_host_rows():
     t.attach_ray_table(rays, phases)
     with pytest.raises(ValueError):
         t.step_ids_async(torch.tensor([0, 600]).pin_memory(), t_rand[0].pin_memory()).loss()
+
+
+# ---- BASELINE config 5: widened stress shapes ------------------------------------------------------------------------------------
+
+def test_config5_widened_stress_shapes():
+    """hidden 256, 16 Fourier bands (D_s = 99, D_t = 107), 256 samples per ray: outside the tile shapes the tcgen05 kernels are built
+    for, so the bf16 path must refuse loudly (NotImplementedError, no silent fallback) and the fp32 SIMT path must match the oracle."""
+    res = parity.run_composite_step_parity(n_rays=24, n_depth=256, precision="fp32", seed=13, hidden=256, n_freq=16, fused=True)
+    assert res["grad_cos_min"] >= parity.TOL["fp32"]["grad_cos"]
+    with pytest.raises(NotImplementedError):
+        parity.run_composite_step_parity(n_rays=8, n_depth=256, precision="bf16", seed=13, hidden=256, n_freq=16, fused=True)
