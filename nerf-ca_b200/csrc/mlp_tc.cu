@@ -729,6 +729,15 @@ __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// CTA-scope monotonic counter in shared memory (epilogue warps -> publisher warp): unlike an mbarrier phase it cannot be overrun
+__device__ __forceinline__ void red_release_cta_shared_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 // generic-proxy global writes <-> async-proxy (bulk copy) reads of the same bytes
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // Bounded spin on a flag: a protocol bug traps (launch failure) instead of hanging the GPU.
@@ -737,7 +746,13 @@ __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t want) {
   const long long t0 = clock64();
   while (ld_acquire_gpu(p) < want) {
     __nanosleep(64);
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (clock64() - t0 > 4000000000LL) {
+#ifdef NERFCA_TIMELINE_BUILD
+      printf("flag wait timeout: block %d warp %d flag %p = %u, want %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), (const void*)p,
+             ld_acquire_gpu(p), want);
+#endif
+      __trap();
+    }
   }
 }
 
@@ -808,16 +823,17 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
   uint32_t* s_wo2 = reinterpret_cast<uint32_t*>(s_wo + 128);   // w_out as packed bf16 pairs
   float* s_g = reinterpret_cast<float*>(s_wo2 + 64);           // d_raw of the tile's rows, two tiles deep (filled by the load warp)
   float* s_gbout = s_g + 256;
+  const uint32_t pub_cnt = smem_u32(s_gbout + 1);     // warp arrivals behind dZ2 stores, 8 per tile, never reset
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_gbout + 4);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 12);
   const uint32_t bar_w = smem_u32(s_bar), bar_ldh = bar_w + 8, bar_ldm = bar_w + 16, bar_acc = bar_w + 24, bar_half = bar_w + 32,
-                 bar_mfree = bar_w + 40, bar_tile = bar_w + 48, bar_slot = bar_w + 56, bar_pub = bar_w + 64;
+                 bar_mfree = bar_w + 40, bar_tile = bar_w + 48, bar_slot = bar_w + 56, bar_h3free = bar_w + 64;
 
   if (warp == 8) {
     if (lane == 0) {
       mbar_init(bar_w, 1); mbar_init(bar_ldh, 1); mbar_init(bar_ldm, 1); mbar_init(bar_acc, 1); mbar_init(bar_half, 1);
       mbar_init(bar_mfree, 8); mbar_init(bar_tile, 1);
-      mbar_init(bar_slot, 1); mbar_init(bar_pub, 8);
+      mbar_init(bar_slot, 1); mbar_init(bar_h3free, 8);
       mbar_init_fence();
     }
     __syncwarp();
@@ -829,7 +845,7 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_wo2[i] = pack_bf16x2(__ldg(fb + 5 * 128 + 2 * i), __ldg(fb + 5 * 128 + 2 * i + 1));
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
       reinterpret_cast<uint4*>(s_ones)[i] = (i < 128) ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-    if (threadIdx.x == 0) s_gbout[0] = 0.f;
+    if (threadIdx.x == 0) { s_gbout[0] = 0.f; reinterpret_cast<uint32_t*>(s_gbout)[1] = 0u; }
   }
   tc_fence_before();
   fence_proxy_async();
@@ -878,8 +894,10 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
         NERFCA_TL(true, 2001);
         mbar_expect_tx(bar_ldm, MASK_BYTES);
         bulk_g2s(smem_u32(s_m4), st + (size_t)STASH_TILES * TILE_BYTES, MASK_BYTES, bar_ldm);
-        // H2, H3 of tile i: into the buffers that H3 / R of tile i - 1 leave when its weight gradient 4 is complete
-        if (i > 0) mbar_wait(bar_half, ph_half);
+        // H2, H3 of tile i: into the buffers that H3 / R of tile i - 1 leave when its weight gradient 4 is complete AND step B of that
+        // tile has read H3's ReLU pattern (bar_h3free; this also keeps bar_ldh from completing a second phase before every epilogue
+        // warp has seen the first: the loads are needed a whole tile later, so the extra wait costs nothing)
+        if (i > 0) { mbar_wait(bar_half, ph_half); mbar_wait(bar_h3free, ph_half); }
         NERFCA_TL(true, 2003);
         mbar_expect_tx(bar_ldh, 2 * TILE_BYTES);
         bulk_g2s(smem_u32(s_buf + (size_t)(i & 3) * TILE_BYTES), st + 2 * (size_t)TILE_BYTES, TILE_BYTES, bar_ldh);
@@ -895,14 +913,19 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
       release_slot(worker + (n_my - 1) * n_workers, 0u);
     }
   } else if (warp == 10) {
-    // ================= publisher: the epilogue warps only arrive on bar_pub behind their dZ2 stores (a CTA-scope release costs them
+    // ================= publisher: the epilogue warps only bump a shared-memory counter behind their dZ2 stores (a CTA-scope release costs them
     // nothing); the GPU-scope release -- which has to wait until those stores have reached L2 -- is paid here, off the tile's path ====
     if (lane == 0) {                // one polling lane that sleeps between probes: the epilogue warps of its scheduler keep their issue slots
       for (long long i = 0; i < n_my; ++i) {
         const long long t0 = clock64();
-        while (!mbar_try_wait(bar_pub, (uint32_t)(i & 1))) {
-          __nanosleep(500);
-          if (clock64() - t0 > 4000000000LL) __trap();
+        while (ld_acquire_cta_shared(pub_cnt) < 8u * (uint32_t)(i + 1)) {     // a counter, not an mbarrier phase: the release below may take
+          __nanosleep(200);                                                      // longer than a tile and must not lose arrivals
+          if (clock64() - t0 > 4000000000LL) {
+#ifdef NERFCA_TIMELINE_BUILD
+            printf("publisher timeout: block %d tile# %lld count %u\n", (int)blockIdx.x, i, ld_acquire_cta_shared(pub_cnt));
+#endif
+            __trap();
+          }
         }
         red_release_gpu_add(nt.produced + (worker + i * n_workers), 8u);
       }
@@ -920,13 +943,22 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
     uint32_t k_m4 = smem_u32(s_m4) + (uint32_t)row * 16u + (uint32_t)ch * 8u;
     uint32_t k_buf = smem_u32(s_buf);
     pin(k_acc); pin(k_a); pin(k_wo2); pin(k_rowoff); pin(k_m4); pin(k_buf);
-    // publish the previous tile's dZ2 (stored a whole step ago): one arrival per warp; the publisher warp raises the GPU-scope flag
-    auto publish = [&]() {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_pub);
-    };
-    uint32_t slot = (uint32_t)(worker % a.ring);      // hand-off slot of the current tile, advanced without a division per tile
+    uint32_t slot = (uint32_t)(worker % a.ring);      // hand-off slot of the tile whose dZ2 is pending, advanced without a division per tile
     const uint32_t slot_step = (uint32_t)(n_workers % a.ring);
+    // dZ2 of a tile is packed in step C but leaves one step later, right behind the next tile's step-A barrier: its 32 KB then drain
+    // through the store path while the CTA waits for dgrad 4 anyway (issued at the end of step C they sat in front of the next step's
+    // shared-memory / mbarrier traffic for ~1000 cycles).  One arrival per warp; the publisher warp raises the GPU-scope flag.
+    uint32_t dz[32];
+    auto store_dz = [&]() {
+      uint8_t* dst = nt.handoff + (size_t)slot * TILE_BYTES + k_rowoff;
+      slot += slot_step;
+      if (slot >= (uint32_t)a.ring) slot -= (uint32_t)a.ring;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)      // streaming stores straight to L2 (a plain store also goes through the L1 path and drains ~2x slower)
+        __stcs(reinterpret_cast<uint4*>(dst + c * CHUNK_BYTES), make_uint4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]));
+      __syncwarp();
+      if (lane == 0) red_release_cta_shared_add(pub_cnt, 1u);
+    };
     const uint32_t w3 = smem_u32(s_w3), w4 = smem_u32(s_w4), ones = smem_u32(s_ones);
     constexpr uint32_t KM = KSTEP_MNMAJOR;
     constexpr uint32_t id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1), id_side = instr_desc(128, 16, 1, 1);
@@ -974,6 +1006,7 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_mfree);        // the pattern and d_raw of this tile have been consumed
+      if (i > 0) mbar_wait(bar_slot, par ^ 1);      // (before the barrier, so that the loader's next arrival cannot overtake this phase)
       NERFCA_TL(warp == 1 && lane == 0, 1013);
       named_bar_sync(1, 256);
       NERFCA_TL(warp == 1 && lane == 0, 1014);
@@ -998,12 +1031,14 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
       }
       // ---- step B: dZ3 = dH3 * 1[H3 > 0] -> S (shared memory, A of wgrad 3) and tensor memory (A of dgrad 3)
       mbar_wait(bar_ldh, par);
+      if (i > 0) store_dz();                          // the previous tile's dZ2 drains while dgrad 4 runs
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
-      if (i > 0) publish();                           // (the stores were issued a whole step ago)
       NERFCA_TL(warp == 1 && lane == 0, 1020);
       ld_acc64(k_acc, va, vb);
       masked_grad_pack64(va, vb, h3 + k_rowoff, w);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_h3free);        // H3's pattern has been read: its buffer may take H2 of the next tile
       NERFCA_TL(warp == 1 && lane == 0, 1021);
       tmem_st32(k_a, w);
       sts_row64(S + k_rowoff, w);
@@ -1026,27 +1061,19 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
         }
         __syncwarp();
       }
-      // ---- step C: dZ2 = dH2 * 1[H2 > 0] -> hand-off buffer (tile-canonical bytes, straight from registers)
+      // ---- step C: dZ2 = dH2 * 1[H2 > 0] -> registers (stored behind the next tile's step-A barrier)
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
       NERFCA_TL(warp == 1 && lane == 0, 1030);
       ld_acc64(k_acc, va, vb);
-      {
-        masked_grad_pack64(va, vb, h2 + k_rowoff, w);
-        mbar_wait(bar_slot, par);
-        NERFCA_TL(warp == 1 && lane == 0, 1031);
-        uint8_t* dst = nt.handoff + (size_t)slot * TILE_BYTES + k_rowoff;
-        slot += slot_step;
-        if (slot >= (uint32_t)a.ring) slot -= (uint32_t)a.ring;
-#pragma unroll
-        for (int c = 0; c < 8; ++c)      // .cg: straight to L2 (a plain store also goes through the L1 path and takes ~2x as long to drain)
-          __stcs(reinterpret_cast<uint4*>(dst + c * CHUNK_BYTES), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
-        __syncwarp();
-      }
+      masked_grad_pack64(va, vb, h2 + k_rowoff, dz);
       tc_fence_before();
       NERFCA_TL(warp == 1 && lane == 0, 1033);
     }
-    if (n_my > 0) publish();                          // the last tile's dZ2
+    if (n_my > 0) {                                   // the last tile's dZ2
+      mbar_wait(bar_slot, (uint32_t)((n_my - 1) & 1));
+      store_dz();
+    }
     // ---- flush the TMEM-resident accumulators
     if (ch == 0) {
 #pragma unroll

@@ -11,6 +11,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace nerfca {
 namespace tc {
@@ -48,7 +49,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (clock64() - t0 > 4000000000LL) {
+#ifdef NERFCA_TIMELINE_BUILD   // developer build only: say which wait gave up
+      printf("mbar_wait timeout: block %d warp %d lane %d barrier smem+0x%x parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+             (int)(threadIdx.x & 31), bar, parity);
+#endif
+      __trap();
+    }
   }
 }
 
