@@ -266,6 +266,22 @@ NERFCA_API int nerfca_adam_step(float* params, float* grads, float* exp_avg, flo
  * nerfca_profile_read synchronises the recorded events and returns total milliseconds and launch count of a family. */
 enum { NERFCA_K_RAYS = 0, NERFCA_K_PACK = 1, NERFCA_K_FIELD_FWD = 2, NERFCA_K_LOSS = 3, NERFCA_K_FIELD_BWD = 4,
        NERFCA_K_ADAM = 5, NERFCA_K_COUNT = 6 };
+/* (e) multi-GPU (nothing upstream): the step's only exchange -- the sum of the ranks' flat gradient buffers --
+ * fused with the optimizer step of nerfca_adam_step, over NVLink / NVSwitch peer memory instead of a separate collective.
+ * Every rank's gradient buffer [n] and a signal pad (>= 1 KB of uint32, zero before the first step) must be peer-mapped;
+ * `grads` / `signals` are DEVICE arrays of world_size peer pointers in rank order, `own_signals` this rank's pad.
+ * epoch = 1, 2, 3, ... must advance by one per call on every rank.  After the call (stream order) the parameters of all
+ * ranks are bit-identical, this rank's gradient buffer is zero and *step_dev has been incremented.  The grid of the
+ * update kernel must be co-resident with its peers' (it is: n / 1024 blocks), all waits are bounded.                 */
+typedef struct nerfca_peers_t {
+  int32_t rank, world_size;
+  const float* const* grads;
+  uint32_t* const* signals;
+  uint32_t* own_signals;
+} nerfca_peers_t;
+NERFCA_API int nerfca_allreduce_adam_step(const nerfca_peers_t* peers, uint32_t epoch, float* params, float* grads, float* exp_avg,
+                               float* exp_avg_sq, int64_t n, int64_t* step_dev, const nerfca_adam_cfg_t* cfg, void* stream);
+
 NERFCA_API int64_t nerfca_launch_count(void);
 NERFCA_API int nerfca_profile_enable(int32_t on);
 NERFCA_API int nerfca_profile_read(int32_t kind, double* ms_total, int64_t* launches);

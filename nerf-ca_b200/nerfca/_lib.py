@@ -63,6 +63,11 @@ class AdamCfgStruct(C.Structure):
                 ("lr_end_factor", C.c_double), ("lr_decay_steps", C.c_int64)]
 
 
+class PeersStruct(C.Structure):          # nerfca_peers_t
+    _fields_ = [("rank", C.c_int32), ("world_size", C.c_int32), ("grads", C.c_void_p), ("signals", C.c_void_p),
+                ("own_signals", C.c_void_p)]
+
+
 K_RAYS, K_PACK, K_FIELD_FWD, K_LOSS, K_FIELD_BWD, K_ADAM, K_COUNT = range(7)
 KERNEL_FAMILY_NAMES = {K_RAYS: "rays", K_PACK: "pack_params", K_FIELD_FWD: "field_forward", K_LOSS: "integral_loss",
                        K_FIELD_BWD: "field_backward", K_ADAM: "adam"}
@@ -96,6 +101,7 @@ _SIGNATURES = {
     "nerfca_train_step": (C.c_int, [C.POINTER(StepStruct), _P]),
     "nerfca_fields_forward": (C.c_int, [C.POINTER(FieldStruct), C.POINTER(FieldStruct), C.POINTER(SamplesStruct), _I32, _P, _P, _P, _P]),
     "nerfca_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _P, C.POINTER(AdamCfgStruct), _F, _I32, _P]),
+    "nerfca_allreduce_adam_step": (C.c_int, [C.POINTER(PeersStruct), C.c_uint32, _P, _P, _P, _P, _I64, _P, C.POINTER(AdamCfgStruct), _P]),
     "nerfca_launch_count": (C.c_int64, []),
     "nerfca_profile_enable": (C.c_int, [_I32]),
     "nerfca_profile_read": (C.c_int, [_I32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

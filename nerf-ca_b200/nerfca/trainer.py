@@ -15,6 +15,8 @@ Rays are independent, so N GPUs each take B rays of the global batch and the onl
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
 from typing import Callable, Dict, Optional
 
 import numpy as np
@@ -43,16 +45,16 @@ def linear_param_decay(curr_iter, start_weight, end_weight, steps, delay_steps=0
     return (1.0 - alpha) * start_weight + alpha * end_weight
 
 
-def flatten_parameters(modules, device):
+def flatten_parameters(modules, device, grad_alloc=None):
     """Move every parameter of `modules` into one flat fp32 buffer (16-byte aligned segments) and give each a .grad view
-    into a second flat buffer.  Returns (flat_params, flat_grads)."""
+    into a second flat buffer (allocated by `grad_alloc(n)` if given, e.g. peer-mapped memory).  Returns (flat_params, flat_grads)."""
     params = [p for m in modules for p in m.parameters()]
     offs, total = [], 0
     for p in params:
         offs.append(total)
         total += (p.numel() + 3) // 4 * 4
     flat_p = torch.zeros(total, dtype=torch.float32, device=device)
-    flat_g = torch.zeros(total, dtype=torch.float32, device=device)
+    flat_g = torch.zeros(total, dtype=torch.float32, device=device) if grad_alloc is None else grad_alloc(total)
     for p, o in zip(params, offs):
         seg = flat_p[o:o + p.numel()].view(p.shape)
         seg.copy_(p.data.to(device=device, dtype=torch.float32))
@@ -75,6 +77,39 @@ def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return flat
+
+
+class PeerGradients:
+    """Peer mapping of the flat gradient buffer for nerfca_allreduce_adam_step: the buffer and a signal pad are allocated in
+    torch's symmetric memory (used for the NVLink mapping and the pointer exchange only; the reduction + optimizer kernel is
+    ours).  Raises if symmetric memory is unavailable -- the caller then stays on the NCCL all-reduce."""
+
+    def __init__(self, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.symm, self.device = symm, device
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.handle = None
+        self.epoch = 0
+
+    def alloc(self, n: int) -> torch.Tensor:
+        self.buf = self.symm.empty(n, dtype=torch.float32, device=self.device)
+        self.buf.zero_()
+        self.handle = self.symm.rendezvous(self.buf, self.group)
+        h = self.handle
+        assert h.world_size == self.world and h.rank == self.rank and h.signal_pad_size >= 1024
+        self.peers = L.PeersStruct(self.rank, self.world, int(h.buffer_ptrs_dev), int(h.signal_pad_ptrs_dev), int(h.signal_pad_ptrs[self.rank]))
+        torch.cuda.synchronize(self.device)
+        h.barrier()                                    # every rank's buffer is zeroed and mapped before anybody's first step
+        return self.buf
+
+    def step(self, flat_p, flat_g, exp_avg, exp_avg_sq, step_dev, adam_cfg):
+        assert flat_g.data_ptr() == self.buf.data_ptr()
+        self.epoch += 1
+        L.check(L.load().nerfca_allreduce_adam_step(C.byref(self.peers), self.epoch, L.ptr(flat_p), L.ptr(flat_g), L.ptr(exp_avg),
+                                                    L.ptr(exp_avg_sq), flat_p.numel(), L.ptr(step_dev), C.byref(adam_cfg), L.stream_ptr()),
+                "nerfca_allreduce_adam_step")
 
 
 class PendingLoss:
@@ -106,7 +141,17 @@ class CompositeTrainer:
         self.hp = dict(COMPOSITE_HP if hp is None else hp)
         self.output_activation = output_activation
         self.world_size, self.dist = int(world_size), process_group
-        self.flat_p, self.flat_g = flatten_parameters([static_model, temp_model], self.device)
+        # N > 1: gradient sum fused with the optimizer step over NVLink peer memory (NERFCA_FUSED_ALLREDUCE=0: NCCL all-reduce + Adam)
+        self.peer_grads = None
+        if self.world_size > 1 and self.device.type == "cuda" and os.environ.get("NERFCA_FUSED_ALLREDUCE", "1") != "0":
+            try:
+                self.peer_grads = PeerGradients(self.device)
+                self.flat_p, self.flat_g = flatten_parameters([static_model, temp_model], self.device, self.peer_grads.alloc)
+            except Exception as e:                          # symmetric memory unavailable on this box: keep the NCCL path
+                print(f"nerfca: peer-mapped gradients unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce", file=sys.stderr)
+                self.peer_grads = None
+        if self.peer_grads is None:
+            self.flat_p, self.flat_g = flatten_parameters([static_model, temp_model], self.device)
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
@@ -184,11 +229,14 @@ class CompositeTrainer:
         cfg.n_rays_global = B * self.world_size
         self.terms.zero_()
         ops.train_step_composite(self.static, self.temp, rays, phases, self._i0(B), depth, self.output_activation, cfg, self.terms)
-        if self.world_size > 1:
-            allreduce_sum_(self.flat_g)
-        L.check(L.load().nerfca_adam_step(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
-                                          self.flat_p.numel(), L.ptr(self.step_dev), C.byref(self.adam), 1.0, 1, L.stream_ptr()),
-                "nerfca_adam_step")
+        if self.peer_grads is not None:
+            self.peer_grads.step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.step_dev, self.adam)
+        else:
+            if self.world_size > 1:
+                allreduce_sum_(self.flat_g)
+            L.check(L.load().nerfca_adam_step(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                                              self.flat_p.numel(), L.ptr(self.step_dev), C.byref(self.adam), 1.0, 1, L.stream_ptr()),
+                    "nerfca_adam_step")
         self.last_terms = self.terms
         return self.terms
 

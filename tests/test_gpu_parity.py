@@ -432,3 +432,17 @@ def test_config5_widened_stress_shapes():
     assert res["grad_cos_min"] >= parity.TOL["fp32"]["grad_cos"]
     with pytest.raises(NotImplementedError):
         parity.run_composite_step_parity(n_rays=8, n_depth=256, precision="bf16", seed=13, hidden=256, n_freq=16, fused=True)
+
+
+# ---- (e) multi-GPU: gradient sum fused with the optimizer step over peer memory (needs >= 2 GPUs; skipped on a one-GPU box) -------
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_fused_allreduce_adam_matches_nccl_path():
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", os.path.join(root, "tools", "check_fused_allreduce.py")], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "replicas bit-identical True" in out.stdout
