@@ -438,6 +438,7 @@ def test_config5_widened_stress_shapes():
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_fused_allreduce_adam_matches_nccl_path():
+    import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
