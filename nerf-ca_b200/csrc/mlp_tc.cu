@@ -443,7 +443,9 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
 //     layer 0 of the slot's next tile is issued right behind it.
 //   * The stash (130 KB per tile) leaves as 16-byte streaming stores straight from the epilogue registers.  That path tops out near
 //     16 B/clk per SM (~4.7 TB/s over the chip) and is what bounds the training forward (the same kernel without a stash runs 3x
-//     faster); routing it through shared-memory staging + bulk stores was measured slower (294 vs 227 us per step).
+//     faster); routing it through shared-memory staging + bulk stores was measured slower both ways it was tried (per-warp 512-byte
+//     bulk stores: 294 us, one 32 KB bulk store per slot and layer: 301 us, against 227 us): the staging traffic competes with the
+//     MMAs' weight reads for shared-memory bandwidth.
 // smem: [packed block][barriers][band weights 32 f32][latent table 256 f32]
 __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
