@@ -203,16 +203,18 @@ __global__ void composite_loss_kernel(const float* __restrict__ raw_s, const flo
     const float bwf = sdf / (float)tot;
     double e1 = 0.0;
     if (bwf >= 1e-19f && bwf <= 1.0f) {
+      // (single-precision logarithms in this sweep: these regulariser gradients carry weights of 1e-12 .. 1e-4 against the pixel term,
+      // so a 1e-7 relative error in them is far below the fp32 rounding of d_raw itself; a double log costs ~10x as much here)
       const double b = fmin(fmax((double)bwf, 1e-19), 1.0);
       const double omb = 1.0 - b;
-      e1 = -(log(b) + 1.0);
-      if (omb >= 1e-19) e1 += log(omb) + 1.0;
+      e1 = -((double)logf((float)b) + 1.0);
+      if (omb >= 1e-19) e1 += (double)logf((float)omb) + 1.0;
     }
     const double kf = c.c_f / BN * e1 / (tot * tot);
     const double g_fd = kf * (ss + 1e-10), g_fs = kf * (-sd);
     // dynamic ray entropy
     const double pd = sd * d / Sd_hat;
-    const double h = -(log(pd + 1e-10) + pd / (pd + 1e-10));
+    const double h = -((double)logf((float)(pd + 1e-10)) + pd / (pd + 1e-10));
     const double g_ed = mask_d ? c.c_e / B * (h - live_d * hp_d) / Sd_hat * d : 0.0;
     const double g_od = c.c_o / B * d;
     const double g_ls = c.c_l * (d + 2.0 * ss * d * d);
