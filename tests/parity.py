@@ -175,3 +175,30 @@ def run_composite_step_parity(n_rays=64, n_depth=40, precision="bf16", seed=0, h
     return {"precision": precision, "loss": float(loss), "loss_oracle": float(loss_o), "loss_rel_err": loss_err,
             "pix_max_abs_err": float(np.max(np.abs(pix.detach().cpu().numpy() - out_o["pix"].detach().numpy()))),
             "grad_rel_l2_max": max(ws["rel"], wd["rel"]), "grad_cos_min": min(ws["cos"], wd["cos"])}
+
+
+def run_static_step_parity(n_rays=200, n_depth=96, precision="bf16", seed=0, hidden=128, n_early=4, n_freq=12, it=50000,
+                           occl_weight=1e-4, device="cuda:0"):
+    """One static-only training step (run_nerf.py:205-230, BASELINE config 1 shapes) on the GPU through the fused static step
+    against the oracle: one field, so the tensor-core kernels run with a single net per launch."""
+    from nerfca import ops
+    tol = TOL[precision]
+    enc_dim = 3 + 6 * n_freq
+    sd_s = orc.init_field_state(enc_dim, hidden, n_early, seed=seed + 1)
+    mask, _ = orc.freq_mask(n_freq, it, 150000, 1)
+    cfg = {"n_freq": n_freq, "n_hidden": n_early, "pos_enc": "free_windowed", "window": mask}
+    rays, _, z = synthetic_batch(n_rays, n_depth, seed)
+    sd_o = {k: v.clone().requires_grad_(True) for k, v in sd_s.items()}
+    i0 = torch.full((n_rays,), I0, dtype=torch.float32)
+    loss_o, out_o = orc.static_step_loss(sd_o, cfg, rays[:, 0, :], rays[:, 1, :], i0, z, rays[:, 2, 0], rays[:, 3, 0], occl_weight)
+    loss_o.backward()
+    dev = torch.device(device)
+    static, _ = build_models(sd_s, None, dev, precision, hidden, n_early, n_freq, mask=mask)
+    tv, pix = ops.train_step_static(static, rays.to(dev), i0.to(dev), z.to(dev), "softplus", occl_weight)
+    loss = ops.loss_from_terms(tv, ops.LossConfig(occl_weight=occl_weight), n_rays, n_depth, static_only=True)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(pix.detach().cpu().numpy(), out_o["pix"].detach().numpy(), rtol=tol["pix_rtol"], atol=tol["pix_atol"])
+    loss_err = abs(float(loss) - float(loss_o)) / abs(float(loss_o))
+    assert loss_err <= (1e-4 if precision == "fp32" else 2e-2), f"loss {float(loss)} vs oracle {float(loss_o)}"
+    w = compare_grads({k: p.grad for k, p in static.named_parameters()}, {k: v.grad for k, v in sd_o.items()}, tol, "static.")
+    return {"precision": precision, "loss_rel_err": loss_err, "grad_rel_l2_max": w["rel"], "grad_cos_min": w["cos"]}

@@ -334,6 +334,16 @@ def test_composite_step_vs_oracle(precision, fused):
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
+def test_static_step_vs_oracle_config1_shapes(precision):
+    """BASELINE config 1 (3d.txt: one static field, hidden 128, 12 bands): the fused static step, one net per tensor-core launch,
+    a ragged tile count (200 x 96 = 150 tiles) and a batch that is not a multiple of anything."""
+    res = parity.run_static_step_parity(n_rays=200, n_depth=96, precision=precision, seed=3)
+    assert res["grad_cos_min"] >= parity.TOL[precision]["grad_cos"]
+    res = parity.run_static_step_parity(n_rays=37, n_depth=500, precision=precision, seed=4)
+    assert res["grad_cos_min"] >= parity.TOL[precision]["grad_cos"]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
 def test_composite_step_30_phases(precision):
     """BASELINE config 3: 30 cardiac phases (time_latents [30, 8]).  On the tensor-core path the latent gradient then takes the
     explicit latent-dgrad + scatter-by-phase route (30 one-hot columns do not fit the padded first layer)."""
