@@ -914,6 +914,49 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
       mbar_wait(bar_mfree, ph_mfree);                   // step A of the last tile
       release_slot(worker + (n_my - 1) * n_workers, 0u);
     }
+  } else if (warp == 9) {
+    // ================= issuing warp: joins the epilogue warps' two named barriers per tile and issues, in the order the results are
+    // needed, the dgrad GEMM everybody waits for and then the weight / bias gradient GEMMs nobody waits for.  (The tensor pipe runs
+    // MMAs in issue order at ~68 cycles per 128x128x16 step and the issuing lane stalls while the queue is full: ~1300 cycles per
+    // step.  As one of the epilogue warps -- the previous arrangement -- that lane made its warp ~500 cycles late for the step's
+    // epilogue and the whole CTA waited for it at the next barrier.  Handing over through an mbarrier instead of sharing the named
+    // barrier, or issuing from several lanes at once, were both measured slower.)
+    const uint32_t w3 = smem_u32(s_w3), w4 = smem_u32(s_w4), ones = smem_u32(s_ones), bufs = smem_u32(s_buf);
+    constexpr uint32_t KM = KSTEP_MNMAJOR;
+    constexpr uint32_t id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1), id_side = instr_desc(128, 16, 1, 1);
+    const uint32_t td_acc = tmem + TOP_ACC, td_a = tmem + TOP_A;
+    mbar_wait(bar_w, 0);
+    for (long long i = 0; i < n_my; ++i) {
+      const uint32_t par = (uint32_t)(i & 1), first = (i > 0) ? 1u : 0u;
+      const uint32_t h2 = bufs + (uint32_t)(i & 3) * TILE_BYTES, h3 = bufs + (uint32_t)((i + 1) & 3) * TILE_BYTES,
+                     R = bufs + (uint32_t)((i + 2) & 3) * TILE_BYTES, S = bufs + (uint32_t)((i + 3) & 3) * TILE_BYTES;
+      named_bar_sync(1, 288);                         // step A: R (shared memory) and dZ4 (tensor memory) are complete
+      tc_fence_after();
+      if (elect_one()) {
+        NERFCA_TL(true, 3010);
+        umma_ts_k<8, KM>(td_acc, td_a, mnmajor(w4), id_dgrad, 0);                                    // dH3 = dZ4 W4
+        umma_commit(bar_acc);
+        mbar_wait(bar_ldh, par);
+        tc_fence_after();
+        umma_k<8, KM, KM>(tmem + TOP_WG4, mnmajor(R), mnmajor(h3), id_wgrad, first);                 // WG4 += R^T H3
+        umma_k<8, KM, KM>(tmem + TOP_BG4, mnmajor(R), mnmajor(ones), id_side, first);                // BG4 += colsum(R)
+        umma_commit(bar_half);
+        NERFCA_TL(true, 3011);
+      }
+      __syncwarp();
+      named_bar_sync(1, 288);                         // step B: S and dZ3 are complete
+      tc_fence_after();
+      if (elect_one()) {
+        NERFCA_TL(true, 3020);
+        umma_ts_k<8, KM>(td_acc, td_a, mnmajor(w3), id_dgrad, 0);                                    // dH2 = dZ3 W3
+        umma_commit(bar_acc);
+        umma_k<8, KM, KM>(tmem + TOP_WG3, mnmajor(S), mnmajor(h2), id_wgrad, first);                 // WG3 += S^T H2
+        umma_k<8, KM, KM>(tmem + TOP_BG3, mnmajor(S), mnmajor(ones), id_side, first);                // BG3 += colsum(S)
+        umma_commit(bar_tile);
+        NERFCA_TL(true, 3021);
+      }
+      __syncwarp();
+    }
   } else if (warp == 10) {
     // ================= publisher: the epilogue warps only bump a shared-memory counter behind their dZ2 stores (a CTA-scope release costs them
     // nothing); the GPU-scope release -- which has to wait until those stores have reached L2 -- is paid here, off the tile's path ====
@@ -961,10 +1004,6 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
       __syncwarp();
       if (lane == 0) red_release_cta_shared_add(pub_cnt, 1u);
     };
-    const uint32_t w3 = smem_u32(s_w3), w4 = smem_u32(s_w4), ones = smem_u32(s_ones);
-    constexpr uint32_t KM = KSTEP_MNMAJOR;
-    constexpr uint32_t id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1), id_side = instr_desc(128, 16, 1, 1);
-    const uint32_t td_acc = tmem + TOP_ACC, td_a = tmem + TOP_A;
     uint32_t ph_acc = 0;
     float gb_sum = 0.f;
     mbar_wait(bar_w, 0);
@@ -972,7 +1011,6 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
       const uint32_t par = (uint32_t)(i & 1);
       const uint32_t h2 = k_buf + (uint32_t)(i & 3) * TILE_BYTES, h3 = k_buf + (uint32_t)((i + 1) & 3) * TILE_BYTES,
                      R = k_buf + (uint32_t)((i + 2) & 3) * TILE_BYTES, S = k_buf + (uint32_t)((i + 3) & 3) * TILE_BYTES;
-      const uint32_t first = (i > 0) ? 1u : 0u;
       uint32_t va[32], vb[32], w[32];
       // ---- step A: R = dZ4' = d_raw 1[H4 > 0] (shared memory, A of wgrad 4), A = dZ4 = dZ4' w_out (tensor memory, A of dgrad 4)
       mbar_wait(bar_ldm, par);
@@ -1010,27 +1048,8 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
       if (lane == 0) mbar_arrive(bar_mfree);        // the pattern and d_raw of this tile have been consumed
       if (i > 0) mbar_wait(bar_slot, par ^ 1);      // (before the barrier, so that the loader's next arrival cannot overtake this phase)
       NERFCA_TL(warp == 1 && lane == 0, 1013);
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 288);       // 8 epilogue warps + the issuing warp
       NERFCA_TL(warp == 1 && lane == 0, 1014);
-      // One lane issues everything in the order the results are needed: the dgrad GEMM first, then the weight / bias gradient GEMMs
-      // nobody waits for.  (The tensor pipe executes MMAs in issue order at ~68 cycles per 128x128x16 step and the issuing lane stalls
-      // while the queue is full, so the ~1300 cycles spent here are tensor-pipe time; issuing from three lanes at once, or from a
-      // dedicated warp behind an mbarrier hand-over, were both measured slower.)
-      if (warp == 0) {
-        tc_fence_after();
-        if (elect_one()) {
-          NERFCA_TL(true, 3010);
-          umma_ts_k<8, KM>(td_acc, td_a, mnmajor(w4), id_dgrad, 0);                                  // dH3 = dZ4 W4
-          umma_commit(bar_acc);
-          mbar_wait(bar_ldh, par);
-          tc_fence_after();
-          umma_k<8, KM, KM>(tmem + TOP_WG4, mnmajor(R), mnmajor(h3), id_wgrad, first);               // WG4 += R^T H3
-          umma_k<8, KM, KM>(tmem + TOP_BG4, mnmajor(R), mnmajor(ones), id_side, first);              // BG4 += colsum(R)
-          umma_commit(bar_half);
-          NERFCA_TL(true, 3011);
-        }
-        __syncwarp();
-      }
       // ---- step B: dZ3 = dH3 * 1[H3 > 0] -> S (shared memory, A of wgrad 3) and tensor memory (A of dgrad 3)
       mbar_wait(bar_ldh, par);
       if (i > 0) store_dz();                          // the previous tile's dZ2 drains while dgrad 4 runs
@@ -1048,21 +1067,8 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
       tc_fence_before();
       fence_proxy_async();
       NERFCA_TL(warp == 1 && lane == 0, 1023);
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 288);       // 8 epilogue warps + the issuing warp
       NERFCA_TL(warp == 1 && lane == 0, 1024);
-      if (warp == 0) {
-        tc_fence_after();
-        if (elect_one()) {
-          NERFCA_TL(true, 3020);
-          umma_ts_k<8, KM>(td_acc, td_a, mnmajor(w3), id_dgrad, 0);                                  // dH2 = dZ3 W3
-          umma_commit(bar_acc);
-          umma_k<8, KM, KM>(tmem + TOP_WG3, mnmajor(S), mnmajor(h2), id_wgrad, first);               // WG3 += S^T H2
-          umma_k<8, KM, KM>(tmem + TOP_BG3, mnmajor(S), mnmajor(ones), id_side, first);              // BG3 += colsum(S)
-          umma_commit(bar_tile);
-          NERFCA_TL(true, 3021);
-        }
-        __syncwarp();
-      }
       // ---- step C: dZ2 = dH2 * 1[H2 > 0] -> registers (stored behind the next tile's step-A barrier)
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
@@ -1184,8 +1190,69 @@ __device__ __forceinline__ void bwd_bot_role(const BwdArgs& a, const BwdNet& nt,
   [[maybe_unused]] int tl_n = 0;
 
   if (warp >= 12) {
-    // ================= warp 12: loader (warps 13-15 only fill the warpgroup) =================
-    reg_dealloc<24>();
+    // ================= warp 12: loader, warp 13: issuing warp (warps 14-15 only fill the warpgroup) =================
+    reg_dealloc<48>();
+    if (warp == 13) {
+      // joins the epilogue warps' named barriers and issues every GEMM of the tile in the order the results are needed (see the top role)
+      const uint32_t w1 = smem_u32(s_w1), w2 = smem_u32(s_w2), ones = smem_u32(s_ones), x0 = smem_u32(s_x0), w0lat = smem_u32(s_w0lat),
+                     bufs = smem_u32(s_buf);
+      constexpr uint32_t KK = KSTEP_KMAJOR, KM = KSTEP_MNMAJOR;
+      constexpr uint32_t id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1), id_side = instr_desc(128, 16, 1, 1);
+      const uint32_t id_wg0 = instr_desc(128, kpad0, 1, 1), id_lat = instr_desc(128, lat_n > 0 ? lat_n : 16, 0, 1);
+      const uint32_t td_acc = tmem + BOT_ACC;
+      mbar_wait(bar_w, 0);
+      for (long long i = 0; i < n_my; ++i) {
+        const uint32_t par = (uint32_t)(i & 1), first = (i > 0) ? 1u : 0u;
+        const uint32_t dz2 = bufs + (uint32_t)(i & 3) * TILE_BYTES, h1 = bufs + (uint32_t)((i + 1) & 3) * TILE_BYTES,
+                       h0 = bufs + (uint32_t)((i + 2) & 3) * TILE_BYTES, dz1 = bufs + (uint32_t)((i + 3) & 3) * TILE_BYTES, dz0 = dz2;
+        // ---- tile start: dH1 = dZ2 W2 (the barrier that closed the previous tile released the accumulator)
+        tc_fence_after();
+        if (elect_one()) {
+          mbar_wait(bar_ld_dz, par);
+          tc_fence_after();
+          NERFCA_TL(true, 3000);
+          umma_k<8, KK, KM>(td_acc, kmajor(dz2), mnmajor(w2), id_dgrad, 0);
+          umma_commit(bar_acc);
+          mbar_wait(bar_ld_h1, par);
+          tc_fence_after();
+          umma_k<8, KM, KM>(tmem + BOT_WG2, mnmajor(dz2), mnmajor(h1), id_wgrad, first);             // WG2 += dZ2^T H1
+          umma_k<8, KM, KM>(tmem + BOT_BG2, mnmajor(dz2), mnmajor(ones), id_side, first);            // BG2 += colsum(dZ2)
+          NERFCA_TL(true, 3001);
+        }
+        __syncwarp();
+        named_bar_sync(1, 288);                       // step B: dZ1 is complete
+        tc_fence_after();
+        if (elect_one()) {
+          NERFCA_TL(true, 3010);
+          umma_commit(bar_free1);      // wgrad 2 complete and H1's pattern read: H1's buffer may take dZ2 of the next tile
+          umma_k<8, KK, KM>(td_acc, kmajor(dz1), mnmajor(w1), id_dgrad, 0);                          // dH0 = dZ1 W1
+          umma_commit(bar_acc);
+          mbar_wait(bar_ld_h0, par);
+          tc_fence_after();
+          umma_k<8, KM, KM>(tmem + BOT_WG1, mnmajor(dz1), mnmajor(h0), id_wgrad, first);             // WG1 += dZ1^T H0
+          umma_k<8, KM, KM>(tmem + BOT_BG1, mnmajor(dz1), mnmajor(ones), id_side, first);            // BG1 += colsum(dZ1)
+          NERFCA_TL(true, 3011);
+        }
+        __syncwarp();
+        named_bar_sync(1, 288);                       // step C: dZ0 is complete
+        tc_fence_after();
+        if (elect_one()) {
+          NERFCA_TL(true, 3020);
+          umma_commit(bar_free2);      // wgrad 1 complete and H0's pattern read: the H0 / dZ1 buffers may be reloaded
+          mbar_wait(bar_x0, par);
+          tc_fence_after();
+          umma_k<8, KM, KM>(tmem + BOT_WG0, mnmajor(dz0), mnmajor(x0), id_wg0, first);               // WG0 += dZ0^T X0 (same lane as the next
+          umma_commit(bar_x0free);                                                                    // dgrad 2: its commit covers this read of dZ0)
+          if (has_lat) {
+            umma_k<8, KK, KM>(td_acc, kmajor(dz0), mnmajor(w0lat), id_lat, 0);                       // latent columns of dX0
+            umma_commit(bar_acc);
+          }
+          NERFCA_TL(true, 3021);
+        }
+        __syncwarp();
+        if (has_lat) named_bar_sync(1, 288);          // the epilogue has read the latent columns: the accumulator is free again
+      }
+    }
     if (warp == 12 && lane == 0) {
       const uint32_t lat_bytes = has_lat ? (uint32_t)(lat_n / 8) * CHUNK_BYTES : 0u;
       mbar_expect_tx(bar_w, 2 * TILE_BYTES + lat_bytes);
@@ -1254,11 +1321,6 @@ __device__ __forceinline__ void bwd_bot_role(const BwdArgs& a, const BwdNet& nt,
     uint32_t k_rowoff = (uint32_t)(ch * 8) * CHUNK_BYTES + (uint32_t)row * 16u;     // this thread's first chunk inside a tile
     uint32_t k_buf = smem_u32(s_buf);
     pin(k_acc); pin(k_rowoff); pin(k_buf);
-    const uint32_t w1 = smem_u32(s_w1), w2 = smem_u32(s_w2), ones = smem_u32(s_ones), x0 = smem_u32(s_x0), w0lat = smem_u32(s_w0lat);
-    constexpr uint32_t KK = KSTEP_KMAJOR, KM = KSTEP_MNMAJOR;
-    constexpr uint32_t id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1), id_side = instr_desc(128, 16, 1, 1);
-    const uint32_t id_wg0 = instr_desc(128, kpad0, 1, 1), id_lat = instr_desc(128, lat_n > 0 ? lat_n : 16, 0, 1);
-    const uint32_t td_acc = tmem + BOT_ACC;
     uint32_t ph_acc = 0;
     mbar_wait(bar_w, 0);
     for (long long i = 0; i < n_my; ++i) {
@@ -1268,24 +1330,7 @@ __device__ __forceinline__ void bwd_bot_role(const BwdArgs& a, const BwdNet& nt,
       const uint32_t par = (uint32_t)(i & 1);
       const uint32_t dz2 = k_buf + (uint32_t)(i & 3) * TILE_BYTES, h1 = k_buf + (uint32_t)((i + 1) & 3) * TILE_BYTES,
                      h0 = k_buf + (uint32_t)((i + 2) & 3) * TILE_BYTES, dz1 = k_buf + (uint32_t)((i + 3) & 3) * TILE_BYTES, dz0 = dz2;
-      const uint32_t first = (i > 0) ? 1u : 0u;
       uint32_t va[32], vb[32], w[32];
-      // ---- issue dgrad 2: dH1 = dZ2 W2 (the barrier that closed the previous tile released the accumulator)
-      if (warp == 0) {
-        if (elect_one()) {
-          mbar_wait(bar_ld_dz, par);
-          tc_fence_after();
-          NERFCA_TL(true, 3000);
-          umma_k<8, KK, KM>(td_acc, kmajor(dz2), mnmajor(w2), id_dgrad, 0);
-          umma_commit(bar_acc);
-          mbar_wait(bar_ld_h1, par);
-          tc_fence_after();
-          umma_k<8, KM, KM>(tmem + BOT_WG2, mnmajor(dz2), mnmajor(h1), id_wgrad, first);             // WG2 += dZ2^T H1
-          umma_k<8, KM, KM>(tmem + BOT_BG2, mnmajor(dz2), mnmajor(ones), id_side, first);            // BG2 += colsum(dZ2)
-          NERFCA_TL(true, 3001);
-        }
-        __syncwarp();
-      }
       // ---- step B: dZ1 = dH1 * 1[H1 > 0] -> shared memory (A of dgrad 1 and of wgrad 1)
       mbar_wait(bar_ld_h1, par);
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
@@ -1297,23 +1342,8 @@ __device__ __forceinline__ void bwd_bot_role(const BwdArgs& a, const BwdNet& nt,
       sts_row64(dz1 + k_rowoff, w);
       tc_fence_before();
       fence_proxy_async();
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 288);       // 8 epilogue warps + the issuing warp
       NERFCA_TL(warp == 1 && lane == 0, 1014);
-      if (warp == 0) {
-        tc_fence_after();
-        if (elect_one()) {
-          NERFCA_TL(true, 3010);
-          umma_commit(bar_free1);      // wgrad 2 complete and H1's pattern read: H1's buffer may take dZ2 of the next tile
-          umma_k<8, KK, KM>(td_acc, kmajor(dz1), mnmajor(w1), id_dgrad, 0);                          // dH0 = dZ1 W1
-          umma_commit(bar_acc);
-          mbar_wait(bar_ld_h0, par);
-          tc_fence_after();
-          umma_k<8, KM, KM>(tmem + BOT_WG1, mnmajor(dz1), mnmajor(h0), id_wgrad, first);             // WG1 += dZ1^T H0
-          umma_k<8, KM, KM>(tmem + BOT_BG1, mnmajor(dz1), mnmajor(ones), id_side, first);            // BG1 += colsum(dZ1)
-          NERFCA_TL(true, 3011);
-        }
-        __syncwarp();
-      }
       // ---- step C: dZ0 = dH0 * 1[H0 > 0] -> shared memory (A of wgrad 0), into the buffer dZ2 occupied
       mbar_wait(bar_ld_h0, par);
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
@@ -1326,25 +1356,8 @@ __device__ __forceinline__ void bwd_bot_role(const BwdArgs& a, const BwdNet& nt,
       sts_row64(dz0 + k_rowoff, w);
       tc_fence_before();
       fence_proxy_async();
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 288);       // 8 epilogue warps + the issuing warp
       NERFCA_TL(warp == 1 && lane == 0, 1024);
-      if (warp == 0) {
-        tc_fence_after();
-        if (elect_one()) {
-          NERFCA_TL(true, 3020);
-          umma_commit(bar_free2);      // wgrad 1 complete and H0's pattern read: the H0 / dZ1 buffers may be reloaded
-          mbar_wait(bar_x0, par);
-          tc_fence_after();
-          umma_k<8, KM, KM>(tmem + BOT_WG0, mnmajor(dz0), mnmajor(x0), id_wg0, first);               // WG0 += dZ0^T X0 (same thread as the next
-          umma_commit(bar_x0free);                                                                    // dgrad 2: its commit covers this read of dZ0)
-          if (has_lat) {
-            umma_k<8, KK, KM>(td_acc, kmajor(dz0), mnmajor(w0lat), id_lat, 0);                       // latent columns of dX0
-            umma_commit(bar_acc);
-          }
-          NERFCA_TL(true, 3021);
-        }
-        __syncwarp();
-      }
       // ---- latent gradient (fallback): columns [enc_dim, enc_dim + T) of dX0 sit at accumulator columns enc_dim - 8 * lat_c0 + t
       if (has_lat) {
         mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
@@ -1376,7 +1389,7 @@ __device__ __forceinline__ void bwd_bot_role(const BwdArgs& a, const BwdNet& nt,
           }
         }
         tc_fence_before();
-        named_bar_sync(1, 256);        // the accumulator has been read: the next tile's dgrad 2 may overwrite it
+        named_bar_sync(1, 288);        // (+ the issuing warp) the accumulator has been read: the next tile's dgrad 2 may overwrite it
       }
       // (without the fallback the accumulator was last read before the barrier of step C)
     }
@@ -1609,7 +1622,7 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
   }
   // role split: n_top + n_bot CTAs per net, all resident at once (one CTA per SM).  NERFCA_BWD_SPLIT="n_top,n_bot" overrides it.
   const int per_net = sm_count() / n_nets;
-  int n_top = per_net / 2, n_bot = per_net - per_net / 2;
+  int n_top = (per_net * 9 + 10) / 20, n_bot = per_net - n_top;      // measured optimum 33 : 41 of 74 (the bottom role has three layers)
   if (!merged) n_top = n_bot = per_net;          // two launches: every SM runs the top role, then every SM the bottom role
   else if (const char* e = getenv("NERFCA_BWD_SPLIT")) {
     int t = 0, b = 0;
