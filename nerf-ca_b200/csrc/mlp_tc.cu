@@ -776,7 +776,12 @@ __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t want) {
 //   * Four 32 KB tile buffers rotate: role k of tile i (0: H2, 1: H3, 2: R, 3: S) lives in buffer (i + k) % 4, so the loads of
 //     tile i + 1 go into the buffers H3 / R of tile i vacate when weight gradient 4 completes.
 // TMEM: ACC [0,128) | WG4 [128,256) | WG3 [256,384) | BG4 [384,400) | BG3 [400,416) | A [416,480)
-constexpr uint32_t TOP_ACC = 0, TOP_WG4 = 128, TOP_WG3 = 256, TOP_BG4 = 384, TOP_BG3 = 400, TOP_A = 416;
+// (each weight-gradient accumulator is 144 columns wide: column 128 collects the bias gradient, see TOP_BUF_STRIDE)
+constexpr uint32_t TOP_ACC = 0, TOP_WG4 = 128, TOP_WG3 = 272, TOP_BG4 = TOP_WG4 + 128, TOP_BG3 = TOP_WG3 + 128, TOP_A = 416;
+// A tile buffer is followed by a constant [128 x 16] bf16 block whose column 0 is 1: read MN-major as the B operand, buffer + tail
+// are a [128 x 144] matrix, so ONE N = 144 GEMM yields dZ^T H (columns 0-127) and colsum(dZ) (column 128).  (The separate N = 16
+// bias GEMMs re-read the whole A operand and cost the tensor pipe about as much as the N = 128 ones.)
+constexpr uint32_t TOP_BUF_STRIDE = TILE_BYTES + 4096;
 constexpr int BWD_THREADS = 16 * 32;   // both roles: warps 0-7 epilogue (warp 0 holds the issuing lane); top: 8 loader; bottom: 8-11 X0, 12 loader
 constexpr int BWD_RING = 128;          // hand-off slots per net (4 MB: lives in L2)
 
@@ -818,9 +823,8 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* s_w3 = smem;
   uint8_t* s_w4 = smem + TILE_BYTES;
-  uint8_t* s_buf = smem + 2 * TILE_BYTES;            // 4 rotating tile buffers
-  uint8_t* s_ones = s_buf + 4 * TILE_BYTES;          // [128 x 16] bf16, column 0 = 1: B operand of the bias-gradient GEMMs
-  uint8_t* s_m4 = s_ones + 4096;                     // high bytes of H4 of the current tile
+  uint8_t* s_buf = smem + 2 * TILE_BYTES;            // 4 rotating tile buffers, each followed by its constant-1 block
+  uint8_t* s_m4 = s_buf + 4 * TOP_BUF_STRIDE;        // ReLU pattern of H4 of the current tile (1 bit per element)
   float* s_wo = reinterpret_cast<float*>(s_m4 + MASK_BYTES);
   uint32_t* s_wo2 = reinterpret_cast<uint32_t*>(s_wo + 128);   // w_out as packed bf16 pairs
   float* s_g = reinterpret_cast<float*>(s_wo2 + 64);           // d_raw of the tile's rows, two tiles deep (filled by the load warp)
@@ -845,8 +849,9 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
     const float* fb = reinterpret_cast<const float*>(nt.pack + nt.f32_off);
     for (int i = threadIdx.x; i < 128; i += blockDim.x) s_wo[i] = __ldg(fb + 5 * 128 + i);
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_wo2[i] = pack_bf16x2(__ldg(fb + 5 * 128 + 2 * i), __ldg(fb + 5 * 128 + 2 * i + 1));
-    for (int i = threadIdx.x; i < 256; i += blockDim.x)
-      reinterpret_cast<uint4*>(s_ones)[i] = (i < 128) ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x)      // the constant-1 block behind each tile buffer
+      reinterpret_cast<uint4*>(s_buf + (size_t)(i >> 8) * TOP_BUF_STRIDE + TILE_BYTES)[i & 255] =
+          ((i & 255) < 128) ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
     if (threadIdx.x == 0) { s_gbout[0] = 0.f; reinterpret_cast<uint32_t*>(s_gbout)[1] = 0u; }
   }
   tc_fence_before();
@@ -902,8 +907,8 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
         if (i > 0) { mbar_wait(bar_half, ph_half); mbar_wait(bar_h3free, ph_half); }
         NERFCA_TL(true, 2003);
         mbar_expect_tx(bar_ldh, 2 * TILE_BYTES);
-        bulk_g2s(smem_u32(s_buf + (size_t)(i & 3) * TILE_BYTES), st + 2 * (size_t)TILE_BYTES, TILE_BYTES, bar_ldh);
-        bulk_g2s(smem_u32(s_buf + (size_t)((i + 1) & 3) * TILE_BYTES), st + 3 * (size_t)TILE_BYTES, TILE_BYTES, bar_ldh);
+        bulk_g2s(smem_u32(s_buf + (size_t)(i & 3) * TOP_BUF_STRIDE), st + 2 * (size_t)TILE_BYTES, TILE_BYTES, bar_ldh);
+        bulk_g2s(smem_u32(s_buf + (size_t)((i + 1) & 3) * TOP_BUF_STRIDE), st + 3 * (size_t)TILE_BYTES, TILE_BYTES, bar_ldh);
         if (i > 0) release_slot(tile - n_workers, seen);
         NERFCA_TL(true, 2005);
       }
@@ -921,15 +926,15 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
     // step.  As one of the epilogue warps -- the previous arrangement -- that lane made its warp ~500 cycles late for the step's
     // epilogue and the whole CTA waited for it at the next barrier.  Handing over through an mbarrier instead of sharing the named
     // barrier, or issuing from several lanes at once, were both measured slower.)
-    const uint32_t w3 = smem_u32(s_w3), w4 = smem_u32(s_w4), ones = smem_u32(s_ones), bufs = smem_u32(s_buf);
+    const uint32_t w3 = smem_u32(s_w3), w4 = smem_u32(s_w4), bufs = smem_u32(s_buf);
     constexpr uint32_t KM = KSTEP_MNMAJOR;
-    constexpr uint32_t id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1), id_side = instr_desc(128, 16, 1, 1);
+    constexpr uint32_t id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 144, 1, 1);
     const uint32_t td_acc = tmem + TOP_ACC, td_a = tmem + TOP_A;
     mbar_wait(bar_w, 0);
     for (long long i = 0; i < n_my; ++i) {
       const uint32_t par = (uint32_t)(i & 1), first = (i > 0) ? 1u : 0u;
-      const uint32_t h2 = bufs + (uint32_t)(i & 3) * TILE_BYTES, h3 = bufs + (uint32_t)((i + 1) & 3) * TILE_BYTES,
-                     R = bufs + (uint32_t)((i + 2) & 3) * TILE_BYTES, S = bufs + (uint32_t)((i + 3) & 3) * TILE_BYTES;
+      const uint32_t h2 = bufs + (uint32_t)(i & 3) * TOP_BUF_STRIDE, h3 = bufs + (uint32_t)((i + 1) & 3) * TOP_BUF_STRIDE,
+                     R = bufs + (uint32_t)((i + 2) & 3) * TOP_BUF_STRIDE, S = bufs + (uint32_t)((i + 3) & 3) * TOP_BUF_STRIDE;
       named_bar_sync(1, 288);                         // step A: R (shared memory) and dZ4 (tensor memory) are complete
       tc_fence_after();
       if (elect_one()) {
@@ -938,8 +943,7 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
         umma_commit(bar_acc);
         mbar_wait(bar_ldh, par);
         tc_fence_after();
-        umma_k<8, KM, KM>(tmem + TOP_WG4, mnmajor(R), mnmajor(h3), id_wgrad, first);                 // WG4 += R^T H3
-        umma_k<8, KM, KM>(tmem + TOP_BG4, mnmajor(R), mnmajor(ones), id_side, first);                // BG4 += colsum(R)
+        umma_k<8, KM, KM>(tmem + TOP_WG4, mnmajor(R), mnmajor(h3), id_wgrad, first);                 // WG4 += R^T [H3 | 1]
         umma_commit(bar_half);
         NERFCA_TL(true, 3011);
       }
@@ -950,8 +954,7 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
         NERFCA_TL(true, 3020);
         umma_ts_k<8, KM>(td_acc, td_a, mnmajor(w3), id_dgrad, 0);                                    // dH2 = dZ3 W3
         umma_commit(bar_acc);
-        umma_k<8, KM, KM>(tmem + TOP_WG3, mnmajor(S), mnmajor(h2), id_wgrad, first);                 // WG3 += S^T H2
-        umma_k<8, KM, KM>(tmem + TOP_BG3, mnmajor(S), mnmajor(ones), id_side, first);                // BG3 += colsum(S)
+        umma_k<8, KM, KM>(tmem + TOP_WG3, mnmajor(S), mnmajor(h2), id_wgrad, first);                 // WG3 += S^T [H2 | 1]
         umma_commit(bar_tile);
         NERFCA_TL(true, 3021);
       }
@@ -1009,8 +1012,8 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
     mbar_wait(bar_w, 0);
     for (long long i = 0; i < n_my; ++i) {
       const uint32_t par = (uint32_t)(i & 1);
-      const uint32_t h2 = k_buf + (uint32_t)(i & 3) * TILE_BYTES, h3 = k_buf + (uint32_t)((i + 1) & 3) * TILE_BYTES,
-                     R = k_buf + (uint32_t)((i + 2) & 3) * TILE_BYTES, S = k_buf + (uint32_t)((i + 3) & 3) * TILE_BYTES;
+      const uint32_t h2 = k_buf + (uint32_t)(i & 3) * TOP_BUF_STRIDE, h3 = k_buf + (uint32_t)((i + 1) & 3) * TOP_BUF_STRIDE,
+                     R = k_buf + (uint32_t)((i + 2) & 3) * TOP_BUF_STRIDE, S = k_buf + (uint32_t)((i + 3) & 3) * TOP_BUF_STRIDE;
       uint32_t va[32], vb[32], w[32];
       // ---- step A: R = dZ4' = d_raw 1[H4 > 0] (shared memory, A of wgrad 4), A = dZ4 = dZ4' w_out (tensor memory, A of dgrad 4)
       mbar_wait(bar_ldm, par);
@@ -1478,7 +1481,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
 // host side
 // =====================================================================================================================
 static size_t fwd_smem_bytes(const NetDims& d) { return (((size_t)d.pack_bytes + 127) & ~(size_t)127) + 10 * 8 + (32 + 256) * 4; }
-constexpr size_t TOP_SMEM = 6 * (size_t)TILE_BYTES + 4096 + MASK_BYTES + 128 * 4 + 64 * 4 + 256 * 4 + 16 + 12 * 8 + 16;
+constexpr size_t TOP_SMEM = 2 * (size_t)TILE_BYTES + 4 * (size_t)TOP_BUF_STRIDE + MASK_BYTES + 128 * 4 + 64 * 4 + 256 * 4 + 16 + 12 * 8 + 16;
 constexpr size_t BOT_SMEM = 6 * (size_t)TILE_BYTES + 96 * 256 + 4096 + 4096 + 256 * 4 + 12 * 8 + 16;
 constexpr size_t BWD_SMEM = TOP_SMEM > BOT_SMEM ? TOP_SMEM : BOT_SMEM;
 static_assert(BWD_SMEM <= 227 * 1024, "backward kernel exceeds the shared memory of an SM");
@@ -1622,7 +1625,7 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
   }
   // role split: n_top + n_bot CTAs per net, all resident at once (one CTA per SM).  NERFCA_BWD_SPLIT="n_top,n_bot" overrides it.
   const int per_net = sm_count() / n_nets;
-  int n_top = (per_net * 9 + 10) / 20, n_bot = per_net - n_top;      // measured optimum 33 : 41 of 74 (the bottom role has three layers)
+  int n_top = (per_net * 21 + 25) / 50, n_bot = per_net - n_top;     // measured optimum 31 : 43 of 74 (the bottom role has three layers)
   if (!merged) n_top = n_bot = per_net;          // two launches: every SM runs the top role, then every SM the bottom role
   else if (const char* e = getenv("NERFCA_BWD_SPLIT")) {
     int t = 0, b = 0;
