@@ -1294,6 +1294,13 @@ __device__ __forceinline__ void bwd_bot_role(const BwdArgs& a, const BwdNet& nt,
         bulk_g2s(smem_u32(s_buf + (size_t)((i + 1) & 3) * TILE_BYTES), st + (size_t)TILE_BYTES, TILE_BYTES, bar_ld_h1);
         mbar_expect_tx(bar_ld_h0, TILE_BYTES);
         bulk_g2s(smem_u32(s_buf + (size_t)((i + 2) & 3) * TILE_BYTES), st, TILE_BYTES, bar_ld_h0);
+        // H0 / H1 of the NEXT tile can only be copied once this tile's step C has released their buffers, and step B of the next tile
+        // then waits for H1: pull them into L2 now, so that copy is an L2 hit instead of an HBM round trip
+        if (i + 1 < n_my) {
+          const uint8_t* nx = nt.stash + (size_t)(tile + n_workers) * STASH_STRIDE;
+          bulk_prefetch_l2(nx, TILE_BYTES);
+          bulk_prefetch_l2(nx + TILE_BYTES, TILE_BYTES);
+        }
       }
       if (n_my > 0) {
         mbar_wait(bar_ld_dz, (uint32_t)((n_my - 1) & 1));
