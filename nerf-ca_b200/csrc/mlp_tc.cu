@@ -1283,13 +1283,16 @@ __device__ __forceinline__ void bwd_bot_role(const BwdArgs& a, const BwdNet& nt,
           mbar_wait(bar_ld_dz, (uint32_t)((i - 1) & 1));        // (long complete) dZ2 of tile i - 1 has left its hand-off slot
           st_release_gpu(nt.consumed + (tile - n_workers), 1u);
         }
+        NERFCA_TL(true, 2001);
         if (seen < 8u) wait_flag_ge(nt.produced + tile, 8u);    // all 8 epilogue warps of the top role have written the tile
+        NERFCA_TL(true, 2002);
         fence_proxy_async_all();
         mbar_expect_tx(bar_ld_dz, TILE_BYTES);
         bulk_g2s(smem_u32(s_buf + (size_t)(i & 3) * TILE_BYTES), nt.handoff + (size_t)slot * TILE_BYTES, TILE_BYTES, bar_ld_dz);
         slot += slot_step;
         if (slot >= (uint32_t)a.ring) slot -= (uint32_t)a.ring;
         if (i > 0) { mbar_wait(bar_free2, ph2); ph2 ^= 1; }     // H0's and dZ1's buffers of tile i - 1
+        NERFCA_TL(true, 2003);
         mbar_expect_tx(bar_ld_h1, TILE_BYTES);
         bulk_g2s(smem_u32(s_buf + (size_t)((i + 1) & 3) * TILE_BYTES), st + (size_t)TILE_BYTES, TILE_BYTES, bar_ld_h1);
         mbar_expect_tx(bar_ld_h0, TILE_BYTES);
@@ -1641,7 +1644,15 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
   }
   // role split: n_top + n_bot CTAs per net, all resident at once (one CTA per SM).  NERFCA_BWD_SPLIT="n_top,n_bot" overrides it.
   const int per_net = sm_count() / n_nets;
-  int n_top = (per_net * 21 + 25) / 50, n_bot = per_net - n_top;     // measured optimum 31 : 43 of 74 (the bottom role has three layers)
+  // measured optimum 31 : 43 of 74 (the bottom role has three layers).  The two counts are kept coprime: tile t goes from top worker
+  // t % n_top to bottom worker t % n_bot, and with a common divisor g the CTAs fall into g closed groups that run in lockstep
+  // (34 : 40 and 36 : 38 measured 6-10 % slower than 33 : 41 and 35 : 39).
+  int n_top = (per_net * 21 + 25) / 50, n_bot = per_net - n_top;
+  {
+    auto gcd = [](int x, int y) { while (y) { const int r = x % y; x = y; y = r; } return x; };
+    while (n_top > 1 && gcd(n_top, per_net - n_top) != 1) --n_top;
+    n_bot = per_net - n_top;
+  }
   if (!merged) n_top = n_bot = per_net;          // two launches: every SM runs the top role, then every SM the bottom role
   else if (const char* e = getenv("NERFCA_BWD_SPLIT")) {
     int t = 0, b = 0;
