@@ -36,7 +36,12 @@ __device__ __forceinline__ void wait_flags(const uint32_t* flags, int world, uin
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
       __nanosleep(100);
-      if (clock64() - t0 > 20000000000LL) __trap();      // ~10 s: a peer never arrived
+      if (clock64() - t0 > 20000000000LL) {              // ~10 s: a peer never arrived
+#ifdef NERFCA_TIMELINE_BUILD
+        printf("peer flag timeout: block %d waits for rank %d, sees %u, epoch %u\n", (int)blockIdx.x, (int)threadIdx.x, ld_acquire_sys(flags + threadIdx.x), epoch);
+#endif
+        __trap();
+      }
     }
   }
   __syncthreads();

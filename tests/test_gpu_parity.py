@@ -457,3 +457,20 @@ def test_fused_allreduce_adam_matches_nccl_path():
                          timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "replicas bit-identical True" in out.stdout
+
+
+def test_training_soak_short():
+    """A few thousand back-to-back optimisation steps at the full batch size: no bounded wait of the tensor-core kernels may trap and the
+    loss sums must stay finite.  (tools/soak.py is the long version: a protocol slip that traps once per ~10^4 steps was found that way.)"""
+    from nerfca import trainer as tr
+    torch.manual_seed(0)
+    t = tr.CompositeTrainer.from_config(device=DEV, precision="bf16", n_depth=500)
+    t.set_iteration(50000)
+    batches = []
+    for k in range(4):
+        rays, phases, z = parity.synthetic_batch(1024, 500, seed=300 + k)
+        batches.append((rays.to(DEV), phases.to(DEV).int(), z.to(DEV)))
+    for k in range(4000):
+        t.step_device(*batches[k % 4])
+    torch.cuda.synchronize()
+    assert torch.isfinite(t.last_terms).all() and torch.isfinite(t.flat_p).all()
