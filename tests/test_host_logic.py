@@ -34,6 +34,8 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_lib.FieldGradsStruct) == 8 + 2 * 8 * _lib.MAX_LAYERS
     assert C.sizeof(_lib.SamplesStruct) == 8 + 8 + 4 + 4 + 8 + 8 + 4 + 4 + 8 + 8 + 8
     assert C.sizeof(_lib.LossCfgStruct) == 6 * 8 + 2 * 4
+    assert C.sizeof(_lib.PeersStruct) == 2 * 4 + 3 * 8          # nerfca_peers_t
+    assert C.sizeof(_lib.AdamCfgStruct) == 5 * 8 + 8            # nerfca_adam_cfg_t
 
 
 def test_cpu_tensors_fail_loudly():
