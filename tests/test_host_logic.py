@@ -114,3 +114,22 @@ def test_schedules_and_losses_host_side():
         assert float(a) == pytest.approx(float(b), rel=1e-12)
     assert torch.equal(mh.weighted_MSELoss()(ss, sd, ss), ((ss - sd) ** 2) * ss)
     assert [len(c) for c in mh.get_minibatches_time(torch.zeros(10, 3), torch.zeros(10), 4)] == [2, 2, 2]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): exactly one JSON line on stdout carrying the
+    contract's keys, for the same metric / unit / workload as the GPU arm."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "training rays/sec (fwd+bwd)" and d["unit"] == "rays/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
