@@ -7,21 +7,26 @@
 //
 // What lives where
 //   shared memory : the bf16 weights the kernel needs (tile-canonical K-major bytes, read K-major by the forward GEMMs
-//                   and MN-major by the dgrad GEMMs), activation / gradient tiles of the tiles in flight
-//   TMEM          : fp32 accumulators; in the backward kernels the weight-gradient accumulators stay resident for the
-//                   CTA's whole lifetime and are flushed once with vector reductions
-//   HBM           : per tile and net only H0 and H2 (bf16, 32 KB each) are stashed by the forward; the backward
-//                   recomputes H1 (from H0), H3, H4 (from H2) and the encoded input X0 on chip, and hands dZ2 from the
-//                   top pass to the bottom pass.  192 KB per tile and net in total (vs 496 KB for stashing everything).
+//                   and MN-major by the dgrad GEMMs), activation / gradient tiles of the tile in flight
+//   TMEM          : fp32 accumulators; the forward also chains its activations through TMEM (TS-form MMA); in the backward the
+//                   weight-gradient accumulators stay resident for the CTA's whole lifetime and are flushed once with vector
+//                   reductions
+//   HBM           : per tile and net the forward stashes H0 .. H3 (bf16, 32 KB each, written straight from the epilogue registers)
+//                   and the ReLU pattern of H4 as one bit per element (2 KB): 130 KB.  The backward recomputes nothing but X0.
+//   L2            : the hand-off of dZ2 from the top backward role to the bottom role (a ring of 32 KB slots + flags)
 //
 // Kernels
-//   tc_forward_kernel   X0 -> H0 .. H4 -> raw.   16 epilogue warps (2 tiles in flight x (row quadrant, column half)),
-//                       1 MMA warp, 1 stash-store warp.  Hidden-layer biases are preloaded into the accumulator with
-//                       tcgen05.st, ReLU is fused into the bf16 conversion, the 128 -> 1 layer is an N = 16 MMA against
-//                       a (hi, lo) bf16 split of the output weights.
-//   tc_bwd_top_kernel   layers 4, 3 (+ output layer): loads H2, recomputes H3, Z4; dZ4 = d_raw * w_out * 1[Z4 > 0];
-//                       wgrad / bias-grad / w_out-grad accumulate in TMEM; writes dZ2 to the hand-off buffer.
-//   tc_bwd_bot_kernel   layers 2, 1, 0: loads dZ2, H0, recomputes H1 and X0; latent gradients by phase.
+//   tc_forward_kernel   X0 -> H0 .. H4 -> raw.   16 epilogue warps (2 tiles in flight x (row quadrant, column half)), each slot
+//                       issues its own MMAs, 4 X0 producer warps.  Hidden-layer biases are added in the epilogue, ReLU is fused
+//                       into the bf16 conversion, the 128 -> 1 layer is an N = 16 MMA against a (hi, lo) bf16 split of w_out.
+//   tc_bwd_kernel       ONE launch, two CTA roles per net (31 : 43 of the 74 CTAs):
+//     top role          layers 4, 3 (+ output layer): loads H2, H3, the H4 pattern, d_raw; dZ4' = d_raw 1[H4 > 0]; dgrad 4, 3;
+//                       wgrad 4, 3 with the bias gradient folded in (N = 144) accumulate in TMEM; dZ2 -> L2 ring.
+//     bottom role       layers 2, 1, 0: polls the ring, loads dZ2, H1, H0; dgrad 2, 1; wgrad 2, 1, 0; rebuilds X0; latent
+//                       gradients through one-hot phase columns of X0 (or an explicit latent dgrad for > 12 phases).
+//     Each role: 8 epilogue warps, one MMA-issuing warp inside the epilogue's named barriers, one load warp (bulk copies),
+//     top: a publisher warp for the GPU-scope flags, bottom: 4 X0 producer warps.  NERFCA_BWD_MERGED=0 runs the roles as
+//     two launches (tc_bwd_top_kernel / tc_bwd_bot_kernel, hand-off through HBM).
 #include <stdlib.h>
 #include <string.h>
 
