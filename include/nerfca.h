@@ -33,7 +33,7 @@ extern "C" {
 #define NERFCA_API
 #endif
 
-#define NERFCA_ABI_VERSION 1
+#define NERFCA_ABI_VERSION 2
 #define NERFCA_MAX_LAYERS 8 /* first layer + hidden H->H layers + output layer */
 
 enum { NERFCA_OK = 0, NERFCA_E_ARG = -1, NERFCA_E_UNSUPPORTED = -2, NERFCA_E_CUDA = -3, NERFCA_E_WORKSPACE = -4 };
@@ -216,6 +216,11 @@ NERFCA_API int nerfca_composite_loss(const float* raw_s, const float* raw_d, con
  * dynamic_field == NULL selects the static run of train/run_nerf.py:205-233.  Scratch is caller-allocated:
  * raw_* / d_raw_* float32 [P]; stash / workspace of nerfca_step_stash_bytes / nerfca_step_workspace_bytes bytes.
  * Parameter gradients are accumulated (+=); pix_out float64 [n_rays]; terms_out float64 [NERFCA_N_LOSS_TERMS] (+=).   */
+enum {
+  NERFCA_STEP_PACKED = 1,       /* the packed bf16 parameter blocks at the head of `workspace` are current (kept so by
+                                   nerfca_adam_step's repack): skip the pack launch                                      */
+  NERFCA_STEP_ZERO_TERMS = 2    /* clear terms_out before accumulating (done inside the forward launch)                  */
+};
 typedef struct nerfca_step_t {
   const nerfca_field_t* static_field;
   const nerfca_field_t* dynamic_field;
@@ -228,7 +233,7 @@ typedef struct nerfca_step_t {
   const double* gt;             /* device, element r at gt[r * gw_stride]                                 */
   const double* wpix;
   int32_t gw_stride;
-  int32_t reserved;
+  int32_t flags;                /* NERFCA_STEP_* bits                                                      */
   const nerfca_loss_cfg_t* loss;
   float* raw_s; float* raw_d; float* d_raw_s; float* d_raw_d;
   void* stash; void* workspace;
@@ -245,20 +250,29 @@ NERFCA_API int nerfca_fields_forward(const nerfca_field_t* static_field, const n
                           const nerfca_samples_t* samples, int32_t precision, float* raw_s, float* raw_d, void* workspace,
                           void* stream);
 
-/* N2  torch.optim.Adam + LinearLR of train/run_composite.py:209-215,305-308 over ONE flat fp32 parameter buffer
- * (params / grads / exp_avg / exp_avg_sq device [n]).  The step counter lives on the device (step_dev, int64,
- * incremented by the call) so the whole training step can be captured in a CUDA graph.  Update of step t = *step_dev+1:
- *   lr_t = lr * (1 + (lr_end_factor - 1) * min(t - 1, lr_decay_steps) / lr_decay_steps)      (LinearLR, start_factor 1)
- *   m = lerp(m, g, 1 - beta1);  v = beta2 v + (1 - beta2) g g;  p -= lr_t / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)
- * grads are multiplied by grad_scale first (1 on one GPU) and, if zero_grads != 0, cleared afterwards so the next
- * step's kernels can accumulate without a separate memset.                                             */
-typedef struct nerfca_adam_cfg_t {
+/* N2  torch.optim.Adam(foreach) + LinearLR of train/run_composite.py:209-215,305-308 over ONE flat fp32 parameter buffer
+ * (params / grads / exp_avg / exp_avg_sq device [n]), bit-for-bit for fp32 parameters (tests/test_gpu_parity.py::
+ * test_adam_matches_torch_bit_for_bit).  The per-update scalars are computed by the HOST in python double arithmetic exactly as
+ * torch does and passed by value (they change every step; the graph replay of nerfca_graph_* updates them in place):
+ *   lr                      the LinearLR value of this update (torch's recursive form, lr_scheduler.py::LinearLR.get_lr)
+ *   bias_correction1        1 - beta1 ** t            bias_correction2_sqrt   (1 - beta2 ** t) ** 0.5       (t = 1, 2, ...)
+ *   m = lerp(m, g, 1 - beta1);  v = beta2 v + (1 - beta2) (g g);  p += -(lr / bc1) * (m / (sqrt(v) / bc2_sqrt + eps))
+ * grads are multiplied by grad_scale first (1 on one GPU) and, if zero_grads != 0, cleared afterwards so the next step's
+ * kernels can accumulate without a separate memset.  repack != NULL: every updated parameter of the two fields is also written,
+ * converted to bf16, to its position in the packed operand blocks at the head of `workspace` (the tcgen05 kernels' copy of the
+ * weights), so the next nerfca_train_step can run with NERFCA_STEP_PACKED and no pack launch.                            */
+typedef struct nerfca_adam_step_t {
   double lr, beta1, beta2, eps;
-  double lr_end_factor;          /* 1.0 = constant learning rate */
-  int64_t lr_decay_steps;
-} nerfca_adam_cfg_t;
-NERFCA_API int nerfca_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step_dev,
-                     const nerfca_adam_cfg_t* cfg, float grad_scale, int32_t zero_grads, void* stream);
+  double bias_correction1;
+  double bias_correction2_sqrt;
+} nerfca_adam_step_t;
+typedef struct nerfca_repack_t {
+  const nerfca_field_t* static_field;   /* weight / bias pointers must lie inside `params`                             */
+  const nerfca_field_t* dynamic_field;  /* or NULL                                                                     */
+  void* workspace;                      /* the step workspace (nerfca_step_workspace_bytes)                            */
+} nerfca_repack_t;
+NERFCA_API int nerfca_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     const nerfca_adam_step_t* cfg, float grad_scale, int32_t zero_grads, const nerfca_repack_t* repack, void* stream);
 
 /* Launch accounting and per-kernel device timing (used by bench.py for `gpu_launches` and the roofline line).
  * nerfca_launch_count: kernels launched by this library since load.  nerfca_profile_enable(1) starts recording a
@@ -271,8 +285,10 @@ enum { NERFCA_K_RAYS = 0, NERFCA_K_PACK = 1, NERFCA_K_FIELD_FWD = 2, NERFCA_K_LO
  * Every rank's gradient buffer [n] and a signal pad (>= 1 KB of uint32, zero before the first step) must be peer-mapped;
  * `grads` / `signals` are DEVICE arrays of world_size peer pointers in rank order, `own_signals` this rank's pad.
  * epoch = 1, 2, 3, ... must advance by one per call on every rank.  After the call (stream order) the parameters of all
- * ranks are bit-identical, this rank's gradient buffer is zero and *step_dev has been incremented.  The grid of the
- * update kernel must be co-resident with its peers' (it is: n / 1024 blocks), all waits are bounded.                 */
+ * ranks are bit-identical and this rank's gradient buffer is zero.  The grid of the update kernel must be co-resident with
+ * its peers' (it is: n / 1024 blocks), all waits are bounded.  terms_out != NULL: the step's NERFCA_N_LOSS_TERMS float64 loss
+ * sums of every rank, stored in the peer-mapped buffer at float offset terms_offset (>= n, even) behind the gradients, are
+ * summed over the ranks in the same exchange (entries 2, 3: maxima) into terms_out (device, local) -- no second collective.   */
 typedef struct nerfca_peers_t {
   int32_t rank, world_size;
   const float* const* grads;
@@ -280,7 +296,27 @@ typedef struct nerfca_peers_t {
   uint32_t* own_signals;
 } nerfca_peers_t;
 NERFCA_API int nerfca_allreduce_adam_step(const nerfca_peers_t* peers, uint32_t epoch, float* params, float* grads, float* exp_avg,
-                               float* exp_avg_sq, int64_t n, int64_t* step_dev, const nerfca_adam_cfg_t* cfg, void* stream);
+                               float* exp_avg_sq, int64_t n, const nerfca_adam_step_t* cfg, const nerfca_repack_t* repack,
+                               int64_t terms_offset, double* terms_out, void* stream);
+
+/* CUDA-graph replay of a training step (nothing upstream; removes the per-kernel launch gaps of run_composite.py:283-308's
+ * eager sequence).  Bracket the step's calls with begin / end_launch on a NON-default stream: the launches are captured, the
+ * previous step's executable graph is updated in place (new pointers / per-step scalars) and launched once.  abort leaves
+ * capture mode after a failed call inside the bracket.                                                                      */
+typedef struct nerfca_graph nerfca_graph_t;
+NERFCA_API int nerfca_graph_create(nerfca_graph_t** out);
+NERFCA_API int nerfca_graph_begin(nerfca_graph_t* g, void* stream);
+NERFCA_API int nerfca_graph_end_launch(nerfca_graph_t* g, void* stream);
+NERFCA_API int nerfca_graph_abort(nerfca_graph_t* g, void* stream);
+NERFCA_API int nerfca_graph_stats(const nerfca_graph_t* g, int64_t* launches, int64_t* updates, int64_t* instantiations);
+NERFCA_API int nerfca_graph_destroy(nerfca_graph_t* g);
+
+/* Parity / debug entry: the bf16 first-layer input tile X0 exactly as the tcgen05 kernels build it in registers (A5 on the hot
+ * path: range-reduced MUFU sin/cos + double-angle steps).  x0_out: device uint16 [roundup128(P), kpad0] bf16 bit patterns
+ * (may be NULL to query kpad0 only); columns: in_dim features, then the constant-1 bias column, then (onehot != 0 and they fit)
+ * one-hot phase columns, then zero padding.                                                                                */
+NERFCA_API int nerfca_debug_x0(const nerfca_field_t* field, const nerfca_samples_t* samples, int32_t onehot, uint16_t* x0_out,
+                    int32_t* kpad0_out, void* stream);
 
 NERFCA_API int64_t nerfca_launch_count(void);
 NERFCA_API int nerfca_profile_enable(int32_t on);

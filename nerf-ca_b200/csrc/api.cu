@@ -22,6 +22,8 @@ static std::vector<ProfRec> g_prof_pool;       // reusable event pairs
 
 ProfScope::ProfScope(int kind, cudaStream_t st) : kind_(kind), st_(st), rec_(nullptr) {
   if (!g_prof_on) return;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return;   // no event timing inside a graph capture
   std::lock_guard<std::mutex> lk(g_prof_mu);
   ProfRec* r = new ProfRec;
   if (!g_prof_pool.empty()) { *r = g_prof_pool.back(); g_prof_pool.pop_back(); }
@@ -88,9 +90,11 @@ int tc_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, const 
 size_t tc_stash_bytes_n(int n_nets, long long P);
 size_t tc_workspace_bytes_n(const nerfca_field_t* const* f, int n_nets, long long P, int backward);
 int tc_fields_forward(const nerfca_field_t* const* f, int n_nets, const nerfca_samples_t& s, float* const* raw_out, void* stash,
-                      void* workspace, int pack, cudaStream_t st);
+                      void* workspace, int pack, double* zero_terms, cudaStream_t st);
 int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_samples_t& s, const float* const* d_raw,
                        const void* stash, void* workspace, int pack, const nerfca_field_grads_t* const* gr, cudaStream_t st);
+
+int tc_debug_x0(const nerfca_field_t& f, const nerfca_samples_t& s, int onehot, uint16_t* out, int* kpad0_out, cudaStream_t st);
 
 static size_t up256(size_t n) { return (n + 255) & ~(size_t)255; }
 
@@ -187,6 +191,20 @@ extern "C" int nerfca_field_backward(const nerfca_field_t* field, const nerfca_s
   return simt_field_backward(*field, *samples, d_raw, stash, workspace, *grads, (cudaStream_t)stream);
 }
 
+extern "C" int nerfca_debug_x0(const nerfca_field_t* field, const nerfca_samples_t* samples, int32_t onehot, uint16_t* x0_out,
+                               int32_t* kpad0_out, void* stream) {
+  int rc = validate_field(field);
+  if (rc) return rc;
+  rc = validate_samples(samples, field->n_latent > 0);
+  if (rc) return rc;
+  rc = tc_supported(*field);
+  if (rc) return rc;
+  int kp = 0;
+  rc = tc_debug_x0(*field, *samples, onehot, x0_out, &kp, (cudaStream_t)stream);
+  if (kpad0_out) *kpad0_out = kp;
+  return rc;
+}
+
 // ---- whole-step entry points ------------------------------------------------------------------------------------------
 static int validate_step(const nerfca_step_t* s, bool training) {
   NERFCA_REQUIRE(s != nullptr, NERFCA_E_ARG, "step is null");
@@ -227,10 +245,16 @@ extern "C" size_t nerfca_step_workspace_bytes(const nerfca_step_t* s) {
     const nerfca_field_t* f[2] = {s->static_field, s->dynamic_field};
     return tc_workspace_bytes_n(f, s->dynamic_field ? 2 : 1, P, 1);
   }
-  size_t n = simt_workspace_bytes(*s->static_field, P, 1);
-  if (s->dynamic_field) {
-    const size_t m = simt_workspace_bytes(*s->dynamic_field, P, 1);
-    n = m > n ? m : n;
+  // one buffer serves every fp32 call made with this descriptor: the stash-less forward of nerfca_fields_forward lays out
+  // enc | ping | pong (in_dim + 2 hidden floats per sample of a chunk), the backward two hidden-wide gradient tiles
+  size_t n = 0;
+  const nerfca_field_t* fs[2] = {s->static_field, s->dynamic_field};
+  for (int i = 0; i < 2; ++i) {
+    if (!fs[i]) continue;
+    for (int backward = 0; backward < 2; ++backward) {
+      const size_t m = simt_workspace_bytes(*fs[i], P, backward);
+      n = m > n ? m : n;
+    }
   }
   return n;
 }
@@ -248,7 +272,7 @@ extern "C" int nerfca_fields_forward(const nerfca_field_t* fs, const nerfca_fiel
   if (precision == NERFCA_PREC_BF16) {
     const nerfca_field_t* f[2] = {fs, fd};
     float* outs[2] = {raw_s, raw_d};
-    return tc_fields_forward(f, fd ? 2 : 1, *samples, outs, nullptr, workspace, 1, cs);
+    return tc_fields_forward(f, fd ? 2 : 1, *samples, outs, nullptr, workspace, 1, nullptr, cs);
   }
   ProfScope prof(NERFCA_K_FIELD_FWD, cs);
   rc = simt_field_forward(*fs, *samples, raw_s, nullptr, workspace, cs);
@@ -273,9 +297,12 @@ extern "C" int nerfca_train_step(const nerfca_step_t* s, void* stream) {
   const int n = dyn ? 2 : 1;
   const long long P = smp.n_points;
   uint8_t* stash_d = (uint8_t*)s->stash + (s->precision == NERFCA_PREC_BF16 ? 0 : up256(simt_stash_bytes(*s->static_field, P)));
+  const bool zero_terms = (s->flags & NERFCA_STEP_ZERO_TERMS) != 0;
   if (s->precision == NERFCA_PREC_BF16) {
-    rc = tc_fields_forward(f, n, smp, raws, s->stash, s->workspace, 1, cs);
+    // (the forward launch also clears the loss sums when asked to: no separate memset node in the step's graph)
+    rc = tc_fields_forward(f, n, smp, raws, s->stash, s->workspace, (s->flags & NERFCA_STEP_PACKED) ? 0 : 1, zero_terms ? s->terms_out : nullptr, cs);
   } else {
+    if (zero_terms) NERFCA_CUDA_OK(cudaMemsetAsync(s->terms_out, 0, NERFCA_N_LOSS_TERMS * sizeof(double), cs));
     ProfScope prof(NERFCA_K_FIELD_FWD, cs);
     rc = simt_field_forward(*f[0], smp, raws[0], s->stash, s->workspace, cs);
     if (!rc && dyn) rc = simt_field_forward(*f[1], smp, raws[1], stash_d, s->workspace, cs);

@@ -33,6 +33,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "pack.cuh"
 #include "tc_common.cuh"
 
 namespace nerfca {
@@ -48,26 +49,6 @@ constexpr uint32_t MASK_BYTES = 2048;            // + the ReLU pattern of H4, on
 constexpr size_t STASH_STRIDE = (size_t)STASH_TILES * 32768 + MASK_BYTES;   // bytes per tile and net
 constexpr int FWD_THREADS = 20 * 32;             // 16 epilogue / issue warps + 4 X0 producer warps
 constexpr int FAST_FREQ = 12;                    // band count the register-resident encoder is specialised for
-
-// ---- packed parameter block of one net (device memory, also the leading part of the forward kernel's shared memory) --
-//   [W0: kpad0 * 256][W1..W4: 4 x 32768][w_out tile: 4096][fp32: bias[5][128], w_out[128], b_out, pad]
-struct NetDims {
-  int in_dim, enc_dim, kpad0;
-  uint32_t w0_bytes, w_bytes, wout_off, f32_off, pack_bytes;
-};
-__host__ __device__ inline uint32_t f32_block_floats() { return TC_N_RELU * 128 + 128 + 32; }
-static NetDims net_dims(const nerfca_field_t& f) {
-  NetDims d;
-  d.in_dim = in_dim_of(f);
-  d.enc_dim = enc_dim_of(f);
-  d.kpad0 = (d.in_dim + 1 + 15) / 16 * 16;
-  d.w0_bytes = (uint32_t)d.kpad0 * 256u;
-  d.w_bytes = d.w0_bytes + 4u * TILE_BYTES;
-  d.wout_off = d.w_bytes;   // [16 x 128] bf16 tile of the 128 -> 1 layer: row 0 = hi part of w_out, row 1 = lo part, rest 0
-  d.f32_off = d.w_bytes + 4096u;
-  d.pack_bytes = d.f32_off + f32_block_floats() * 4u;
-  return d;
-}
 
 int tc_supported(const nerfca_field_t& f) {
   NERFCA_REQUIRE(f.hidden == TC_H, NERFCA_E_UNSUPPORTED, "the tcgen05 path is built for hidden == 128 (use precision fp32)");
@@ -124,9 +105,6 @@ __global__ void pack_params_kernel(PackArgs pa) {
   }
 }
 
-// packed blocks of the nets sit back to back in `dst`, each rounded up to 256 B
-static size_t pack_stride(const NetDims& d) { return ((size_t)d.pack_bytes + 255) & ~(size_t)255; }
-
 static int pack_params(const nerfca_field_t* const* f, int n_nets, void* dst, cudaStream_t st) {
   PackArgs pa;
   size_t off = 0;
@@ -147,12 +125,50 @@ static int pack_params(const nerfca_field_t* const* f, int n_nets, void* dst, cu
   return NERFCA_OK;
 }
 
+// Table for the optimizer kernels (pack.cuh): where each tensor of `fields` sits inside the flat parameter buffer and where its
+// packed copy goes.  Fields whose tensors are not all inside the buffer, or not of the packed shape, give an error.
+int make_repack_table(const nerfca_field_t* const* fields, int n_nets, void* workspace, const float* params, long long n,
+                      RepackTable* out) {
+  out->n_segs = 0;
+  NERFCA_REQUIRE(n_nets >= 1 && n_nets <= 2 && workspace && params, NERFCA_E_ARG, "bad repack arguments");
+  size_t off = 0;
+  int ns = 0;
+  for (int i = 0; i < n_nets; ++i) {
+    const nerfca_field_t& f = *fields[i];
+    int rc = tc_supported(f);
+    if (rc) return rc;
+    const NetDims d = net_dims(f);
+    RepackNet& rn = out->net[i];
+    rn.out = (uint8_t*)workspace + off;
+    rn.in_dim = d.in_dim; rn.kpad0 = d.kpad0; rn.w0_bytes = d.w0_bytes; rn.wout_off = d.wout_off; rn.f32_off = d.f32_off;
+    off += pack_stride(d);
+    for (int l = 0; l <= TC_N_RELU; ++l) {
+      for (int is_bias = 0; is_bias < 2; ++is_bias) {
+        const float* t = is_bias ? f.bias[l] : f.weight[l];
+        if (!t) continue;
+        const int K = (l == 0) ? d.in_dim : 128;
+        const int count = is_bias ? (l == TC_N_RELU ? 1 : 128) : (l == TC_N_RELU ? 128 : 128 * K);
+        NERFCA_REQUIRE(t >= params && t + count <= params + n, NERFCA_E_ARG, "a field tensor lies outside the flat parameter buffer");
+        NERFCA_REQUIRE(((t - params) & 3) == 0, NERFCA_E_ARG, "field tensors must start on 4-float boundaries of the flat buffer");
+        RepackSeg& sg = out->seg[ns++];
+        sg.begin = (long long)(t - params);
+        sg.count = count;
+        sg.kind = (short)(l == TC_N_RELU ? (is_bias ? SEG_BOUT : SEG_WOUT) : (is_bias ? SEG_BIAS : SEG_WEIGHT));
+        sg.layer = (short)l; sg.K = (short)K; sg.net = (short)i;
+      }
+    }
+  }
+  out->n_segs = ns;
+  return NERFCA_OK;
+}
+
 // ---- first-layer input tile X0 (bf16, tile-canonical) ------------------------------------------------------------
 // Each tile row is built by the two threads (column halves ch = 0 / 1) that own it.  Fast path (BANDS, 12 bands):
-// the sines / cosines of bands 0-5 and 6-11 come from one accurate sincosf per coordinate (at band 0 resp. band 6)
-// followed by double-angle steps, everything in registers, 16-byte stores.  The result differs from the fp32 reference
-// expression by < 1e-5 absolute (the reference's own "+ fl32(pi/2)" argument rounding is 2.4e-4 at band 11), far
-// below the bf16 rounding applied to the tile.  Other encodings take the generic per-feature path.
+// the sines / cosines of bands 0-5 and 6-11 come from one range-reduced MUFU sin/cos pair per coordinate (at band 0 resp.
+// band 6, sincos_reduced) followed by double-angle steps, everything in registers, 16-byte stores.  Against the fp32
+// reference expression the features differ by <= 2e-5 (ours) + 2.4e-4 (the reference's own "+ fl32(pi/2)" argument
+// rounding at band 11, which the double-angle cosine does not reproduce) before the bf16 rounding applied to the tile
+// (half-ulp 2e-3); tests/test_gpu_parity.py::test_tensor_core_x0_tile bounds it.  Other encodings take the generic path.
 struct X0Desc {
   EncDesc enc;
   int kpad0;
@@ -199,6 +215,17 @@ __device__ __forceinline__ RowIn fetch_row(const X0Desc& xd, const SampleSrc& sr
   return r;
 }
 
+// sin / cos of an argument of a few hundred radians (2^6 |x|): two-term Cody-Waite reduction to [-pi, pi] (the power-of-two scaling
+// of the argument is exact), then the MUFU approximations, whose absolute error inside that range is ~5e-7.  The five double-angle
+// steps that follow double the error each: <= 2e-5 at the highest band, against a bf16 half-ulp of 2e-3 and the reference's own
+// "+ fl32(pi/2)" argument rounding of 2.4e-4 there.
+__device__ __forceinline__ void sincos_reduced(float a, float& s, float& c) {
+  const float k = rintf(a * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, a);          // 2 pi = 6.2831854820251465 (fp32) - 1.7484555e-7
+  r = fmaf(k, 1.7484555e-7f, r);
+  __sincosf(r, &s, &c);
+}
+
 // band_w / lat_tab: per-band weights [n_freq] (or null) and the latent table [n_phases, n_latent]; either global or a
 // shared-memory copy.  Every branch below is warp-uniform (ch, the encoding and kpad0 are), which the TMEM sink needs.
 template <class Sink>
@@ -215,9 +242,9 @@ __device__ __forceinline__ void emit_x0_row(const X0Desc& xd, const RowIn& in, c
     constexpr int SPLIT = 40;                    // features [0, 40) belong to ch 0 (5 chunks), the rest to ch 1
     const float scale = ch ? (float)(1 << HB) : 1.f;
     float s[3], c[3];
-    __sincosf(x * scale, &s[0], &c[0]);
-    __sincosf(y * scale, &s[1], &c[1]);
-    __sincosf(z * scale, &s[2], &c[2]);
+    sincos_reduced(x * scale, s[0], c[0]);
+    sincos_reduced(y * scale, s[1], c[1]);
+    sincos_reduced(z * scale, s[2], c[2]);
     // features are produced in index order and leave in 16-byte chunks as soon as 8 of them exist; `cnt` is a
     // compile-time constant at every use once the loops are unrolled, so `buf` stays in registers
     float buf[8];
@@ -383,6 +410,7 @@ struct FwdArgs {
   FwdNet net[2];
   int n_nets;
   long long n_tiles;
+  double* zero_terms;   // optional: NERFCA_N_LOSS_TERMS loss sums to clear (they are accumulated by the loss kernel that follows)
   long long* dbg;   // optional event timeline of one CTA (NERFCA_TIMELINE=fwd, NERFCA_TIMELINE_CTA=n)
   int dbg_cta;
 };
@@ -482,6 +510,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
     __syncwarp();
     tmem_alloc(smem_u32(s_tmem), 512);
   }
+  if (a.zero_terms && blockIdx.x == 0 && threadIdx.x < NERFCA_N_LOSS_TERMS) a.zero_terms[threadIdx.x] = 0.0;
   {
     const EncDesc& e = nt.x0.enc;
     for (int i = threadIdx.x; i < 32; i += blockDim.x) s_bw[i] = (e.band_weight && i < e.n_freq) ? __ldg(e.band_weight + i) : 1.f;
@@ -1558,7 +1587,7 @@ static unsigned grid_for(int n_nets, long long n_tiles) {
 // Forward of n_nets (1 or 2) fields over the same sample set in one launch.  pack != 0: (re)pack the parameters into
 // the head of `workspace` first.
 int tc_fields_forward(const nerfca_field_t* const* f, int n_nets, const nerfca_samples_t& s, float* const* raw_out, void* stash,
-                      void* workspace, int pack, cudaStream_t st) {
+                      void* workspace, int pack, double* zero_terms, cudaStream_t st) {
   if (pack) {
     int rc = pack_params(f, n_nets, workspace, st);
     if (rc) return rc;
@@ -1567,6 +1596,7 @@ int tc_fields_forward(const nerfca_field_t* const* f, int n_nets, const nerfca_s
   a.src = make_src(s);
   a.n_nets = n_nets;
   a.n_tiles = (long long)n_tiles_of(s.n_points);
+  a.zero_terms = zero_terms;
   size_t off = 0, smem = 0;
   for (int i = 0; i < n_nets; ++i) {
     const NetDims d = net_dims(*f[i]);
@@ -1695,6 +1725,29 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
   return NERFCA_OK;
 }
 
+// ---- parity / debug entry: the first-layer input tile exactly as the tensor-core kernels build it ------------------------------
+struct GlobalSink {
+  uint16_t* row_out;   // this row's kpad0 bf16 values
+  __device__ __forceinline__ void chunk(int c, const float* v) const { *reinterpret_cast<uint4*>(row_out + c * 8) = pack_chunk(v); }
+};
+__global__ void x0_debug_kernel(X0Desc xd, SampleSrc src, uint16_t* out) {
+  const long long p = (long long)blockIdx.x * TILE_M + threadIdx.x;
+  const RowIn in = fetch_row(xd, src, p, p < src.n_points);
+  const GlobalSink sink{out + (size_t)p * xd.kpad0};
+  emit_x0_row(xd, in, xd.enc.band_weight, xd.enc.latents, sink, 0);
+  emit_x0_row(xd, in, xd.enc.band_weight, xd.enc.latents, sink, 1);
+}
+int tc_debug_x0(const nerfca_field_t& f, const nerfca_samples_t& s, int onehot, uint16_t* out, int* kpad0_out, cudaStream_t st) {
+  const NetDims d = net_dims(f);
+  if (kpad0_out) *kpad0_out = d.kpad0;
+  if (!out || s.n_points == 0) return NERFCA_OK;
+  X0Desc xd = make_x0(f, d);
+  if (onehot && f.n_latent > 0 && f.n_phases <= d.kpad0 - d.in_dim - 1) xd.onehot = f.n_phases;
+  x0_debug_kernel<<<(unsigned)n_tiles_of(s.n_points), TILE_M, 0, st>>>(xd, make_src(s), out);
+  NERFCA_LAUNCH_OK();
+  return NERFCA_OK;
+}
+
 // ---- single-field entry points (module-level CPPN.forward / Temporal.forward_composite and their autograd) ----------
 size_t tc_stash_bytes(const nerfca_field_t& f, long long P) { (void)f; return tc_stash_bytes_n(1, P); }
 size_t tc_workspace_bytes(const nerfca_field_t& f, long long P, int backward) {
@@ -1705,7 +1758,7 @@ int tc_field_forward(const nerfca_field_t& f, const nerfca_samples_t& s, float* 
                      cudaStream_t st) {
   const nerfca_field_t* fs[1] = {&f};
   float* outs[1] = {raw_out};
-  return tc_fields_forward(fs, 1, s, outs, stash, workspace, 1, st);
+  return tc_fields_forward(fs, 1, s, outs, stash, workspace, 1, nullptr, st);
 }
 int tc_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, const float* d_raw, const void* stash, void* workspace,
                       const nerfca_field_grads_t& gr, cudaStream_t st) {

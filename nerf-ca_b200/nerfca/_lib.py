@@ -11,6 +11,7 @@ import os
 
 import torch
 
+ABI_VERSION = 2
 MAX_LAYERS = 8
 N_LOSS_TERMS = 16
 
@@ -52,15 +53,22 @@ class StepStruct(C.Structure):
     _fields_ = [("static_field", C.POINTER(FieldStruct)), ("dynamic_field", C.POINTER(FieldStruct)),
                 ("static_grads", C.POINTER(FieldGradsStruct)), ("dynamic_grads", C.POINTER(FieldGradsStruct)),
                 ("samples", C.POINTER(SamplesStruct)), ("precision", C.c_int32), ("activation", C.c_int32),
-                ("i0", C.c_void_p), ("gt", C.c_void_p), ("wpix", C.c_void_p), ("gw_stride", C.c_int32), ("reserved", C.c_int32),
+                ("i0", C.c_void_p), ("gt", C.c_void_p), ("wpix", C.c_void_p), ("gw_stride", C.c_int32), ("flags", C.c_int32),
                 ("loss", C.POINTER(LossCfgStruct)),
                 ("raw_s", C.c_void_p), ("raw_d", C.c_void_p), ("d_raw_s", C.c_void_p), ("d_raw_d", C.c_void_p),
                 ("stash", C.c_void_p), ("workspace", C.c_void_p), ("pix_out", C.c_void_p), ("terms_out", C.c_void_p)]
 
 
-class AdamCfgStruct(C.Structure):
+class AdamStepStruct(C.Structure):       # nerfca_adam_step_t: the scalars of ONE update, computed by the host as torch does
     _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
-                ("lr_end_factor", C.c_double), ("lr_decay_steps", C.c_int64)]
+                ("bias_correction1", C.c_double), ("bias_correction2_sqrt", C.c_double)]
+
+
+class RepackStruct(C.Structure):         # nerfca_repack_t
+    _fields_ = [("static_field", C.POINTER(FieldStruct)), ("dynamic_field", C.POINTER(FieldStruct)), ("workspace", C.c_void_p)]
+
+
+STEP_PACKED, STEP_ZERO_TERMS = 1, 2
 
 
 class PeersStruct(C.Structure):          # nerfca_peers_t
@@ -100,8 +108,16 @@ _SIGNATURES = {
     "nerfca_step_workspace_bytes": (C.c_size_t, [C.POINTER(StepStruct)]),
     "nerfca_train_step": (C.c_int, [C.POINTER(StepStruct), _P]),
     "nerfca_fields_forward": (C.c_int, [C.POINTER(FieldStruct), C.POINTER(FieldStruct), C.POINTER(SamplesStruct), _I32, _P, _P, _P, _P]),
-    "nerfca_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _P, C.POINTER(AdamCfgStruct), _F, _I32, _P]),
-    "nerfca_allreduce_adam_step": (C.c_int, [C.POINTER(PeersStruct), C.c_uint32, _P, _P, _P, _P, _I64, _P, C.POINTER(AdamCfgStruct), _P]),
+    "nerfca_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, C.POINTER(AdamStepStruct), _F, _I32, C.POINTER(RepackStruct), _P]),
+    "nerfca_allreduce_adam_step": (C.c_int, [C.POINTER(PeersStruct), C.c_uint32, _P, _P, _P, _P, _I64, C.POINTER(AdamStepStruct),
+                                             C.POINTER(RepackStruct), _I64, _P, _P]),
+    "nerfca_graph_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "nerfca_graph_begin": (C.c_int, [_P, _P]),
+    "nerfca_graph_end_launch": (C.c_int, [_P, _P]),
+    "nerfca_graph_abort": (C.c_int, [_P, _P]),
+    "nerfca_graph_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "nerfca_graph_destroy": (C.c_int, [_P]),
+    "nerfca_debug_x0": (C.c_int, [C.POINTER(FieldStruct), C.POINTER(SamplesStruct), _I32, _P, C.POINTER(C.c_int32), _P]),
     "nerfca_launch_count": (C.c_int64, []),
     "nerfca_profile_enable": (C.c_int, [_I32]),
     "nerfca_profile_read": (C.c_int, [_I32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -122,7 +138,7 @@ def load():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.nerfca_abi_version() != 1:
+        if lib.nerfca_abi_version() != ABI_VERSION:
             raise RuntimeError("libnerfca_b200.so ABI version mismatch")
         _lib = lib
     return _lib

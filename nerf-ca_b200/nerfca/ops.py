@@ -421,53 +421,112 @@ def _grad_struct(spec: FieldSpec, grads: Sequence[torch.Tensor]) -> L.FieldGrads
     return g
 
 
+class StepPlan:
+    """Everything one fused training step needs that does not change from step to step: the field / gradient descriptors over
+    the models' parameter tensors, scratch (raw outputs, their gradients, activation stash, workspace) and the ray-sum output
+    buffer, for a fixed (n_rays, n_depth).  `run` only patches the per-step pointers into the prepared C structs and makes ONE
+    C call, so it is allocation-free (usable inside a nerfca_graph_* capture bracket) and cheap on the host."""
+
+    def __init__(self, static_model, temp_model, n_rays: int, n_depth: int, device, output_activation: str, shared_scratch=True):
+        lib = L.load()
+        self.models = [static_model] + ([temp_model] if temp_model is not None else [])
+        self.n_rays, self.n_depth, self.device = int(n_rays), int(n_depth), torch.device(device)
+        self.prec = self.models[0]._precision_code()
+        if any(m._precision_code() != self.prec for m in self.models):
+            raise ValueError("both fields must use the same precision in a fused step")
+        self.specs = [m._spec() for m in self.models]
+        self.params = [_check_params(sp, m._param_list()) for sp, m in zip(self.specs, self.models)]
+        self.grads = [_grad_buffers(m._param_list()) for m in self.models]
+        self.fstructs = [sp.struct(p) for sp, p in zip(self.specs, self.params)]
+        self.gstructs = [_grad_struct(sp, g) for sp, g in zip(self.specs, self.grads)]
+        B, P, n = self.n_rays, self.n_rays * self.n_depth, len(self.models)
+        dev = self.device
+        self.pix = torch.empty((B,), dtype=torch.float64, device=dev)
+        self.samples = L.SamplesStruct()
+        self.samples.n_points, self.samples.n_rays, self.samples.n_depth = P, B, self.n_depth
+        self.loss = L.LossCfgStruct()
+        st = self.step = L.StepStruct()
+        st.static_field, st.static_grads = C.pointer(self.fstructs[0]), C.pointer(self.gstructs[0])
+        if n > 1:
+            st.dynamic_field, st.dynamic_grads = C.pointer(self.fstructs[1]), C.pointer(self.gstructs[1])
+        st.samples, st.loss = C.pointer(self.samples), C.pointer(self.loss)
+        st.precision, st.activation = self.prec, activation_code(output_activation)
+        get = _Scratch.get if shared_scratch else (lambda key, shape, dtype, d: torch.empty(shape if isinstance(shape, tuple) else (int(shape),), dtype=dtype, device=d))
+        self.raw = get(("raw", n, P), (4 if n > 1 else 2, P), torch.float32, dev)
+        st.raw_s, st.d_raw_s = L.ptr(self.raw[0]), L.ptr(self.raw[1])
+        if n > 1:
+            st.raw_d, st.d_raw_d = L.ptr(self.raw[2]), L.ptr(self.raw[3])
+        if P > 0:
+            self.stash = get(("stash", n, P, self.prec), lib.nerfca_step_stash_bytes(C.byref(st)), torch.uint8, dev)
+            self.ws = get(("ws", n, P, self.prec), lib.nerfca_step_workspace_bytes(C.byref(st)), torch.uint8, dev)
+            st.stash, st.workspace = L.ptr(self.stash), L.ptr(self.ws)
+        st.pix_out = L.ptr(self.pix)
+        self.refresh_bands()
+
+    def refresh_bands(self):
+        """Re-read the per-band window tensors of the models (they change with the iteration; an H2D copy when they do -- call it
+        outside a capture bracket)."""
+        for m, sp, fs in zip(self.models, self.specs, self.fstructs):
+            if sp.enc_mode == L.ENC_BANDS:
+                sp.band_weight = m._band_weight(sp.n_freq)
+                fs.band_weight = L.ptr(sp.band_weight)
+
+    def repack_struct(self) -> L.RepackStruct:
+        r = L.RepackStruct()
+        r.static_field = C.pointer(self.fstructs[0])
+        if len(self.models) > 1:
+            r.dynamic_field = C.pointer(self.fstructs[1])
+        r.workspace = L.ptr(self.ws)
+        return r
+
+    def run(self, rays: torch.Tensor, phases, i0: torch.Tensor, depth: torch.Tensor, cfg: "LossConfig", terms: torch.Tensor,
+            flags: int = 0):
+        """rays [B,4,3] f64 (contiguous rows), phases [B] int32 or None, i0 [B] f32, depth [N] f32 -- all on the device."""
+        B = self.n_rays
+        if tuple(rays.shape) != (B, 4, 3) or rays.dtype != torch.float64 or not rays.is_contiguous():
+            raise ValueError(f"rays must be a contiguous float64 [{B},4,3] tensor")
+        if depth.dtype != torch.float32 or depth.numel() != self.n_depth or not depth.is_contiguous():
+            raise ValueError("depth must be a contiguous float32 [n_depth] tensor")
+        if B == 0:
+            return terms
+        s = self.samples
+        base = rays.data_ptr()
+        s.origins, s.dirs, s.depth = base, base + 3 * 8, L.ptr(depth)
+        s.ray_dtype, s.ray_stride = L.F64, 12
+        if len(self.models) > 1:
+            if phases is None or phases.dtype != torch.int32 or phases.numel() != B:
+                raise ValueError("phases must be an int32 [B] tensor")
+            s.phase_ray = L.ptr(phases)
+        st = self.step
+        st.i0, st.gt, st.wpix, st.gw_stride = L.ptr(i0), base + 6 * 8, base + 9 * 8, 12
+        c = self.loss
+        c.favor_s_weight, c.dyn_entropy_weight = float(cfg.favor_s_weight), float(cfg.dyn_entropy_weight)
+        c.occl_weight, c.l1_weight = float(cfg.occl_weight), float(cfg.l1_weight)
+        c.entro_mask_thre, c.entro_weighted_thresh = float(cfg.entro_mask_thre), float(cfg.entro_weighted_thresh)
+        c.entro_use_weighting = int(bool(cfg.entro_use_weighting))
+        c.n_rays_global = int(cfg.n_rays_global or B)
+        st.terms_out, st.flags = L.ptr(terms), int(flags)
+        L.check(L.load().nerfca_train_step(C.byref(st), L.stream_ptr()), "nerfca_train_step")
+        return terms
+
+
 def _fused_step(static_model, temp_model, rays: torch.Tensor, phases, i0: torch.Tensor, depth: torch.Tensor, output_activation: str,
                 cfg: LossConfig, terms: Optional[torch.Tensor]):
     """nerfca_train_step: forward of both fields (one launch), line integral + losses + dL/d_raw, both backward passes."""
     if rays.dim() != 3 or rays.shape[1:] != (4, 3):
         raise ValueError("rays must be [B,4,3] (origin, direction, pixel, weight rows)")
-    lib = L.load()
-    samples = Samples.from_rays(rays[:, 0, :], rays[:, 1, :], depth, phases)
-    dev = samples.device
-    B, P = rays.shape[0], samples.n_points
-    models = [static_model] + ([temp_model] if temp_model is not None else [])
-    prec = models[0]._precision_code()
-    if any(m._precision_code() != prec for m in models):
-        raise ValueError("both fields must use the same precision in a fused step")
-    specs = [m._spec() for m in models]
-    pars = [_check_params(sp, m._param_list()) for sp, m in zip(specs, models)]
-    fstructs = [sp.struct(p) for sp, p in zip(specs, pars)]
-    gstructs = [_grad_struct(sp, _grad_buffers(m._param_list())) for sp, m in zip(specs, models)]
-    gt, wpix = rays[:, 2, 0], rays[:, 3, 0]
-    if gt.dtype != torch.float64 or gt.stride(0) != wpix.stride(0):
-        gt, wpix = gt.to(torch.float64).contiguous(), wpix.to(torch.float64).contiguous()
-    pix = torch.empty((B,), dtype=torch.float64, device=dev)
+    dev = rays.device
+    rays = rays.detach().to(torch.float64).contiguous()
+    z = depth.detach().to(device=dev, dtype=torch.float32).contiguous()
+    plan = StepPlan(static_model, temp_model, rays.shape[0], z.shape[0], dev, output_activation)
+    ph = None
+    if temp_model is not None:
+        ph = phases.detach().flatten().to(device=dev).to(torch.int64).to(torch.int32).contiguous()
     if terms is None:
         terms = torch.zeros((L.N_LOSS_TERMS,), dtype=torch.float64, device=dev)
-    lc = cfg.struct(B)
-    i0f = i0.to(device=dev, dtype=torch.float32).contiguous()
-    st = L.StepStruct()
-    st.static_field = C.pointer(fstructs[0])
-    st.static_grads = C.pointer(gstructs[0])
-    if len(models) > 1:
-        st.dynamic_field = C.pointer(fstructs[1])
-        st.dynamic_grads = C.pointer(gstructs[1])
-    st.samples = C.pointer(samples.struct())
-    st.precision, st.activation = prec, activation_code(output_activation)
-    st.i0, st.gt, st.wpix = L.ptr(i0f), L.ptr(gt), L.ptr(wpix)
-    st.gw_stride = gt.stride(0) if B > 1 else 1
-    st.loss = C.pointer(lc)
-    n = len(models)
-    scratch = _Scratch.get(("raw", n, P), (4 if n > 1 else 2, P), torch.float32, dev)
-    st.raw_s, st.d_raw_s = L.ptr(scratch[0]), L.ptr(scratch[1])
-    if n > 1:
-        st.raw_d, st.d_raw_d = L.ptr(scratch[2]), L.ptr(scratch[3])
-    stash = _Scratch.get(("stash", n, P, prec), lib.nerfca_step_stash_bytes(C.byref(st)), torch.uint8, dev)
-    ws = _Scratch.get(("ws", n, P, prec), lib.nerfca_step_workspace_bytes(C.byref(st)), torch.uint8, dev)
-    st.stash, st.workspace = L.ptr(stash), L.ptr(ws)
-    st.pix_out, st.terms_out = L.ptr(pix), L.ptr(terms)
-    L.check(lib.nerfca_train_step(C.byref(st), L.stream_ptr()), "nerfca_train_step")
-    return terms, pix
+    i0f = i0.detach().to(device=dev, dtype=torch.float32).contiguous()
+    plan.run(rays, ph, i0f, z, cfg, terms)
+    return terms, plan.pix
 
 
 def train_step_composite(static_model, temp_model, rays: torch.Tensor, phases: torch.Tensor, i0: torch.Tensor,

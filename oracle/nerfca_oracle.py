@@ -187,7 +187,7 @@ def pos_enc(x: torch.Tensor, n_freq: int, mode: str, window: Optional[torch.Tens
         val = 2 * np.pi * basis * fourier_coeff
         return torch.cat([torch.sin(val), torch.cos(val)], dim=-1)
     shape = x.shape[:-1]
-    scales = 2.0 ** torch.arange(0, n_freq)
+    scales = (2.0 ** torch.arange(0, n_freq)).to(x.device)
     xb = x[..., None, :] * scales[:, None]
     feat = torch.sin(torch.stack([xb, xb + 0.5 * torch.pi], axis=-2))
     if mode in ("free_windowed", "nerfies_windowed"):
@@ -249,7 +249,7 @@ def activation(name: str):
 
 def dists_from_depth(z: torch.Tensor, like_dtype: torch.dtype) -> torch.Tensor:
     # train/model_helpers.py:73-74: last delta = 1e-10 in ray_directions.dtype
-    e = torch.tensor([1e-10], dtype=like_dtype)
+    e = torch.tensor([1e-10], dtype=like_dtype, device=z.device)
     return torch.cat((z[..., 1:] - z[..., :-1], e.expand(z[..., :1].shape)), dim=-1)
 
 
@@ -301,7 +301,7 @@ def ray_entropy(sig, d, mask_thre=0.1, clip=1e-19, use_weighting=False, wpix=(),
     ssum = torch.sum(sdist, dim=-1, keepdim=True)
     mask = torch.where(ssum < mask_thre, 0.0, 1.0).flatten().int()
     if len(wpix) > 0 and use_weighting:
-        wm = torch.zeros(mask.shape).int()
+        wm = torch.zeros(mask.shape, device=mask.device).int()
         wm[: wpix.shape[0]] = torch.where(wpix > 1 + wthresh, 1.0, 0.0).int()
         mask = torch.bitwise_or(wm, mask)
     p = sdist / torch.clip(ssum, min=clip)
@@ -313,7 +313,7 @@ def occlusion(sig, d, reg_perc=0.1, use_back=False):
     # train/model_helpers.py:226-248 (mask is all ones unless use_back; no caller sets it)
     cum = torch.cumsum(d, dim=0).unsqueeze(dim=0).repeat((sig.shape[0], 1))
     front = torch.where(cum < reg_perc * cum[-1, -1], 1.0, 0.0).int()
-    back = torch.ones(front.shape)
+    back = torch.ones(front.shape, device=front.device)
     if use_back:
         back = torch.where(cum > (1 - reg_perc) * cum[-1, -1], 1.0, 0.0)
     mask = torch.bitwise_or(front, back.int())

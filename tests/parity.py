@@ -103,7 +103,8 @@ def oracle_composite_step(sd_s, sd_d, cfg_s, cfg_d, rays, phases, z, hp, it):
 
 
 def compare_grads(got: dict, want: dict, tol: dict, prefix=""):
-    worst = {"rel": 0.0, "cos": 1.0}
+    """Asserts the per-tensor bounds and returns the worst rel-L2 / cosine with the names of the tensors that set them."""
+    worst = {"rel": 0.0, "cos": 1.0, "rel_name": "", "cos_name": ""}
     for k, w in want.items():
         g = got[k].detach().cpu().numpy()
         w = w.numpy()
@@ -112,7 +113,10 @@ def compare_grads(got: dict, want: dict, tol: dict, prefix=""):
         r, c = rel_l2(g, w), cosine(g, w)
         assert r <= tol["grad_rel"], f"{prefix}{k}: gradient rel-L2 {r:.3e} > {tol['grad_rel']}"
         assert c >= tol["grad_cos"], f"{prefix}{k}: gradient cosine {c:.6f} < {tol['grad_cos']}"
-        worst["rel"], worst["cos"] = max(worst["rel"], r), min(worst["cos"], c)
+        if r > worst["rel"]:
+            worst["rel"], worst["rel_name"] = r, prefix + k
+        if c < worst["cos"]:
+            worst["cos"], worst["cos_name"] = c, prefix + k
     return worst
 
 
@@ -172,9 +176,12 @@ def run_composite_step_parity(n_rays=64, n_depth=40, precision="bf16", seed=0, h
     gd = {k: p.grad for k, p in temp.named_parameters()}
     ws = compare_grads(gs, gs_o, tol, "static.")
     wd = compare_grads(gd, gd_o, tol, "dynamic.")
+    wr = ws if ws["rel"] >= wd["rel"] else wd
+    wc = ws if ws["cos"] <= wd["cos"] else wd
     return {"precision": precision, "loss": float(loss), "loss_oracle": float(loss_o), "loss_rel_err": loss_err,
             "pix_max_abs_err": float(np.max(np.abs(pix.detach().cpu().numpy() - out_o["pix"].detach().numpy()))),
-            "grad_rel_l2_max": max(ws["rel"], wd["rel"]), "grad_cos_min": min(ws["cos"], wd["cos"])}
+            "grad_rel_l2_max": wr["rel"], "grad_rel_l2_worst_tensor": wr["rel_name"], "grad_cos_min": wc["cos"],
+            "grad_cos_worst_tensor": wc["cos_name"]}
 
 
 def run_static_step_parity(n_rays=200, n_depth=96, precision="bf16", seed=0, hidden=128, n_early=4, n_freq=12, it=50000,

@@ -384,6 +384,232 @@ def test_full_size_step_properties(precision):
         assert parity.rel_l2((a + b).cpu().numpy(), c.cpu().numpy()) <= 2e-3   # fp32 atomics: order-dependent rounding only
 
 
+# ---- the timed configuration itself against the oracle (1024 rays x 500 samples: thousands of tiles per net, so every CTA of the
+# persistent tensor-core kernels is deep in its steady state: buffer rotation, hand-off ring wrap-around, deferred stores) ----------
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("shape", ["config2", "config3_30_phases", "ragged"])
+def test_full_size_step_vs_oracle(precision, shape):
+    """BASELINE configs 2 / 3 at their full per-step size through the fused step vs the CPU oracle: pixels, loss, the 11 loss terms'
+    total, and all 26 gradient tensors.  `ragged`: 1000 rays x 333 samples = 2601.6 tiles (a partial last tile, tile boundaries that
+    never coincide with ray boundaries)."""
+    n_rays, n_depth, n_phases = {"config2": (1024, 500, 10), "config3_30_phases": (1024, 500, 30), "ragged": (1000, 333, 10)}[shape]
+    res = parity.run_composite_step_parity(n_rays=n_rays, n_depth=n_depth, precision=precision, seed=21, fused=True, n_phases=n_phases)
+    print(shape, precision, res)
+    assert res["grad_cos_min"] >= parity.TOL[precision]["grad_cos"]
+
+
+# ---- A5 on the hot path: the first-layer input tile as the tensor-core kernels build it ----------------------------------------
+
+def _x0_debug(spec, samples, params, onehot):
+    import ctypes as C
+    from nerfca import _lib as L
+    fs = spec.struct([p.detach() for p in params])
+    kp = C.c_int32(0)
+    L.check(L.load().nerfca_debug_x0(C.byref(fs), C.byref(samples.struct()), onehot, None, C.byref(kp), L.stream_ptr()), "nerfca_debug_x0")
+    rows = (samples.n_points + 127) // 128 * 128
+    out = torch.zeros((rows, kp.value), dtype=torch.int16, device=samples.device)
+    L.check(L.load().nerfca_debug_x0(C.byref(fs), C.byref(samples.struct()), onehot, L.ptr(out), C.byref(kp), L.stream_ptr()), "nerfca_debug_x0")
+    return out.view(torch.bfloat16).float().cpu().numpy()
+
+
+def test_tensor_core_x0_tile():
+    """The bf16 X0 tile of the tcgen05 kernels (range-reduced MUFU sin/cos at bands 0 and 6 + double-angle steps) against the fp32
+    reference-exact encoder nerfca_encode, over |x| <= 2.8 (the scene box) and every window state.  Bound per feature:
+    half a bf16 ulp of the value (2^-9 relative) + 3e-4 absolute (the reference's own fl32(arg + pi/2) argument rounding, 2.4e-4 at
+    band 11, which the double-angle cosine does not reproduce, + <= 2e-5 of the approximation)."""
+    from nerfca import ops
+    g = torch.Generator().manual_seed(3)
+    x = ((torch.rand((5000, 3), generator=g) * 2 - 1) * 2.8)
+    x[:8] = torch.tensor([[2.8, -2.8, 0.0], [0.0, 0.0, 0.0], [1e-3, -1e-3, 2.7999], [-2.8, 2.8, 2.8], [0.5, 0.25, 0.125],
+                          [1.5707964, 3.1415927 / 2, -1.5707964], [2.0, -1.0, 1.0], [0.1, 0.2, 0.3]])
+    ph = torch.randint(0, 10, (5000,), generator=g)
+    sd_d = orc.init_field_state(83, 128, 4, 10, 8, seed=2)
+    for it in (1234, 50000, 150000):
+        mask, _ = orc.freq_mask(12, it, 150000, 1)
+        _, t = parity.build_models(orc.init_field_state(75, 128, 4, seed=1), sd_d, DEV, "bf16", mask=mask)
+        spec = t._spec()
+        smp = ops.Samples.from_points(x.to(DEV), ph.to(DEV))
+        want = ops.encode(spec, smp, t._param_list()).cpu().numpy()                      # [P, 83] fp32, <= 2 ulp of the reference
+        got = _x0_debug(spec, smp, t._param_list(), onehot=1)
+        assert got.shape[1] == 96
+        err = np.abs(got[:5000, :83] - want)
+        bound = np.abs(want) * 2.0 ** -8 + 3e-4
+        assert (err <= bound).all(), (it, float((err - bound).max()), np.unravel_index(np.argmax(err - bound), err.shape))
+        assert np.array_equal(got[:5000, :3], x.to(torch.bfloat16).float().numpy())      # raw coordinates: plain bf16 rounding
+        assert np.all(got[:5000, 83] == 1.0)                                            # constant-1 column (layer-0 bias)
+        onehot = got[:5000, 84:94]
+        assert np.array_equal(onehot.argmax(1), ph.numpy()) and np.all(onehot.sum(1) == 1.0)
+        assert np.all(got[:5000, 94:] == 0.0) and np.all(got[5000:] == 0.0)              # padding columns / rows beyond P
+
+
+# ---- N2: the fused optimizer kernel against torch.optim.Adam + LinearLR ---------------------------------------------------------
+
+def _adam_reference(p0, grads, lr, end_factor, total_iters):
+    p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p], lr=lr, betas=(0.9, 0.999), eps=1e-8, foreach=True)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=end_factor, total_iters=total_iters)
+    for g in grads:
+        p.grad = g.clone()
+        opt.step()
+        sched.step()
+    st = opt.state[p]
+    return p.detach(), st["exp_avg"], st["exp_avg_sq"]
+
+
+def test_adam_matches_torch_bit_for_bit():
+    """nerfca_adam_step ("must match torch Adam bit-for-bit in fp32") vs torch.optim.Adam(foreach=True) +
+    LinearLR(1 -> 0.01) on the same device over 1000 updates of random gradients whose magnitudes span 1e-12 .. 1 (masked
+    frequency bands see 1e-8-scaled gradients): torch.equal on parameters, exp_avg and exp_avg_sq."""
+    import ctypes as C
+    from nerfca import _lib as L, trainer as tr
+    n, steps = 152916, 1000
+    g = torch.Generator(device=DEV).manual_seed(7)
+    p0 = torch.randn(n, device=DEV, generator=g) * 0.1
+    scale = 10.0 ** (-12 * torch.rand(n, device=DEV, generator=g))
+    grads = [torch.randn(n, device=DEV, generator=g) * scale for _ in range(steps)]
+    grads[3][:100] = 0.0                                      # exact zeros too
+    want_p, want_m, want_v = _adam_reference(p0, grads, 1e-3, 0.01, 150000)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    sched = tr.AdamSchedule(1e-3, (0.9, 0.999), 1e-8, 0.01, 150000)
+    lib = L.load()
+    for gk in grads:
+        gbuf = gk.clone()
+        cfg = sched.next()
+        L.check(lib.nerfca_adam_step(L.ptr(p), L.ptr(gbuf), L.ptr(m), L.ptr(v), n, C.byref(cfg), 1.0, 1, None, L.stream_ptr()), "nerfca_adam_step")
+    torch.cuda.synchronize()
+    assert float(gbuf.abs().max()) == 0.0                     # zero_grads
+    for name, a, b in (("exp_avg", m, want_m), ("exp_avg_sq", v, want_v), ("params", p, want_p)):
+        bad = int((a != b).sum())
+        ulps = ulp_diff(a.cpu().numpy(), b.cpu().numpy()).max() if bad else 0
+        assert bad == 0, f"{name}: {bad} of {n} elements differ from torch after {steps} updates (max {ulps} ulp)"
+
+
+def test_adam_repack_keeps_operand_tiles_current():
+    """The bf16 operand blocks the optimizer kernel writes (nerfca_repack_t) equal a fresh pack of the updated parameters: a trainer
+    that never re-packs (NERFCA_STEP_PACKED after the first step) and one that re-packs every step stay bit-identical."""
+    from nerfca import trainer as tr
+    rays, phases, z = parity.synthetic_batch(256, 64, seed=31)
+    rays, phases, z = rays.to(DEV), phases.to(DEV).int(), z.to(DEV)
+    outs = []
+    for force_pack in (False, True):
+        torch.manual_seed(0)
+        t = tr.CompositeTrainer.from_config(device=DEV, precision="bf16", n_depth=64)
+        t.set_iteration(50000)
+        for k in range(6):
+            if force_pack:
+                t.parameters_changed()
+            t.step_device(rays, phases, z)
+        torch.cuda.synchronize()
+        outs.append((t.flat_p.clone(), t.last_terms.clone(), t._plan(256).ws[:400000].clone()))
+    assert parity.rel_l2(outs[0][0].cpu().numpy(), outs[1][0].cpu().numpy()) <= 1e-5      # fp32 atomics order only
+    np.testing.assert_allclose(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy(), rtol=1e-4)
+    # the packed blocks themselves (both nets, ~318 KB): same bytes wherever the fp32 parameters round to the same bf16
+    a, b = outs[0][2].view(torch.int16), outs[1][2].view(torch.int16)
+    assert float((a != b).float().mean()) < 1e-3
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_trainer_trajectory_vs_oracle_and_torch_adam(precision):
+    """20 optimisation steps of CompositeTrainer (graph replay, fused Adam, re-pack in the optimizer kernel, gradient clearing,
+    per-step frequency mask / loss weights via set_iteration) vs the CPU oracle's loss + torch.optim.Adam + LinearLR driven the way
+    run_composite.py:227-308 drives them.  Compared: the loss of every step and the parameter UPDATE p_20 - p_0 per net."""
+    from nerfca import trainer as tr
+    n_rays, n_depth, steps, it0 = 128, 64, 20, 49990
+    torch.manual_seed(0)
+    t = tr.CompositeTrainer.from_config(device=DEV, precision=precision, n_depth=n_depth)
+    sd_s = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in t.static.state_dict().items()}
+    sd_d = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in t.temp.state_dict().items()}
+    p0 = t.flat_p.clone()
+    opt = torch.optim.Adam(list(sd_d.values()) + list(sd_s.values()), lr=1e-3)              # run_composite.py:209-212
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.01, total_iters=150000)
+    i0 = torch.full((n_rays,), parity.I0, dtype=torch.float32)
+    losses_o, losses_g = [], []
+    for k in range(steps):
+        rays, phases, z = parity.synthetic_batch(n_rays, n_depth, seed=400 + k)
+        it = it0 + k
+        mask, _ = orc.freq_mask(12, it, 150000, 1)
+        cfg = {"n_freq": 12, "n_hidden": 4, "pos_enc": "free_windowed", "window": mask}
+        loss, _ = orc.composite_step_loss(sd_s, sd_d, cfg, cfg, rays[:, 0, :], rays[:, 1, :], phases, i0, z, rays[:, 2, 0], rays[:, 3, 0],
+                                          orc.COMPOSITE_HP, it)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        sched.step()
+        losses_o.append(float(loss))
+        t.set_iteration(it)
+        t.step_device(rays.to(DEV), phases.to(DEV).int(), z.to(DEV))
+        losses_g.append(float(t.loss_from(t.last_terms, n_rays)))
+    torch.cuda.synchronize()
+    rt = 1e-4 if precision == "fp32" else 2e-2
+    np.testing.assert_allclose(losses_g, losses_o, rtol=rt)
+    assert losses_o[-1] < losses_o[0]                                                       # and it trains
+    for name, model, sd in (("static", t.static, sd_s), ("dynamic", t.temp, sd_d)):
+        got_upd, want_upd = [], []
+        for k, p in model.named_parameters():
+            o = (p.data_ptr() - t.flat_p.data_ptr()) // 4
+            start = p0[o:o + p.numel()].cpu().numpy().ravel()
+            got_upd.append(p.detach().cpu().numpy().ravel() - start)
+            want_upd.append(sd[k].detach().numpy().ravel() - start)
+        got_upd, want_upd = np.concatenate(got_upd), np.concatenate(want_upd)
+        r = parity.rel_l2(got_upd, want_upd)
+        print(f"trajectory {precision} {name}: update rel-L2 {r:.3e}, |update| {np.linalg.norm(want_upd):.3e}")
+        # Adam normalises every coordinate's step to ~lr, so coordinates whose gradient is noise-level (masked frequency bands, 1e-8
+        # weights) turn a bf16-sized gradient error into an O(1) relative error of THEIR update; the bound is on the whole update vector
+        assert r <= (2e-2 if precision == "fp32" else 0.35), (name, r)
+    st = t.graph_stats()
+    assert st["enabled"] and st["launches"] == steps and st["instantiations"] <= 2
+
+
+def test_graph_replay_equals_eager_launches():
+    """The CUDA-graph replay of a step (one launch) and the same C calls launched one by one give the same trajectory."""
+    from nerfca import trainer as tr
+    batches = []
+    for k in range(5):
+        rays, phases, z = parity.synthetic_batch(200, 77, seed=500 + k)
+        batches.append((rays.to(DEV), phases.to(DEV).int(), z.to(DEV)))
+    res = []
+    for use_graph in (True, False):
+        torch.manual_seed(0)
+        t = tr.CompositeTrainer.from_config(device=DEV, precision="bf16", n_depth=77, use_graph=use_graph)
+        t.set_iteration(50000)
+        terms = []
+        for b in batches:
+            t.step_device(*b)
+            terms.append(t.last_terms.clone())
+        torch.cuda.synchronize()
+        res.append((t.flat_p.clone(), torch.stack(terms)))
+        assert t.graph_stats()["enabled"] == use_graph
+    assert parity.rel_l2(res[0][0].cpu().numpy(), res[1][0].cpu().numpy()) <= 1e-5
+    np.testing.assert_allclose(res[0][1].cpu().numpy(), res[1][1].cpu().numpy(), rtol=1e-4)
+
+
+def test_render_fp32_workspace_is_large_enough():
+    """fp32 render passes lay out enc | ping | pong in the step workspace (the size query returned the smaller backward
+    size): a full-chunk pass must not write past nerfca_step_workspace_bytes -- checked with a guard region behind the buffer."""
+    import ctypes as C
+    from nerfca import ops, _lib as L
+    sd_s = orc.init_field_state(75, 128, 4, seed=1)
+    sd_d = orc.init_field_state(83, 128, 4, 10, 8, seed=2)
+    s, t = parity.build_models(sd_s, sd_d, DEV, "fp32", mask=np.ones(12, dtype=np.float32))
+    B, N = 600, 500                                               # 300 000 samples > one 262 144-sample chunk
+    rays, phases, z = parity.synthetic_batch(B, N, seed=5)
+    o, d = rays[:, 0, :].float().to(DEV).contiguous(), rays[:, 1, :].float().to(DEV).contiguous()
+    smp = ops.Samples.from_rays(o, d, z.to(DEV), phases.to(DEV))
+    fs_s, fs_d = s._spec().struct([p.detach() for p in s._param_list()]), t._spec().struct([p.detach() for p in t._param_list()])
+    stp = L.StepStruct()
+    stp.static_field, stp.dynamic_field, stp.samples, stp.precision = C.pointer(fs_s), C.pointer(fs_d), C.pointer(smp.struct()), L.PREC_FP32
+    need = L.load().nerfca_step_workspace_bytes(C.byref(stp))
+    guard = 1 << 20
+    buf = torch.full((need + guard,), 0x5A, dtype=torch.uint8, device=DEV)
+    raw = torch.empty((2, B * N), dtype=torch.float32, device=DEV)
+    L.check(L.load().nerfca_fields_forward(C.byref(fs_s), C.byref(fs_d), C.byref(smp.struct()), L.PREC_FP32, L.ptr(raw[0]), L.ptr(raw[1]),
+                                           L.ptr(buf), L.stream_ptr()), "nerfca_fields_forward")
+    torch.cuda.synchronize()
+    assert bool((buf[need:] == 0x5A).all()), "nerfca_fields_forward wrote past its workspace"
+    assert torch.isfinite(raw).all()
+
+
 # ---- N1: device-resident ray table, batches gathered on the device ---------------------------------------------------------
 
 def test_gather_batch_bit_exact_and_flags_bad_ids():
@@ -429,8 +655,11 @@ def test_trainer_step_from_ids_equals_step_from_host_rows():
     assert losses[0][0] == pytest.approx(losses[1][0], rel=1e-6)
     assert parity.rel_l2(losses[0][1].cpu().numpy(), losses[1][1].cpu().numpy()) <= 1e-5     # fp32 atomics order only
     t.attach_ray_table(rays, phases)
-    with pytest.raises(ValueError):
-        t.step_ids_async(torch.tensor([0, 600]).pin_memory(), t_rand[0].pin_memory()).loss()
+    before = t.flat_p.clone()
+    with pytest.raises(IndexError):          # like upstream's numpy fancy index: raised before anything is enqueued or updated
+        t.step_ids_async(torch.tensor([0, 600]).pin_memory(), t_rand[0].pin_memory())
+    torch.cuda.synchronize()
+    assert torch.equal(before, t.flat_p)
 
 
 # ---- BASELINE config 5: widened stress shapes ------------------------------------------------------------------------------------

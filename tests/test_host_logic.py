@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.nerfca_abi_version() == 1
+    assert lib.nerfca_abi_version() == _lib.ABI_VERSION
     out = os.popen(f"nm -D --defined-only {_lib.LIB_PATH}").read()
     for name in declared:
         assert f" T {name}" in out
@@ -35,7 +35,8 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_lib.SamplesStruct) == 8 + 8 + 4 + 4 + 8 + 8 + 4 + 4 + 8 + 8 + 8
     assert C.sizeof(_lib.LossCfgStruct) == 6 * 8 + 2 * 4
     assert C.sizeof(_lib.PeersStruct) == 2 * 4 + 3 * 8          # nerfca_peers_t
-    assert C.sizeof(_lib.AdamCfgStruct) == 5 * 8 + 8            # nerfca_adam_cfg_t
+    assert C.sizeof(_lib.AdamStepStruct) == 6 * 8               # nerfca_adam_step_t
+    assert C.sizeof(_lib.RepackStruct) == 3 * 8                 # nerfca_repack_t
 
 
 def test_cpu_tensors_fail_loudly():

@@ -71,7 +71,7 @@ def _worker(rank, world, port, ret):
         torch.set_num_threads(1)
         sd_s, sd_d, cfg, rays, phases, z = _setup()
         hs, hd = _Holder(sd_s), _Holder(sd_d)
-        flat_p, flat_g = tr.flatten_parameters([hs, hd], "cpu")          # the product's flat parameter / gradient buffers
+        flat_p, flat_g, _ = tr.flatten_parameters([hs, hd], "cpu")       # the product's flat parameter / gradient buffers
         sl = tr.shard_slice(N_RAYS, rank, world)
         loss = _shard_loss(hs.state(), hd.state(), cfg, rays[sl], phases[sl], z, N_RAYS)
         params = list(hs.parameters()) + list(hd.parameters())
@@ -125,3 +125,38 @@ def test_shard_slices_cover_the_batch():
             s = tr.shard_slice(n, r, w)
             seen.extend(range(s.start, s.stop))
         assert seen == list(range(n))
+
+
+def test_adam_schedule_scalars_equal_torch():
+    """The host-side scalars handed to nerfca_adam_step (learning rate of LinearLR's recursive form, bias corrections) are the ones
+    torch.optim.Adam + LinearLR(1 -> 0.01 over 150000) use, bit for bit, over the first 3000 updates and around the end of the decay."""
+    p = torch.nn.Parameter(torch.zeros(4))
+    opt = torch.optim.Adam([p], lr=1e-3)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.01, total_iters=40)
+    mine = tr.AdamSchedule(1e-3, (0.9, 0.999), 1e-8, 0.01, 40)
+    for t in range(1, 60):
+        cfg = mine.next()
+        assert cfg.lr == opt.param_groups[0]["lr"], t
+        assert cfg.bias_correction1 == 1 - 0.9 ** t and cfg.bias_correction2_sqrt == (1 - 0.999 ** t) ** 0.5
+        p.grad = torch.ones(4)
+        opt.step()
+        sched.step()
+    assert mine.lr == opt.param_groups[0]["lr"] == pytest.approx(1e-5)
+    opt = torch.optim.Adam([p], lr=1e-3)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.01, total_iters=150000)
+    mine = tr.AdamSchedule(1e-3, (0.9, 0.999), 1e-8, 0.01, 150000)
+    for t in range(1, 3001):
+        assert mine.next().lr == opt.param_groups[0]["lr"], t
+        opt.step()
+        sched.step()
+
+
+def test_global_batch_size_of_uneven_shards():
+    """10 rays over 3 ranks are sharded 4 / 3 / 3: every rank must divide by the GLOBAL 10, not by local * world (12 / 9 / 9)."""
+    class T:                      # the method only needs world_size
+        world_size = 3
+    sizes = [tr.shard_slice(10, r, 3).stop - tr.shard_slice(10, r, 3).start for r in range(3)]
+    assert sizes == [4, 3, 3]
+    for b in sizes:
+        assert tr.CompositeTrainer._global_rays(T, b, 10) == 10
+    assert tr.CompositeTrainer._global_rays(T, 4, None) == 12          # default: even shards

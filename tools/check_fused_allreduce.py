@@ -17,12 +17,14 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-N_RAYS, N_DEPTH, STEPS = 256, 500, 6
+N_DEPTH, STEPS = 500, 6
+N_RAYS = 256 if rank == 0 else 192                 # UNEVEN shards: the 1/B of every mean must be the global batch size
+N_GLOBAL = 256 + 192 * (world - 1)
 batches = []
 for k in range(STEPS):
     rays, phases, z = parity.synthetic_batch(N_RAYS, N_DEPTH, seed=100 + 10 * k + rank)      # a different shard on every rank
     _, _, z = parity.synthetic_batch(1, N_DEPTH, seed=100 + 10 * k)                            # the same depth draw on every rank
-    batches.append((rays.to(dev), phases.to(dev).int(), z.to(dev)))
+    batches.append((rays.to(dev), phases.to(dev).int(), z.to(dev), N_GLOBAL))
 
 
 def run(fused: bool):
@@ -52,19 +54,22 @@ def params_after(fused):
     for b in batches:
         t.step_device(*b)
     torch.cuda.synchronize()
-    return t.flat_p.clone(), int(t.step_dev.item()), float(t.flat_g.abs().max())
+    return t.flat_p.clone(), t.schedule.t, float(t.flat_g.abs().max()), t.last_terms.clone(), (t.peer_grads is not None)
 
 
-pf, step_f, gmax_f = params_after(True)
-pn, step_n, gmax_n = params_after(False)
+pf, step_f, gmax_f, terms_f, was_fused = params_after(True)
+pn, step_n, gmax_n, terms_n, was_nccl_fused = params_after(False)
+assert was_fused and not was_nccl_fused
 gathered = [torch.zeros_like(pf) for _ in range(world)]
 dist.all_gather(gathered, pf)
 identical = all(torch.equal(gathered[0], g) for g in gathered[1:])
 rel = parity.rel_l2(pf.cpu().numpy(), pn.cpu().numpy())
+terms_rel = parity.rel_l2(terms_f.cpu().numpy(), terms_n.cpu().numpy())      # the loss sums that rode in the gradient exchange
 _, ms_f = run(True)
 _, ms_n = run(False)
 if rank == 0:
     print(f"world {world}: replicas bit-identical {identical}; fused vs NCCL params rel-L2 {rel:.3e}; steps {step_f}/{step_n}; "
           f"grad buffers cleared {gmax_f == 0.0}/{gmax_n == 0.0}; ms/step fused {ms_f:.4f}  nccl {ms_n:.4f}", flush=True)
-    assert identical and rel <= 1e-4 and step_f == step_n == STEPS and gmax_f == 0.0
+    print(f"loss sums fused vs NCCL rel-L2 {terms_rel:.3e}", flush=True)
+    assert identical and rel <= 1e-4 and step_f == step_n == STEPS and gmax_f == 0.0 and terms_rel <= 1e-12
 dist.destroy_process_group()
