@@ -6,8 +6,14 @@
 // kernels run back to back without host-side launch gaps.
 #include "common.cuh"
 
+// A small rotation of executable graphs, each with the event of its last launch: an executable graph is only updated once its
+// previous launch has finished (the host waits on that event), which also bounds the number of steps the host can run ahead of the
+// GPU to NERFCA_GRAPH_DEPTH.  (Updating ONE executable graph while thousands of its launches were still queued crashed inside the
+// driver in a 4 000-step soak run.)
+constexpr int NERFCA_GRAPH_DEPTH = 4;
 struct nerfca_graph {
-  cudaGraphExec_t exec = nullptr;
+  cudaGraphExec_t exec[NERFCA_GRAPH_DEPTH] = {};
+  cudaEvent_t done[NERFCA_GRAPH_DEPTH] = {};
   bool capturing = false;
   long long launches = 0, updates = 0, instantiations = 0;
 };
@@ -34,20 +40,31 @@ extern "C" int nerfca_graph_end_launch(nerfca_graph* g, void* stream) {
   g->capturing = false;
   cudaGraph_t graph = nullptr;
   NERFCA_CUDA_OK(cudaStreamEndCapture((cudaStream_t)stream, &graph));
+  const int k = (int)(g->launches % NERFCA_GRAPH_DEPTH);
+  if (g->done[k]) {
+    cudaError_t e = cudaEventSynchronize(g->done[k]);            // the launch that last used this executable graph has finished
+    if (e != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      set_error(std::string("nerfca_graph_end_launch: a previous step failed -> ") + cudaGetErrorString(e));
+      return NERFCA_E_CUDA;
+    }
+  } else {
+    NERFCA_CUDA_OK(cudaEventCreateWithFlags(&g->done[k], cudaEventDisableTiming));
+  }
   bool ok = false;
-  if (g->exec) {
+  if (g->exec[k]) {
     cudaGraphExecUpdateResultInfo info;
-    if (cudaGraphExecUpdate(g->exec, graph, &info) == cudaSuccess) {
+    if (cudaGraphExecUpdate(g->exec[k], graph, &info) == cudaSuccess) {
       ok = true;
       ++g->updates;
     } else {
       cudaGetLastError();                      // a changed launch sequence: build a new executable graph
-      cudaGraphExecDestroy(g->exec);
-      g->exec = nullptr;
+      cudaGraphExecDestroy(g->exec[k]);
+      g->exec[k] = nullptr;
     }
   }
   if (!ok) {
-    cudaError_t e = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaError_t e = cudaGraphInstantiate(&g->exec[k], graph, 0);
     if (e != cudaSuccess) {
       cudaGraphDestroy(graph);
       set_error(std::string("nerfca_graph_end_launch: cudaGraphInstantiate -> ") + cudaGetErrorString(e));
@@ -56,7 +73,8 @@ extern "C" int nerfca_graph_end_launch(nerfca_graph* g, void* stream) {
     ++g->instantiations;
   }
   cudaGraphDestroy(graph);
-  NERFCA_CUDA_OK(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+  NERFCA_CUDA_OK(cudaGraphLaunch(g->exec[k], (cudaStream_t)stream));
+  NERFCA_CUDA_OK(cudaEventRecord(g->done[k], (cudaStream_t)stream));
   ++g->launches;
   return NERFCA_OK;
 }
@@ -84,7 +102,10 @@ extern "C" int nerfca_graph_stats(const nerfca_graph* g, int64_t* launches, int6
 
 extern "C" int nerfca_graph_destroy(nerfca_graph* g) {
   if (!g) return NERFCA_OK;
-  if (g->exec) cudaGraphExecDestroy(g->exec);
+  for (int k = 0; k < NERFCA_GRAPH_DEPTH; ++k) {
+    if (g->exec[k]) cudaGraphExecDestroy(g->exec[k]);
+    if (g->done[k]) cudaEventDestroy(g->done[k]);
+  }
   delete g;
   return NERFCA_OK;
 }

@@ -1523,6 +1523,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
   bwd_bot_role(a, a.net[blockIdx.x % a.n_nets], blockIdx.x / a.n_nets, a.n_bot);
 }
 
+#include "mlp_tc_bwd2.cuh"
+
 // =====================================================================================================================
 // host side
 // =====================================================================================================================
@@ -1691,6 +1693,27 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
   NERFCA_REQUIRE(n_top >= 1 && n_bot >= 1, NERFCA_E_UNSUPPORTED, "tcgen05 backward needs at least two SMs per net");
   a.n_top = n_top; a.n_bot = n_bot; a.ring = (int)ring;
   NERFCA_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)n_nets * 2 * a.n_tiles * sizeof(uint32_t), st));
+  // second-generation kernel (two tiles in flight per CTA, mlp_tc_bwd2.cuh) unless NERFCA_BWD_V1=1 or the two-launch mode is asked for
+  if (merged && !env_flag("NERFCA_BWD_V1", 0)) {
+    if (!getenv("NERFCA_BWD_SPLIT")) {
+      // per tile the top role issues ~2 200 and the bottom role ~2 700 tensor-pipe cycles (both bounded by shared-memory bandwidth):
+      // 33 : 41 of 74, kept coprime (see below)
+      auto gcd2 = [](int x, int y) { while (y) { const int r = x % y; x = y; y = r; } return x; };
+      n_top = (per_net * 45 + 50) / 100;
+      while (n_top > 1 && gcd2(n_top, per_net - n_top) != 1) --n_top;
+      n_bot = per_net - n_top;
+      if (n_top > a.n_tiles) n_top = (int)a.n_tiles;
+      if (n_bot > a.n_tiles) n_bot = (int)a.n_tiles;
+      a.n_top = n_top; a.n_bot = n_bot;
+    }
+    a.role = 0;
+    a.dbg = nullptr;
+    NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD2_SMEM));
+    ProfScope prof(NERFCA_K_FIELD_BWD, st);
+    tc_bwd2_kernel<<<(unsigned)(n_nets * (n_top + n_bot)), BWD2_THREADS, BWD2_SMEM, st>>>(a);
+    NERFCA_LAUNCH_OK();
+    return NERFCA_OK;
+  }
   NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
   NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_bwd_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOP_SMEM));
   NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_bwd_bot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BOT_SMEM));

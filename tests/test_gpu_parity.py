@@ -556,9 +556,9 @@ def test_trainer_trajectory_vs_oracle_and_torch_adam(precision):
         print(f"trajectory {precision} {name}: update rel-L2 {r:.3e}, |update| {np.linalg.norm(want_upd):.3e}")
         # Adam normalises every coordinate's step to ~lr, so coordinates whose gradient is noise-level (masked frequency bands, 1e-8
         # weights) turn a bf16-sized gradient error into an O(1) relative error of THEIR update; the bound is on the whole update vector
-        assert r <= (2e-2 if precision == "fp32" else 0.35), (name, r)
+        assert r <= (1e-3 if precision == "fp32" else 5e-2), (name, r)     # measured: 7e-5 / 1e-2
     st = t.graph_stats()
-    assert st["enabled"] and st["launches"] == steps and st["instantiations"] <= 2
+    assert st["enabled"] and st["launches"] == steps and st["instantiations"] <= 8
 
 
 def test_graph_replay_equals_eager_launches():
