@@ -1,6 +1,8 @@
 // X-ray line integral (A9), its autograd, and the fused training loss + closed-form dL/d_raw (A9 + A10).
 // One warp per ray (one CTA per ray in the fused loss kernel); ray sums by warp shuffle; HBM traffic = the raw field outputs in,
 // sigma / gradients out.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nerfca {
@@ -82,9 +84,8 @@ struct LossCfg {
 // One CTA of LOSS_THREADS threads per ray (a warp per ray leaves the SMs at ~10 % occupancy for 1024 rays, and the fp64 logarithms
 // make the kernel latency bound); sigma_s / sigma_d of the ray live in shared memory between the three sweeps, the ray sums go
 // through warp shuffles and a small shared-memory exchange (fixed order: the result does not depend on scheduling).
-constexpr int LOSS_THREADS = 128;
 // sums `v[0..N)` over the CTA; every thread returns with the totals.  scratch: N * (LOSS_THREADS / 32) doubles
-template <int N>
+template <int N, int LOSS_THREADS>
 __device__ __forceinline__ void block_sum(double (&v)[N], double* scratch) {
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -103,14 +104,15 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double* scratch) {
     v[k] = t;
   }
 }
-__global__ void composite_loss_kernel(const float* __restrict__ raw_s, const float* __restrict__ raw_d,
+template <int LOSS_THREADS>
+__global__ void __launch_bounds__(LOSS_THREADS) composite_loss_kernel(const float* __restrict__ raw_s, const float* __restrict__ raw_d,
                                       const float* __restrict__ z, const float* __restrict__ i0,
                                       const double* __restrict__ gt, const double* __restrict__ wpix, int gw_stride,
                                       int n_rays, int n, int act, LossCfg c, double* __restrict__ pix_out,
                                       double* __restrict__ terms, float* __restrict__ d_raw_s, float* __restrict__ d_raw_d) {
   extern __shared__ double sm_d[];
   double* scratch = sm_d;                                   // 8 * (LOSS_THREADS / 32) doubles
-  float* ss_c = reinterpret_cast<float*>(sm_d + 8 * (LOSS_THREADS / 32));
+  float* ss_c = reinterpret_cast<float*>(sm_d + 8 * (256 / 32));
   float* sd_c = ss_c + n;
   const int ray = blockIdx.x, lane = threadIdx.x;           // `lane`: index of the thread within the ray's CTA
   if (ray >= n_rays) return;
@@ -139,7 +141,7 @@ __global__ void composite_loss_kernel(const float* __restrict__ raw_s, const flo
   {
     // the six ray sums in one exchange, the two maxima in a second one
     double v[6] = {W, Ss, Sd, l2, bw_sum, fav_sum};
-    block_sum<6>(v, scratch);
+    block_sum<6, LOSS_THREADS>(v, scratch);
     W = v[0]; Ss = v[1]; Sd = v[2]; l2 = v[3]; bw_sum = v[4]; fav_sum = v[5];
     mx_s = warp_max(mx_s); mx_d = warp_max(mx_d);
     __syncthreads();
@@ -168,7 +170,7 @@ __global__ void composite_loss_kernel(const float* __restrict__ raw_s, const flo
   }
   {
     double v[3] = {ent_s, ent_d, hp_d};
-    block_sum<3>(v, scratch);
+    block_sum<3, LOSS_THREADS>(v, scratch);
     ent_s = v[0]; ent_d = v[1]; hp_d = v[2];
   }
 
@@ -319,12 +321,22 @@ extern "C" int nerfca_composite_loss(const float* raw_s, const float* raw_d, con
     NERFCA_LAUNCH_OK();
     return NERFCA_OK;
   }
-  const size_t smem = 8 * (LOSS_THREADS / 32) * sizeof(double) + (size_t)2 * n_depth * sizeof(float);
+  // one CTA per ray; 256 threads (2 samples per thread and sweep at N = 500): the kernel is bound by the latency of its three
+  // dependent sweeps, not by throughput (NERFCA_LOSS_THREADS=128 selects the narrower CTA for comparison)
+  static const int loss_threads = (getenv("NERFCA_LOSS_THREADS") && atoi(getenv("NERFCA_LOSS_THREADS")) == 128) ? 128 : 256;
+  const size_t smem = 8 * (256 / 32) * sizeof(double) + (size_t)2 * n_depth * sizeof(float);
   NERFCA_REQUIRE(smem <= 200 * 1024, NERFCA_E_UNSUPPORTED, "n_depth too large for the fused loss kernel");
-  if (smem > 48 * 1024)
-    NERFCA_CUDA_OK(cudaFuncSetAttribute(composite_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  composite_loss_kernel<<<n_rays, LOSS_THREADS, smem, st>>>(raw_s, raw_d, depth, i0, gt, wpix, gw_stride, n_rays, n_depth, activation, c,
-                                                         pix_out, terms_out, d_raw_s, d_raw_d);
+  if (loss_threads == 128) {
+    if (smem > 48 * 1024)
+      NERFCA_CUDA_OK(cudaFuncSetAttribute(composite_loss_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    composite_loss_kernel<128><<<n_rays, 128, smem, st>>>(raw_s, raw_d, depth, i0, gt, wpix, gw_stride, n_rays, n_depth, activation, c,
+                                                        pix_out, terms_out, d_raw_s, d_raw_d);
+  } else {
+    if (smem > 48 * 1024)
+      NERFCA_CUDA_OK(cudaFuncSetAttribute(composite_loss_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    composite_loss_kernel<256><<<n_rays, 256, smem, st>>>(raw_s, raw_d, depth, i0, gt, wpix, gw_stride, n_rays, n_depth, activation, c,
+                                                        pix_out, terms_out, d_raw_s, d_raw_d);
+  }
   NERFCA_LAUNCH_OK();
   return NERFCA_OK;
 }

@@ -776,7 +776,8 @@ __device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr) {
 }
 // generic-proxy global writes <-> async-proxy (bulk copy) reads of the same bytes
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// Bounded spin on a flag: a protocol bug traps (launch failure) instead of hanging the GPU.
+// Bounded spin on a flag: a protocol bug traps (launch failure) instead of hanging the GPU.  (Polling with relaxed loads + one
+// acquire fence after the successful poll -- to spare the L1 invalidation an acquire load implies -- measured 4 % slower, r3j.)
 __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t want) {
   if (ld_acquire_gpu(p) >= want) return;
   const long long t0 = clock64();
@@ -1579,6 +1580,23 @@ static X0Desc make_x0(const nerfca_field_t& f, const NetDims& d) {
   return x;
 }
 
+__global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_kernel(BwdArgs a);
+// can `grid` CTAs of the one-launch backward be resident at the same time on this device (and may it be launched cooperatively)?
+static bool bwd_coresident(int grid) {
+  static int cached_grid = -1, cached = 0;
+  if (cached_grid == grid) return cached != 0;
+  int dev = 0, coop = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  bool ok = coop != 0 && cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tc_bwd_kernel, BWD_THREADS, BWD_SMEM) == cudaSuccess &&
+            (long long)per_sm * sm_count() >= grid;
+  if (!ok) cudaGetLastError();
+  cached_grid = grid;
+  cached = ok ? 1 : 0;
+  return ok;
+}
+
 static unsigned grid_for(int n_nets, long long n_tiles) {
   long long g = sm_count() / n_nets * n_nets;
   const long long need = n_tiles * n_nets;
@@ -1645,7 +1663,11 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
   a.n_tiles = (long long)n_tiles_of(s.n_points);
   size_t off = 0;
   uint8_t* handoff = (uint8_t*)workspace + tc_pack_bytes_n(f, n_nets);
-  const int merged = env_flag("NERFCA_BWD_MERGED", 1);
+  // The one-launch mode makes top-role and bottom-role CTAs wait on each other's flags: that is only deadlock-free if every CTA of
+  // the grid is resident at once.  It is therefore launched COOPERATIVELY (the driver co-schedules the whole grid or refuses), and
+  // only if the occupancy query says grid <= resident CTAs (MPS partitions, MIG slices or green contexts shrink that); otherwise
+  // the roles run as two launches with the hand-off through HBM.
+  const int merged = env_flag("NERFCA_BWD_MERGED", 1) && bwd_coresident(sm_count() / n_nets * n_nets);
   const size_t ring = merged ? (size_t)BWD_RING : ((size_t)a.n_tiles > (size_t)BWD_RING ? (size_t)a.n_tiles : (size_t)BWD_RING);
   const size_t ring_alloc = (size_t)a.n_tiles > (size_t)BWD_RING ? (size_t)a.n_tiles : (size_t)BWD_RING;
   uint32_t* flags = reinterpret_cast<uint32_t*>(handoff + (size_t)n_nets * ring_alloc * TILE_BYTES);
@@ -1693,8 +1715,10 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
   NERFCA_REQUIRE(n_top >= 1 && n_bot >= 1, NERFCA_E_UNSUPPORTED, "tcgen05 backward needs at least two SMs per net");
   a.n_top = n_top; a.n_bot = n_bot; a.ring = (int)ring;
   NERFCA_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)n_nets * 2 * a.n_tiles * sizeof(uint32_t), st));
-  // second-generation kernel (two tiles in flight per CTA, mlp_tc_bwd2.cuh) unless NERFCA_BWD_V1=1 or the two-launch mode is asked for
-  if (merged && !env_flag("NERFCA_BWD_V1", 0)) {
+  // NERFCA_BWD_V2=1: the second-generation kernel (two tiles in flight per CTA on one shared accumulator, mlp_tc_bwd2.cuh).  Parity-
+  // green and soak-clean, but measured 5 % SLOWER than tc_bwd_kernel (r3j: 410 vs 390 us): with every dgrad in SS form the two tiles
+  // in flight compete for the shared-memory bandwidth that the MMAs' operand reads already saturate, see DESIGN.md section 6.
+  if (merged && env_flag("NERFCA_BWD_V2", 0)) {
     if (!getenv("NERFCA_BWD_SPLIT")) {
       // per tile the top role issues ~2 200 and the bottom role ~2 700 tensor-pipe cycles (both bounded by shared-memory bandwidth):
       // 33 : 41 of 74, kept coprime (see below)
@@ -1708,10 +1732,21 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
     }
     a.role = 0;
     a.dbg = nullptr;
+    a.dbg_cta = getenv("NERFCA_TIMELINE_CTA") ? atoi(getenv("NERFCA_TIMELINE_CTA")) : 0;
+    const bool tl2 = timeline_wanted("top") || timeline_wanted("bot");     // developer aid (make TL=1)
+    if (tl2) {
+      NERFCA_CUDA_OK(cudaMalloc(&a.dbg, 8008 * sizeof(long long)));
+      NERFCA_CUDA_OK(cudaMemsetAsync(a.dbg, 0, 8008 * sizeof(long long), st));
+    }
     NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD2_SMEM));
-    ProfScope prof(NERFCA_K_FIELD_BWD, st);
-    tc_bwd2_kernel<<<(unsigned)(n_nets * (n_top + n_bot)), BWD2_THREADS, BWD2_SMEM, st>>>(a);
-    NERFCA_LAUNCH_OK();
+    {
+      ProfScope prof(NERFCA_K_FIELD_BWD, st);
+      void* kargs[] = {&a};
+      NERFCA_CUDA_OK(cudaLaunchCooperativeKernel((const void*)tc_bwd2_kernel, dim3((unsigned)(n_nets * (n_top + n_bot))), dim3(BWD2_THREADS), kargs,
+                                                 BWD2_SMEM, st));
+      NERFCA_LAUNCH_OK();
+    }
+    if (tl2) return timeline_dump(a.dbg, st);
     return NERFCA_OK;
   }
   NERFCA_CUDA_OK(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
@@ -1729,7 +1764,9 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
     ProfScope prof(NERFCA_K_FIELD_BWD, st);
     if (merged) {
       a.role = 0;
-      tc_bwd_kernel<<<(unsigned)(n_nets * (n_top + n_bot)), BWD_THREADS, BWD_SMEM, st>>>(a);
+      void* kargs[] = {&a};
+      NERFCA_CUDA_OK(cudaLaunchCooperativeKernel((const void*)tc_bwd_kernel, dim3((unsigned)(n_nets * (n_top + n_bot))), dim3(BWD_THREADS), kargs,
+                                                 BWD_SMEM, st));
       NERFCA_LAUNCH_OK();
     } else {
       BwdArgs b = a;

@@ -42,6 +42,7 @@ __device__ __forceinline__ void acc_acquire(uint32_t ticket_addr, uint32_t rel_a
   if (ld_acquire_cta_shared(rel_addr) < need) {
     const long long t0 = clock64();
     while (ld_acquire_cta_shared(rel_addr) < need) {
+      __nanosleep(40);
       if (clock64() - t0 > 4000000000LL) {
 #ifdef NERFCA_TIMELINE_BUILD
         printf("accumulator lock timeout: block %d warp %d need %u have %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), need, ld_acquire_cta_shared(rel_addr));
@@ -136,8 +137,13 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
   const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
+  [[maybe_unused]] int tl_n = 0;     // developer timeline (make TL=1, NERFCA_TIMELINE=top): regions 1/2 = epilogue slot 0/1 (warp 1 / 9, lane 0), 3 = issuer 0, 0 = issuer 1
 
-  if (warp >= 16) reg_dealloc<56>();
+  // register budget (setmaxnreg; the CTA's pool starts EMPTY: only what warps hand back can be taken): the kernel launches with
+  // 80 x 768 = 61 440 registers = 16 epilogue warps x 88 + 8 other warps x 64.  With these budgets ptxas spills 24 bytes in the whole
+  // kernel.  Spills are poison here: the flag polls of the hand-off (gpu-scope acquire = CCTL.IVALL) keep invalidating L1, so
+  // every reload of a spilled MMA descriptor went to L2 (measured: 3 600 cycles to issue the 8 MMAs of one dgrad at 40 registers).
+  if (warp >= 16) reg_dealloc<64>();
   if (warp == 18 || warp == 19) {
     // ================= load warp of slot s =================
     const int s = warp - 18;
@@ -150,29 +156,38 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
       bulk_g2s(smem_u32(s_w3), nt.pack + nt.w0_bytes + 2 * (size_t)TILE_BYTES, TILE_BYTES, bar_w);
       bulk_g2s(smem_u32(s_w4), nt.pack + nt.w0_bytes + 3 * (size_t)TILE_BYTES, TILE_BYTES, bar_w);
     }
-    for (long long j = 0; j < n_s; ++j) {
+    // H4 pattern + d_raw of the slot's j-th tile -> the small per-slot buffers (whole warp: d_raw by plain loads, the last tile may
+    // be ragged and rows past the end get a zero gradient); free once step A of the slot's previous tile has consumed its own
+    auto load_pattern = [&](long long j) {
       const long long tile = worker + (s + 2 * j) * n_workers;
-      const uint8_t* st = nt.stash + (size_t)tile * STASH_STRIDE;
-      const uint32_t pj = (uint32_t)(j & 1);
-      // d_raw of the tile's rows (plain loads: the last tile may be ragged; rows past the end get a zero gradient)
       float gv[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const long long p = tile * TILE_M + lane * 4 + e;
         gv[e] = (p < a.src.n_points) ? __ldg(nt.d_raw + p) : 0.f;
       }
-      if (j > 0) mbar_wait(bar_of(s, B_MFREE), pj ^ 1);          // step A of the slot's previous tile has consumed its pattern + d_raw
+      if (j > 0) mbar_wait(bar_of(s, B_MFREE), (uint32_t)((j - 1) & 1));
       *reinterpret_cast<float4*>(g_dst + lane * 4) = make_float4(gv[0], gv[1], gv[2], gv[3]);
       __syncwarp();
       if (lane == 0) {
         mbar_expect_tx(bar_of(s, B_LDM), MASK_BYTES);
-        bulk_g2s(m4, st + (size_t)STASH_TILES * TILE_BYTES, MASK_BYTES, bar_of(s, B_LDM));
+        bulk_g2s(m4, nt.stash + (size_t)tile * STASH_STRIDE + (size_t)STASH_TILES * TILE_BYTES, MASK_BYTES, bar_of(s, B_LDM));
+      }
+      __syncwarp();
+    };
+    if (n_s > 0) load_pattern(0);
+    for (long long j = 0; j < n_s; ++j) {
+      const long long tile = worker + (s + 2 * j) * n_workers;
+      const uint8_t* st = nt.stash + (size_t)tile * STASH_STRIDE;
+      const uint32_t pj = (uint32_t)(j & 1);
+      if (lane == 0) {
         if (j > 0) mbar_wait(bar_of(s, B_WG3), pj ^ 1);          // weight gradient 3 of the previous tile no longer reads dZ3 (b1) / H2 (b2)
         mbar_expect_tx(bar_of(s, B_LDH3), TILE_BYTES);
         bulk_g2s(b1, st + 3 * (size_t)TILE_BYTES, TILE_BYTES, bar_of(s, B_LDH3));
-        // hand-off slot of this tile: free once the bottom role has copied out the tile that used it `ring` tiles earlier
-        if (tile >= a.ring) wait_flag_ge(nt.consumed + (tile - a.ring), 1u);
-        mbar_arrive(bar_of(s, B_SLOT));
+      }
+      __syncwarp();
+      if (j + 1 < n_s) load_pattern(j + 1);                       // (waits for step A of tile j: early in the tile)
+      if (lane == 0) {
         mbar_wait(bar_of(s, B_WG4), pj);                           // weight gradient 4 no longer reads R: its buffer takes H2
         mbar_expect_tx(bar_of(s, B_LDH2), TILE_BYTES);
         bulk_g2s(b2, st + 2 * (size_t)TILE_BYTES, TILE_BYTES, bar_of(s, B_LDH2));
@@ -180,8 +195,13 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
           const uint8_t* nx = nt.stash + (size_t)(tile + 2 * n_workers) * STASH_STRIDE;
           bulk_prefetch_l2(nx + 2 * (size_t)TILE_BYTES, TILE_BYTES);
           bulk_prefetch_l2(nx + 3 * (size_t)TILE_BYTES, TILE_BYTES);
-          bulk_prefetch_l2(nx + (size_t)STASH_TILES * TILE_BYTES, MASK_BYTES);
         }
+        // hand-off slot of this tile: free once the bottom role has copied out the tile that used it `ring` tiles earlier.  The
+        // arrival comes AFTER weight gradient 4 of this tile was issued, i.e. after step A of this tile, i.e. after the epilogue
+        // warps have consumed the arrival for the slot's previous tile in its step C: never more than one phase ahead of its
+        // only waiter (arriving earlier let this barrier run two phases ahead and the waiter's parity test alias).
+        if (tile >= a.ring) wait_flag_ge(nt.consumed + (tile - a.ring), 1u);
+        mbar_arrive(bar_of(s, B_SLOT));
       }
       __syncwarp();
     }
@@ -198,22 +218,33 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
       tc_fence_after();
       for (long long j = 0; j < n_s; ++j) {
         const uint32_t pj = (uint32_t)(j & 1);
+        const int tb = s ? 100 : 3000;
         mbar_wait(bar_of(s, B_READY), 0);                          // step A: R is in b2
+        NERFCA_TL(true, tb + 1);
         acc_acquire(acc_ticket, acc_rel);
+        NERFCA_TL(true, tb + 2);
         umma_k<8, KK, KM>(tmem + T2_ACC, kmajor(b2), mnmajor(w4), id_dgrad, 0);                  // dH3 = R W4'
         umma_commit(bar_of(s, B_ACC));
+        NERFCA_TL(true, tb + 3);
         mbar_wait(bar_of(s, B_LDH3), pj);
         tc_fence_after();
+        NERFCA_TL(true, tb + 4);
         umma_k<8, KM, KM>(tmem + T2_WG4, mnmajor(b2), mnmajor(b1), id_wgrad, 1);                 // WG4 += R^T [H3 | 1]
         umma_commit(bar_of(s, B_WG4));
+        NERFCA_TL(true, tb + 5);
         mbar_wait(bar_of(s, B_READY), 1);                          // step B: dZ3 is in b1
+        NERFCA_TL(true, tb + 11);
         acc_acquire(acc_ticket, acc_rel);
+        NERFCA_TL(true, tb + 12);
         umma_k<8, KK, KM>(tmem + T2_ACC, kmajor(b1), mnmajor(w3), id_dgrad, 0);                  // dH2 = dZ3 W3
         umma_commit(bar_of(s, B_ACC));
+        NERFCA_TL(true, tb + 13);
         mbar_wait(bar_of(s, B_LDH2), pj);
         tc_fence_after();
+        NERFCA_TL(true, tb + 14);
         umma_k<8, KM, KM>(tmem + T2_WG3, mnmajor(b1), mnmajor(b2), id_wgrad, 1);                 // WG3 += dZ3^T [H2 | 1]
         umma_commit(bar_of(s, B_WG3));
+        NERFCA_TL(true, tb + 15);
       }
     }
     __syncwarp();
@@ -250,7 +281,7 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
     }
     __syncwarp();
   } else if (warp < 16) {
-    reg_alloc<96>();
+    reg_alloc<88>();
     // ================= 2 x 8 epilogue warps: slot = warp / 8, thread = (row, column half) =================
     const int slot = warp >> 3, q = warp & 3, ch = (warp >> 2) & 1;
     const int row = q * 32 + lane;
@@ -285,9 +316,14 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
     for (long long j = 0; j < n_s; ++j) {
       const uint32_t pj = (uint32_t)(j & 1);
       uint32_t va[32], vb[32], w[32];
+      const bool tl_me = (warp & 7) == 1 && lane == 0;
+      const int te = 1000 + 1000 * slot;
       // ---- step A: R = d_raw 1[H4 > 0] -> b2 (A operand of dgrad 4 and of wgrad 4)
+      NERFCA_TL(tl_me, te + 0);
       mbar_wait(bar_of(slot, B_LDM), pj);
+      NERFCA_TL(tl_me, te + 1);
       if (j > 0) mbar_wait(bar_of(slot, B_WG3), pj ^ 1);         // weight gradient 3 of the previous tile no longer reads H2 in b2
+      NERFCA_TL(tl_me, te + 2);
       {
         const float g_cur = g_src[row];
         if (ch == 0) gb_sum += g_cur;
@@ -305,24 +341,36 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) { mbar_arrive(bar_of(slot, B_MFREE)); mbar_arrive(bar_of(slot, B_READY)); }
+      NERFCA_TL(tl_me, te + 3);
       // ---- step B: dZ3 = dH3 * 1[H3 > 0] -> b1, over H3 itself once weight gradient 4 has read it
       mbar_wait(bar_of(slot, B_ACC), ph_acc); ph_acc ^= 1;
       tc_fence_after();
+      NERFCA_TL(tl_me, te + 10);
       ld_acc64(k_acc, va, vb);
       acc_release(acc_rel, lane);
+      NERFCA_TL(tl_me, te + 11);
       mbar_wait(bar_of(slot, B_LDH3), pj);
+      NERFCA_TL(tl_me, te + 12);
       masked_grad_pack64(va, vb, b1, w);
+      NERFCA_TL(tl_me, te + 13);
       mbar_wait(bar_of(slot, B_WG4), pj);
+      NERFCA_TL(tl_me, te + 14);
       sts_row64(b1, w);
       warp_publish_smem(bar_of(slot, B_READY), lane);
+      NERFCA_TL(tl_me, te + 15);
       // ---- step C: dZ2 = dH2 * 1[H2 > 0] -> the hand-off ring (L2)
       mbar_wait(bar_of(slot, B_ACC), ph_acc); ph_acc ^= 1;
       tc_fence_after();
+      NERFCA_TL(tl_me, te + 20);
       ld_acc64(k_acc, va, vb);
       acc_release(acc_rel, lane);
+      NERFCA_TL(tl_me, te + 21);
       mbar_wait(bar_of(slot, B_LDH2), pj);
+      NERFCA_TL(tl_me, te + 22);
       masked_grad_pack64(va, vb, b2, w);
+      NERFCA_TL(tl_me, te + 23);
       mbar_wait(bar_of(slot, B_SLOT), pj);
+      NERFCA_TL(tl_me, te + 24);
       {
         uint8_t* dst = nt.handoff + (size_t)ring_slot * TILE_BYTES + k_rowoff;
         ring_slot += ring_step;
@@ -462,7 +510,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
 
   if (warp >= 20) {
     // ================= 4 X0 warps: thread = tile row; ONE X0 buffer serves both slots, tiles in the CTA's order =================
-    reg_dealloc<64>();
+    reg_dealloc<64>();       // (register budget: see the top role)
     const int row = (warp - 20) * 32 + lane;
     RowIn rin;
     {
@@ -479,7 +527,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
       warp_publish_smem(bar_of((int)(i & 1), B_X0), lane);
     }
   } else if (warp >= 16) {
-    reg_dealloc<56>();
+    reg_dealloc<64>();
     if (warp >= 18) {
       // ================= load warp of slot s =================
       const int s = warp - 18;
@@ -572,7 +620,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
     }
   } else {
     // ================= 2 x 8 epilogue warps: slot = warp / 8, thread = (row, column half) =================
-    reg_alloc<96>();
+    reg_alloc<88>();
     const int slot = warp >> 3, q = warp & 3, ch = (warp >> 2) & 1;
     const int row = q * 32 + lane;
     const long long n_s = (n_my + 1 - slot) / 2;

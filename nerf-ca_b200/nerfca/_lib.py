@@ -83,7 +83,7 @@ KERNEL_FAMILY_NAMES = {K_RAYS: "rays", K_PACK: "pack_params", K_FIELD_FWD: "fiel
 
 
 
-LIB_NAME = "libnerfca_b200.so"
+LIB_NAME = os.environ.get("NERFCA_LIB", "libnerfca_b200.so")      # developer aid: NERFCA_LIB=libnerfca_b200_tl.so (make TL=1) prints which bounded wait gave up
 LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), LIB_NAME)
 
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
