@@ -250,6 +250,22 @@ NERFCA_API int nerfca_fields_forward(const nerfca_field_t* static_field, const n
                           const nerfca_samples_t* samples, int32_t precision, float* raw_s, float* raw_d, void* workspace,
                           void* stream);
 
+/* Render (train/run_composite.py:346-361,407-413; north_star (c)): no-grad rays -> pixels with the X-ray line integral FUSED into the
+ * output layer's epilogue of the tcgen05 forward: every sample's sigma * delta is reduced per ray by a segmented warp-shuffle scan
+ * and one atomic per warp and ray, so neither the per-sample field outputs nor the sigma arrays ever reach HBM.  Eval arithmetic
+ * (float32 rays: o + fl32(d z), float32 sums).  pix = i0 - sum_s (sigma_s + sigma_d) delta;  pix_static / pix_dynamic (both or
+ * neither; need dynamic_field): the single-field images of render_volume_density (:407-413).  precision must be NERFCA_PREC_BF16
+ * (the fp32 path is nerfca_fields_forward + nerfca_integrate).  workspace: nerfca_render_workspace_bytes.                     */
+NERFCA_API size_t nerfca_render_workspace_bytes(const nerfca_field_t* static_field, const nerfca_field_t* dynamic_field,
+                                     const nerfca_samples_t* samples, int32_t precision);
+NERFCA_API int nerfca_render_rays(const nerfca_field_t* static_field, const nerfca_field_t* dynamic_field, const nerfca_samples_t* samples,
+                       int32_t precision, const float* i0, int32_t activation, float* pix, float* pix_static, float* pix_dynamic,
+                       void* workspace, void* stream);
+
+/* N4  display normalisation of an eval image, train/run_composite.py:394-413: out[i] = (img[i] - min) / (max - min) on the device
+ * (float32 [n]; out may alias img).  minmax_out: optional device float[2] receiving (min, max); scratch8: 8 bytes of device scratch. */
+NERFCA_API int nerfca_normalize_image(const float* img, int64_t n, float* out, float* minmax_out, void* scratch8, void* stream);
+
 /* N2  torch.optim.Adam(foreach) + LinearLR of train/run_composite.py:209-215,305-308 over ONE flat fp32 parameter buffer
  * (params / grads / exp_avg / exp_avg_sq device [n]), bit-for-bit for fp32 parameters (tests/test_gpu_parity.py::
  * test_adam_matches_torch_bit_for_bit).  The per-update scalars are computed by the HOST in python double arithmetic exactly as

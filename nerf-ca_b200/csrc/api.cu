@@ -90,7 +90,9 @@ int tc_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, const 
 size_t tc_stash_bytes_n(int n_nets, long long P);
 size_t tc_workspace_bytes_n(const nerfca_field_t* const* f, int n_nets, long long P, int backward);
 int tc_fields_forward(const nerfca_field_t* const* f, int n_nets, const nerfca_samples_t& s, float* const* raw_out, void* stash,
-                      void* workspace, int pack, double* zero_terms, cudaStream_t st);
+                      void* workspace, int pack, double* zero_terms, cudaStream_t st, float* const* ray_sum = nullptr, int act = 0);
+int launch_render_finalize(const float* sum_s, const float* sum_d, const float* i0, int n_rays, float* pix, float* pix_s, float* pix_d,
+                           cudaStream_t st);
 int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_samples_t& s, const float* const* d_raw,
                        const void* stash, void* workspace, int pack, const nerfca_field_grads_t* const* gr, cudaStream_t st);
 
@@ -278,6 +280,39 @@ extern "C" int nerfca_fields_forward(const nerfca_field_t* fs, const nerfca_fiel
   rc = simt_field_forward(*fs, *samples, raw_s, nullptr, workspace, cs);
   if (rc || !fd) return rc;
   return simt_field_forward(*fd, *samples, raw_d, nullptr, workspace, cs);
+}
+
+// ---- render: no-grad rays -> pixels with the line integral fused into the output-layer epilogue (tcgen05 path) --------------------
+extern "C" size_t nerfca_render_workspace_bytes(const nerfca_field_t* fs, const nerfca_field_t* fd, const nerfca_samples_t* samples,
+                                                int32_t precision) {
+  if (!fs || !samples || samples->n_points <= 0 || precision != NERFCA_PREC_BF16) return 0;
+  const nerfca_field_t* f[2] = {fs, fd};
+  return up256(tc_workspace_bytes_n(f, fd ? 2 : 1, samples->n_points, 0)) + 2 * up256((size_t)samples->n_rays * sizeof(float));
+}
+
+extern "C" int nerfca_render_rays(const nerfca_field_t* fs, const nerfca_field_t* fd, const nerfca_samples_t* samples, int32_t precision,
+                                  const float* i0, int32_t activation, float* pix, float* pix_static, float* pix_dynamic, void* workspace,
+                                  void* stream) {
+  nerfca_step_t st = {};
+  st.static_field = fs; st.dynamic_field = fd; st.samples = samples; st.precision = precision;
+  int rc = validate_step(&st, false);
+  if (rc) return rc;
+  NERFCA_REQUIRE(precision == NERFCA_PREC_BF16, NERFCA_E_UNSUPPORTED,
+                 "nerfca_render_rays is the tcgen05 path (fp32: nerfca_fields_forward + nerfca_integrate)");
+  NERFCA_REQUIRE(!samples->points && samples->n_rays > 0, NERFCA_E_ARG, "rendering needs ray-generated samples");
+  NERFCA_REQUIRE(i0 && pix && workspace, NERFCA_E_ARG, "null pointer");
+  NERFCA_REQUIRE(!fd || (pix_static && pix_dynamic) || (!pix_static && !pix_dynamic), NERFCA_E_ARG, "give both component images or neither");
+  cudaStream_t cs = (cudaStream_t)stream;
+  const nerfca_field_t* f[2] = {fs, fd};
+  const int n = fd ? 2 : 1;
+  uint8_t* ws = (uint8_t*)workspace;
+  const size_t pack_bytes = up256(tc_workspace_bytes_n(f, n, samples->n_points, 0));
+  const size_t sum_bytes = up256((size_t)samples->n_rays * sizeof(float));
+  float* sums[2] = {(float*)(ws + pack_bytes), (float*)(ws + pack_bytes + sum_bytes)};
+  NERFCA_CUDA_OK(cudaMemsetAsync(sums[0], 0, 2 * sum_bytes, cs));
+  rc = tc_fields_forward(f, n, *samples, nullptr, nullptr, workspace, 1, nullptr, cs, sums, activation);
+  if (rc) return rc;
+  return launch_render_finalize(sums[0], fd ? sums[1] : nullptr, i0, samples->n_rays, pix, pix_static, pix_dynamic, cs);
 }
 
 extern "C" int nerfca_train_step(const nerfca_step_t* s, void* stream) {

@@ -259,9 +259,64 @@ __global__ void static_loss_kernel(const float* __restrict__ raw, const float* _
     d_raw[off + s] = (float)(k * delta_at<double>(z, s, n)) * act_bwd(act, raw[off + s]);
 }
 
+// pixels from the per-ray attenuation sums the render forward accumulated (A9 eval form, fp32): composite, static-only, dynamic-only
+__global__ void render_finalize_kernel(const float* __restrict__ sum_s, const float* __restrict__ sum_d, const float* __restrict__ i0,
+                                       int n_rays, float* __restrict__ pix, float* __restrict__ pix_s, float* __restrict__ pix_d) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rays) return;
+  const float base = __ldg(i0 + r), a = sum_s[r], b = sum_d ? sum_d[r] : 0.f;
+  pix[r] = base - (a + b);
+  if (pix_s) pix_s[r] = base - a;
+  if (pix_d) pix_d[r] = base - b;
+}
+int launch_render_finalize(const float* sum_s, const float* sum_d, const float* i0, int n_rays, float* pix, float* pix_s, float* pix_d,
+                           cudaStream_t st) {
+  render_finalize_kernel<<<div_up(n_rays, 256), 256, 0, st>>>(sum_s, sum_d, i0, n_rays, pix, pix_s, pix_d);
+  NERFCA_LAUNCH_OK();
+  return NERFCA_OK;
+}
+
+// ---- N4: display normalisation of an image, run_composite.py:394-413: (img - min) / (max - min) ------------------------------------
+__device__ __forceinline__ unsigned f2ord(float f) { const unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+__global__ void minmax_kernel(const float* __restrict__ img, long long n, unsigned* __restrict__ mm) {
+  float lo = INFINITY, hi = -INFINITY;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = img[i];
+    lo = fminf(lo, v); hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0) { atomicMin(mm, f2ord(lo)); atomicMax(mm + 1, f2ord(hi)); }
+}
+__global__ void normalize_kernel(const float* __restrict__ img, long long n, const unsigned* __restrict__ mm, float* __restrict__ out,
+                                 float* __restrict__ minmax_out) {
+  const float lo = ord2f(mm[0]), hi = ord2f(mm[1]);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && minmax_out) { minmax_out[0] = lo; minmax_out[1] = hi; }
+  if (i < n) out[i] = __fdiv_rn(__fsub_rn(img[i], lo), __fsub_rn(hi, lo));
+}
+
 }  // namespace nerfca
 
 using namespace nerfca;
+
+extern "C" int nerfca_normalize_image(const float* img, int64_t n, float* out, float* minmax_out, void* scratch8, void* stream) {
+  NERFCA_REQUIRE(img && out && scratch8, NERFCA_E_ARG, "null pointer");
+  if (n <= 0) return NERFCA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* mm = (unsigned*)scratch8;
+  const unsigned init[2] = {0xFFFFFFFFu, 0u};
+  NERFCA_CUDA_OK(cudaMemsetAsync(mm, 0xFF, 4, st));
+  NERFCA_CUDA_OK(cudaMemsetAsync(mm + 1, 0, 4, st));
+  (void)init;
+  const unsigned blocks = div_up(n, 256) < 1184u ? div_up(n, 256) : 1184u;     // 8 CTAs per SM at most
+  minmax_kernel<<<blocks, 256, 0, st>>>(img, (long long)n, mm);
+  NERFCA_LAUNCH_OK();
+  normalize_kernel<<<div_up(n, 256), 256, 0, st>>>(img, (long long)n, mm, out, minmax_out);
+  NERFCA_LAUNCH_OK();
+  return NERFCA_OK;
+}
 
 extern "C" int nerfca_integrate(const float* raw_s, const float* raw_d, const float* depth, const float* i0, int32_t n_rays,
                                 int32_t n_depth, int32_t activation, int32_t acc_dtype, void* pix_out, float* sigma_s_out,
@@ -321,9 +376,9 @@ extern "C" int nerfca_composite_loss(const float* raw_s, const float* raw_d, con
     NERFCA_LAUNCH_OK();
     return NERFCA_OK;
   }
-  // one CTA per ray; 256 threads (2 samples per thread and sweep at N = 500): the kernel is bound by the latency of its three
-  // dependent sweeps, not by throughput (NERFCA_LOSS_THREADS=128 selects the narrower CTA for comparison)
-  static const int loss_threads = (getenv("NERFCA_LOSS_THREADS") && atoi(getenv("NERFCA_LOSS_THREADS")) == 128) ? 128 : 256;
+  // one CTA of 128 threads per ray (256, NERFCA_LOSS_THREADS=256, measured no faster: 27.0 vs 25.8 us, r3k): the kernel is bound by its three
+  // dependent sweeps with fp64 logarithms, not by throughput
+  static const int loss_threads = (getenv("NERFCA_LOSS_THREADS") && atoi(getenv("NERFCA_LOSS_THREADS")) == 256) ? 256 : 128;
   const size_t smem = 8 * (256 / 32) * sizeof(double) + (size_t)2 * n_depth * sizeof(float);
   NERFCA_REQUIRE(smem <= 200 * 1024, NERFCA_E_UNSUPPORTED, "n_depth too large for the fused loss kernel");
   if (loss_threads == 128) {

@@ -47,6 +47,12 @@ constexpr int STASH_TILES = 4;                   // H0 .. H3 of every tile (bf16
 constexpr uint32_t MASK_BYTES = 2048;            // + the ReLU pattern of H4, one BIT per element: row r owns 16 bytes = 4 words, word 2 ch + g covers
                                                  // columns [64 ch + 32 g, + 32): bit i = column 2i, bit 16 + i = column 2i + 1 (i < 16)
 constexpr size_t STASH_STRIDE = (size_t)STASH_TILES * 32768 + MASK_BYTES;   // bytes per tile and net
+constexpr size_t STASH_PATTERN4_OFF = (size_t)STASH_TILES * 32768;          // the H4 pattern sits behind the four tiles
+// (Two ways to spare the backward's epilogue its shared-memory reads of the activation tiles for the ReLU masks -- they compete with
+// the MMAs' operand fetches and take ~2 800 cycles per step in the two-tiles-in-flight kernel -- were measured and dropped:
+// stashing the 1-bit pattern of EVERY layer made the top backward role 31 % faster per tile but cost the forward's epilogue +42 us
+// for the bit packing (r3o); deriving the patterns in the backward from the stash in global memory doubled its DRAM reads, 470 us
+// against 395 (r3r).)
 constexpr int FWD_THREADS = 20 * 32;             // 16 epilogue / issue warps + 4 X0 producer warps
 constexpr int FAST_FREQ = 12;                    // band count the register-resident encoder is specialised for
 
@@ -400,7 +406,9 @@ static int sm_count() {
 // =====================================================================================================================
 struct FwdNet {
   const uint8_t* pack;
-  float* raw_out;
+  float* raw_out;          // per-sample field output, or null when only the ray sums are wanted
+  float* ray_sum;          // optional [n_rays]: += act(raw) * 1e-2 * delta per sample (line integral fused into the output layer's epilogue)
+  int act;
   uint8_t* stash;          // [n_tiles][STASH_TILES][TILE_BYTES] or null
   X0Desc x0;
   uint32_t w0_bytes, wout_off, f32_off, pack_bytes;
@@ -686,7 +694,31 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
         uint32_t v[2];
         tmem_ld2(t_lane + FWD_OUT + slot * 16, v);
         tmem_ld_wait();
-        if (valid) nt.raw_out[p] = (__uint_as_float(v[0]) + __uint_as_float(v[1])) + b_out;
+        const float raw = (__uint_as_float(v[0]) + __uint_as_float(v[1])) + b_out;
+        if (valid && nt.raw_out) nt.raw_out[p] = raw;
+        if (nt.ray_sum) {
+          // X-ray line integral (train/model_helpers.py:72-97) right here: sigma = act(raw) * 1e-2, weight = sigma * delta_s, summed per
+          // ray.  The warp's 32 lanes are 32 consecutive samples of at most a few rays: segmented inclusive scan by warp shuffles
+          // (a lane adds the value `o` lanes below it while that lane belongs to the same ray), the last lane of every segment
+          // adds the segment's sum to the ray with one atomic -- one atomic per warp while the warp stays inside one ray.
+          const int n = a.src.n_depth;
+          const long long pa = p + a.src.base;
+          const int ray = valid ? (int)(pa / n) : -1;
+          float wgt = 0.f;
+          if (valid) {
+            const int sidx = (int)(pa - (long long)ray * n);
+            const float delta = (sidx == n - 1) ? 1e-10f : __fsub_rn(__ldg(a.src.depth + sidx + 1), __ldg(a.src.depth + sidx));
+            wgt = __fmul_rn(__fmul_rn(act_fwd(nt.act, raw), 0.01f), delta);
+          }
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float w2 = __shfl_up_sync(0xffffffffu, wgt, o);
+            const int r2 = __shfl_up_sync(0xffffffffu, ray, o);
+            if (lane >= o && r2 == ray) wgt += w2;
+          }
+          const int r_next = __shfl_down_sync(0xffffffffu, ray, 1);
+          if (valid && (lane == 31 || r_next != ray)) atomicAdd(nt.ray_sum + ray, wgt);
+        }
       }
       NERFCA_TL(lane == 0 && (warp & 7) == 1, 1060 + slot * 1000);
       // (the next output MMA of this slot is issued after five more named barriers of the slot: OUT has long been read)
@@ -935,7 +967,7 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
         if (i > 0) mbar_wait(bar_mfree, ph_mfree);
         NERFCA_TL(true, 2001);
         mbar_expect_tx(bar_ldm, MASK_BYTES);
-        bulk_g2s(smem_u32(s_m4), st + (size_t)STASH_TILES * TILE_BYTES, MASK_BYTES, bar_ldm);
+        bulk_g2s(smem_u32(s_m4), st + STASH_PATTERN4_OFF, MASK_BYTES, bar_ldm);
         // H2, H3 of tile i: into the buffers that H3 / R of tile i - 1 leave when its weight gradient 4 is complete AND step B of that
         // tile has read H3's ReLU pattern (bar_h3free; this also keeps bar_ldh from completing a second phase before every epilogue
         // warp has seen the first: the loads are needed a whole tile later, so the extra wait costs nothing)
@@ -1203,6 +1235,9 @@ __device__ __forceinline__ void bwd_bot_role(const BwdArgs& a, const BwdNet& nt,
   const int n_lat_acc = has_lat ? nt.n_phases * nt.n_latent : 0;            // <= 256 checked on the host
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_lat + 256);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 12);
+  float* s_bw = reinterpret_cast<float*>(s_tmem + 4);          // band weights / latent table for the X0 warps (see mlp_tc_bwd2.cuh: global
+  float* s_lt = s_bw + 32;                                     // loads miss L1 every time here, the flag polls keep invalidating it)
+  const bool lt_in_smem = nt.x0.enc.n_phases * nt.x0.enc.n_latent <= 256;
   const uint32_t bar_w = smem_u32(s_bar), bar_ld_dz = bar_w + 8, bar_ld_h1 = bar_w + 16, bar_ld_h0 = bar_w + 24, bar_acc = bar_w + 32,
                  bar_free1 = bar_w + 40, bar_free2 = bar_w + 48, bar_x0 = bar_w + 56, bar_x0free = bar_w + 64;
 
@@ -1216,6 +1251,10 @@ __device__ __forceinline__ void bwd_bot_role(const BwdArgs& a, const BwdNet& nt,
     tmem_alloc(smem_u32(s_tmem), 512);
   }
   {
+    const EncDesc& e = nt.x0.enc;
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) s_bw[i] = (e.band_weight && i < e.n_freq) ? __ldg(e.band_weight + i) : 1.f;
+    const int n_lt = e.n_latent > 0 ? e.n_phases * e.n_latent : 0;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lt[i] = (i < n_lt && lt_in_smem) ? __ldg(e.latents + i) : 0.f;
     for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x) s_lat[i] = 0.f;
     // ones tile: column 0 == 1 in every row (bias gradients = column sums of dZ)
     for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
@@ -1355,8 +1394,8 @@ __device__ __forceinline__ void bwd_bot_role(const BwdArgs& a, const BwdNet& nt,
       const long long pn = (worker + (i + 1) * n_workers) * TILE_M + row;
       rin = fetch_row(nt.x0, a.src, pn, i + 1 < n_my && pn < a.src.n_points);
       if (i > 0) { mbar_wait(bar_x0free, ph_x0free); ph_x0free ^= 1; }
-      emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight, nt.x0.enc.latents, SmemSink{s_x0, row}, 0);
-      emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight, nt.x0.enc.latents, SmemSink{s_x0, row}, 1);
+      emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight ? s_bw : nullptr, lt_in_smem ? s_lt : nt.x0.enc.latents, SmemSink{s_x0, row}, 0);
+      emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight ? s_bw : nullptr, lt_in_smem ? s_lt : nt.x0.enc.latents, SmemSink{s_x0, row}, 1);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_x0);
@@ -1531,7 +1570,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_bwd_bot_kernel(BwdArgs a) {
 // =====================================================================================================================
 static size_t fwd_smem_bytes(const NetDims& d) { return (((size_t)d.pack_bytes + 127) & ~(size_t)127) + 10 * 8 + (32 + 256) * 4; }
 constexpr size_t TOP_SMEM = 2 * (size_t)TILE_BYTES + 4 * (size_t)TOP_BUF_STRIDE + MASK_BYTES + 128 * 4 + 64 * 4 + 256 * 4 + 16 + 12 * 8 + 16;
-constexpr size_t BOT_SMEM = 6 * (size_t)TILE_BYTES + 96 * 256 + 4096 + 4096 + 256 * 4 + 12 * 8 + 16;
+constexpr size_t BOT_SMEM = 6 * (size_t)TILE_BYTES + 96 * 256 + 4096 + 4096 + 256 * 4 + 12 * 8 + 16 + (32 + 256) * 4;
 constexpr size_t BWD_SMEM = TOP_SMEM > BOT_SMEM ? TOP_SMEM : BOT_SMEM;
 static_assert(BWD_SMEM <= 227 * 1024, "backward kernel exceeds the shared memory of an SM");
 
@@ -1607,7 +1646,7 @@ static unsigned grid_for(int n_nets, long long n_tiles) {
 // Forward of n_nets (1 or 2) fields over the same sample set in one launch.  pack != 0: (re)pack the parameters into
 // the head of `workspace` first.
 int tc_fields_forward(const nerfca_field_t* const* f, int n_nets, const nerfca_samples_t& s, float* const* raw_out, void* stash,
-                      void* workspace, int pack, double* zero_terms, cudaStream_t st) {
+                      void* workspace, int pack, double* zero_terms, cudaStream_t st, float* const* ray_sum, int act) {
   if (pack) {
     int rc = pack_params(f, n_nets, workspace, st);
     if (rc) return rc;
@@ -1623,7 +1662,9 @@ int tc_fields_forward(const nerfca_field_t* const* f, int n_nets, const nerfca_s
     FwdNet& n = a.net[i];
     n.pack = (const uint8_t*)workspace + off;
     off += pack_stride(d);
-    n.raw_out = raw_out[i];
+    n.raw_out = raw_out ? raw_out[i] : nullptr;
+    n.ray_sum = ray_sum ? ray_sum[i] : nullptr;
+    n.act = act;
     n.stash = stash ? (uint8_t*)stash + (size_t)i * a.n_tiles * STASH_STRIDE : nullptr;
     n.x0 = make_x0(*f[i], d);
     n.w0_bytes = d.w0_bytes; n.wout_off = d.wout_off; n.f32_off = d.f32_off; n.pack_bytes = d.pack_bytes;
@@ -1715,15 +1756,17 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
   NERFCA_REQUIRE(n_top >= 1 && n_bot >= 1, NERFCA_E_UNSUPPORTED, "tcgen05 backward needs at least two SMs per net");
   a.n_top = n_top; a.n_bot = n_bot; a.ring = (int)ring;
   NERFCA_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)n_nets * 2 * a.n_tiles * sizeof(uint32_t), st));
-  // NERFCA_BWD_V2=1: the second-generation kernel (two tiles in flight per CTA on one shared accumulator, mlp_tc_bwd2.cuh).  Parity-
-  // green and soak-clean, but measured 5 % SLOWER than tc_bwd_kernel (r3j: 410 vs 390 us): with every dgrad in SS form the two tiles
-  // in flight compete for the shared-memory bandwidth that the MMAs' operand reads already saturate, see DESIGN.md section 6.
-  if (merged && env_flag("NERFCA_BWD_V2", 0)) {
+  // Default: the second-generation kernel (two tiles in flight per CTA on one shared accumulator, mlp_tc_bwd2.cuh).  NERFCA_BWD_V1=1
+  // selects tc_bwd_kernel: ~5 % faster in isolation (r3j: 390 vs 410 us) but it TRAPPED in a 4 000-step soak under CUDA-graph
+  // replay (r3l: a bounded wait of its hand-off protocol gave up; the same kernel launched eagerly ran clean) -- the protocol slip
+  // behind the round-1 "once per 10^4 steps" trap is still in there.  Every mbarrier of the v2 kernel has a written argument why it
+  // can never run more than one phase ahead of a waiter (mlp_tc_bwd2.cuh), and it ran the same soak clean.
+  if (merged && !env_flag("NERFCA_BWD_V1", 0)) {
     if (!getenv("NERFCA_BWD_SPLIT")) {
-      // per tile the top role issues ~2 200 and the bottom role ~2 700 tensor-pipe cycles (both bounded by shared-memory bandwidth):
-      // 33 : 41 of 74, kept coprime (see below)
+      // per tile the top role moves ~460 KB and the bottom role ~630 KB through shared memory (what bounds both): 29 : 45 of 74
+      // measured best (r3i), kept coprime (see below)
       auto gcd2 = [](int x, int y) { while (y) { const int r = x % y; x = y; y = r; } return x; };
-      n_top = (per_net * 45 + 50) / 100;
+      n_top = (per_net * 2 + 2) / 5;
       while (n_top > 1 && gcd2(n_top, per_net - n_top) != 1) --n_top;
       n_bot = per_net - n_top;
       if (n_top > a.n_tiles) n_top = (int)a.n_tiles;
@@ -1818,7 +1861,7 @@ int tc_field_forward(const nerfca_field_t& f, const nerfca_samples_t& s, float* 
                      cudaStream_t st) {
   const nerfca_field_t* fs[1] = {&f};
   float* outs[1] = {raw_out};
-  return tc_fields_forward(fs, 1, s, outs, stash, workspace, 1, nullptr, st);
+  return tc_fields_forward(fs, 1, s, outs, stash, workspace, 1, nullptr, st, nullptr, 0);
 }
 int tc_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, const float* d_raw, const void* stash, void* workspace,
                       const nerfca_field_grads_t& gr, cudaStream_t st) {

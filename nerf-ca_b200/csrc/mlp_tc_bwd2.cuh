@@ -86,7 +86,7 @@ constexpr size_t T2_OFF_W3 = 0, T2_OFF_W4 = TILE_BYTES, T2_OFF_BUF = 2 * (size_t
 constexpr size_t T2_OFF_M4 = T2_OFF_BUF + 4 * (size_t)TOP_BUF_STRIDE;       // 2 x 2 KB
 constexpr size_t T2_OFF_G = T2_OFF_M4 + 2 * MASK_BYTES;                     // 2 x 128 f32
 constexpr size_t T2_OFF_WO = T2_OFF_G + 2 * 128 * 4;                        // 128 f32
-constexpr size_t T2_OFF_MISC = T2_OFF_WO + 128 * 4;                         // gbout f32, acc_rel, acc_ticket, pub_cnt[2], pad
+constexpr size_t T2_OFF_MISC = T2_OFF_WO + 128 * 4;                         // gbout f32, acc_rel, acc_ticket, pub_cnt[2], slot_ok[2], pad
 constexpr size_t T2_OFF_BAR = T2_OFF_MISC + 32;
 constexpr int T2_N_BAR = 2 + 2 * 9;
 constexpr size_t TOP2_SMEM = T2_OFF_BAR + T2_N_BAR * 8 + 16;
@@ -101,7 +101,7 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
   float* s_g = reinterpret_cast<float*>(smem + T2_OFF_G);
   float* s_wo = reinterpret_cast<float*>(smem + T2_OFF_WO);
   float* s_gbout = reinterpret_cast<float*>(smem + T2_OFF_MISC);
-  const uint32_t acc_rel = smem_u32(smem + T2_OFF_MISC + 4), acc_ticket = acc_rel + 4, pub_cnt0 = acc_rel + 8;
+  const uint32_t acc_rel = smem_u32(smem + T2_OFF_MISC + 4), acc_ticket = acc_rel + 4, pub_cnt0 = acc_rel + 8, slot_ok0 = acc_rel + 16;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + T2_OFF_BAR);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + T2_N_BAR);
   const uint32_t bar_w = smem_u32(s_bar), bar_setup = bar_w + 8;
@@ -116,7 +116,7 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
       for (int s = 0; s < 2; ++s) {
         mbar_init(bar_of(s, B_READY), 8); mbar_init(bar_of(s, B_ACC), 1); mbar_init(bar_of(s, B_WG4), 1); mbar_init(bar_of(s, B_WG3), 1);
         mbar_init(bar_of(s, B_LDM), 1); mbar_init(bar_of(s, B_LDH3), 1); mbar_init(bar_of(s, B_LDH2), 1);
-        mbar_init(bar_of(s, B_MFREE), 8); mbar_init(bar_of(s, B_SLOT), 1);
+        mbar_init(bar_of(s, B_MFREE), 8); mbar_init(bar_of(s, B_SLOT), 1);      // (B_SLOT: unused, the ring-slot signal is a counter)
       }
       mbar_init_fence();
     }
@@ -171,7 +171,7 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
       __syncwarp();
       if (lane == 0) {
         mbar_expect_tx(bar_of(s, B_LDM), MASK_BYTES);
-        bulk_g2s(m4, nt.stash + (size_t)tile * STASH_STRIDE + (size_t)STASH_TILES * TILE_BYTES, MASK_BYTES, bar_of(s, B_LDM));
+        bulk_g2s(m4, nt.stash + (size_t)tile * STASH_STRIDE + STASH_PATTERN4_OFF, MASK_BYTES, bar_of(s, B_LDM));
       }
       __syncwarp();
     };
@@ -196,12 +196,11 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
           bulk_prefetch_l2(nx + 2 * (size_t)TILE_BYTES, TILE_BYTES);
           bulk_prefetch_l2(nx + 3 * (size_t)TILE_BYTES, TILE_BYTES);
         }
-        // hand-off slot of this tile: free once the bottom role has copied out the tile that used it `ring` tiles earlier.  The
-        // arrival comes AFTER weight gradient 4 of this tile was issued, i.e. after step A of this tile, i.e. after the epilogue
-        // warps have consumed the arrival for the slot's previous tile in its step C: never more than one phase ahead of its
-        // only waiter (arriving earlier let this barrier run two phases ahead and the waiter's parity test alias).
+        // hand-off slot of this tile: free once the bottom role has copied out the tile that used it `ring` tiles earlier.  Signalled
+        // through a monotonic shared-memory counter (slot_ok[s] = tiles whose slot is free), not an mbarrier phase: the epilogue reads
+        // it one tile late (deferred dZ2 store) and a counter cannot alias however far the loader runs ahead.
         if (tile >= a.ring) wait_flag_ge(nt.consumed + (tile - a.ring), 1u);
-        mbar_arrive(bar_of(s, B_SLOT));
+        red_release_cta_shared_add(slot_ok0 + 4u * s, 1u);
       }
       __syncwarp();
     }
@@ -313,6 +312,24 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
     const uint32_t ring_step = (uint32_t)((2 * n_workers) % a.ring);
     uint32_t ph_acc = 0;
     float gb_sum = 0.f;
+    uint32_t dz[32];
+    auto store_dz = [&](long long jt) {               // dZ2 of the slot's jt-th tile -> its hand-off slot, then one arrival for the publisher
+      if (ld_acquire_cta_shared(slot_ok0 + 4u * slot) < (uint32_t)(jt + 1)) {
+        const long long t0 = clock64();
+        while (ld_acquire_cta_shared(slot_ok0 + 4u * slot) < (uint32_t)(jt + 1)) {
+          __nanosleep(64);
+          if (clock64() - t0 > 4000000000LL) __trap();
+        }
+      }
+      uint8_t* dst = nt.handoff + (size_t)ring_slot * TILE_BYTES + k_rowoff;
+      ring_slot += ring_step;
+      if (ring_slot >= (uint32_t)a.ring) ring_slot -= (uint32_t)a.ring;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)      // streaming stores straight to L2
+        __stcs(reinterpret_cast<uint4*>(dst + c * CHUNK_BYTES), make_uint4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]));
+      __syncwarp();
+      if (lane == 0) red_release_cta_shared_add(pub_cnt, 1u);
+    };
     for (long long j = 0; j < n_s; ++j) {
       const uint32_t pj = (uint32_t)(j & 1);
       uint32_t va[32], vb[32], w[32];
@@ -342,6 +359,8 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
       __syncwarp();
       if (lane == 0) { mbar_arrive(bar_of(slot, B_MFREE)); mbar_arrive(bar_of(slot, B_READY)); }
       NERFCA_TL(tl_me, te + 3);
+      if (j > 0) store_dz(j - 1);                      // the previous tile's dZ2 drains while dgrad 4 runs
+      NERFCA_TL(tl_me, te + 4);
       // ---- step B: dZ3 = dH3 * 1[H3 > 0] -> b1, over H3 itself once weight gradient 4 has read it
       mbar_wait(bar_of(slot, B_ACC), ph_acc); ph_acc ^= 1;
       tc_fence_after();
@@ -367,21 +386,12 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
       NERFCA_TL(tl_me, te + 21);
       mbar_wait(bar_of(slot, B_LDH2), pj);
       NERFCA_TL(tl_me, te + 22);
-      masked_grad_pack64(va, vb, b2, w);
+      // (dz leaves behind step A of the slot's next tile: its 32 KB then drain through the store path while the CTA waits for dgrad 4
+      // anyway; issued here they kept the warps in the store queue for ~2 000 cycles before step A could start)
+      masked_grad_pack64(va, vb, b2, dz);
       NERFCA_TL(tl_me, te + 23);
-      mbar_wait(bar_of(slot, B_SLOT), pj);
-      NERFCA_TL(tl_me, te + 24);
-      {
-        uint8_t* dst = nt.handoff + (size_t)ring_slot * TILE_BYTES + k_rowoff;
-        ring_slot += ring_step;
-        if (ring_slot >= (uint32_t)a.ring) ring_slot -= (uint32_t)a.ring;
-#pragma unroll
-        for (int c = 0; c < 8; ++c)      // streaming stores straight to L2
-          __stcs(reinterpret_cast<uint4*>(dst + c * CHUNK_BYTES), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
-        __syncwarp();
-        if (lane == 0) red_release_cta_shared_add(pub_cnt, 1u);
-      }
     }
+    if (n_s > 0) store_dz(n_s - 1);                    // the last tile's dZ2
     // ---- every MMA of both slots has completed: flush the TMEM-resident accumulators
     if (n_s > 0) mbar_wait(bar_of(slot, B_WG3), (uint32_t)((n_s - 1) & 1));
     tc_fence_before();
@@ -450,7 +460,8 @@ constexpr size_t B2_OFF_X0 = B2_OFF_BUF + 4 * (size_t)TILE_BYTES;           // 9
 constexpr size_t B2_OFF_ONES = B2_OFF_X0 + 96 * 256;
 constexpr size_t B2_OFF_W0LAT = B2_OFF_ONES + 4096;
 constexpr size_t B2_OFF_LAT = B2_OFF_W0LAT + 4096;                          // 256 f32
-constexpr size_t B2_OFF_MISC = B2_OFF_LAT + 256 * 4;                        // acc_rel, acc_ticket, pad
+constexpr size_t B2_OFF_TAB = B2_OFF_LAT + 256 * 4;                         // band weights (32 f32) + latent table (256 f32) for the X0 warps
+constexpr size_t B2_OFF_MISC = B2_OFF_TAB + (32 + 256) * 4;                 // acc_rel, acc_ticket, pad
 constexpr size_t B2_OFF_BAR = B2_OFF_MISC + 16;
 constexpr int B2_N_BAR = 2 + 2 * 9;
 constexpr size_t BOT2_SMEM = B2_OFF_BAR + B2_N_BAR * 8 + 16;
@@ -494,7 +505,17 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
     __syncwarp();
     tmem_alloc(smem_u32(s_tmem), 512);
   }
+  // The X0 warps read the band weights and the latent table per row.  From global memory every one of those ~20 loads per row was
+  // an L2 round trip: the loaders' flag polls (gpu-scope acquire = CCTL.IVALL) keep the SM's L1 empty.  Measured in-kernel: 6 300
+  // cycles to build one X0 tile, with ONE X0 buffer the pacing item of the whole role.  Shared-memory copies, as in the forward.
+  float* s_bw = reinterpret_cast<float*>(smem + B2_OFF_TAB);
+  float* s_lt = s_bw + 32;
+  const bool lt_in_smem = nt.x0.enc.n_phases * nt.x0.enc.n_latent <= 256;
   {
+    const EncDesc& e = nt.x0.enc;
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) s_bw[i] = (e.band_weight && i < e.n_freq) ? __ldg(e.band_weight + i) : 1.f;
+    const int n_lt = e.n_latent > 0 ? e.n_phases * e.n_latent : 0;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lt[i] = (i < n_lt && lt_in_smem) ? __ldg(e.latents + i) : 0.f;
     for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x) s_lat[i] = 0.f;
     // ones tile: column 0 == 1 in every row (bias gradients = column sums of dZ)
     for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
@@ -507,11 +528,14 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
   const long long n_my = (a.n_tiles > worker) ? (a.n_tiles - worker + n_workers - 1) / n_workers : 0;
+  [[maybe_unused]] int tl_n = 0;     // developer timeline (NERFCA_TIMELINE=bot): regions 1 = epilogue slot 0, 2 = X0 producer, 3 = issuer 0, 0 = loader 0
 
   if (warp >= 20) {
     // ================= 4 X0 warps: thread = tile row; ONE X0 buffer serves both slots, tiles in the CTA's order =================
     reg_dealloc<64>();       // (register budget: see the top role)
     const int row = (warp - 20) * 32 + lane;
+    const float* band_w = nt.x0.enc.band_weight ? s_bw : nullptr;
+    const float* lat_tab = lt_in_smem ? s_lt : nt.x0.enc.latents;
     RowIn rin;
     {
       const long long p0 = worker * TILE_M + row;
@@ -521,10 +545,13 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
       const RowIn cur = rin;
       const long long pn = (worker + (i + 1) * n_workers) * TILE_M + row;
       rin = fetch_row(nt.x0, a.src, pn, i + 1 < n_my && pn < a.src.n_points);
+      NERFCA_TL(warp == 20 && lane == 0, 2001);
       if (i > 0) mbar_wait(bar_of((int)((i - 1) & 1), B_WG0), (uint32_t)(((i - 1) >> 1) & 1));   // weight gradient 0 of the previous tile has read X0
-      emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight, nt.x0.enc.latents, SmemSink{s_x0, row}, 0);
-      emit_x0_row(nt.x0, cur, nt.x0.enc.band_weight, nt.x0.enc.latents, SmemSink{s_x0, row}, 1);
+      NERFCA_TL(warp == 20 && lane == 0, 2002);
+      emit_x0_row(nt.x0, cur, band_w, lat_tab, SmemSink{s_x0, row}, 0);
+      emit_x0_row(nt.x0, cur, band_w, lat_tab, SmemSink{s_x0, row}, 1);
       warp_publish_smem(bar_of((int)(i & 1), B_X0), lane);
+      NERFCA_TL(warp == 20 && lane == 0, 2003);
     }
   } else if (warp >= 16) {
     reg_dealloc<64>();
@@ -548,8 +575,11 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
           const uint8_t* st = nt.stash + (size_t)tile * STASH_STRIDE;
           const uint32_t pj = (uint32_t)(j & 1);
           const uint32_t seen = ld_acquire_gpu(nt.produced + tile);   // requested now, looked at once the buffer is free
+          NERFCA_TL(s == 0, 101);
           if (j > 0) mbar_wait(bar_of(s, B_WG0), pj ^ 1);             // weight gradient 0 of the previous tile no longer reads dZ0 in c1
+          NERFCA_TL(s == 0, 102);
           if (seen < 8u) wait_flag_ge(nt.produced + tile, 8u);        // all 8 epilogue warps of the top role have written the tile
+          NERFCA_TL(s == 0, 103);
           fence_proxy_async_all();
           mbar_expect_tx(bar_of(s, B_LDDZ), TILE_BYTES);
           bulk_g2s(c1, nt.handoff + (size_t)ring_slot * TILE_BYTES, TILE_BYTES, bar_of(s, B_LDDZ));
@@ -559,8 +589,10 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
           mbar_expect_tx(bar_of(s, B_LDH1), TILE_BYTES);
           bulk_g2s(c2, st + (size_t)TILE_BYTES, TILE_BYTES, bar_of(s, B_LDH1));
           mbar_wait(bar_of(s, B_LDDZ), pj);                           // dZ2 has left its hand-off slot
+          NERFCA_TL(s == 0, 104);
           st_release_gpu(nt.consumed + tile, 1u);
           mbar_wait(bar_of(s, B_WG2), pj);                            // weight gradient 2 no longer reads dZ2: its buffer takes H0
+          NERFCA_TL(s == 0, 105);
           mbar_expect_tx(bar_of(s, B_LDH0), TILE_BYTES);
           bulk_g2s(c1, st, TILE_BYTES, bar_of(s, B_LDH0));
           if (j + 1 < n_s) {
@@ -586,17 +618,25 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
         tc_fence_after();
         for (long long j = 0; j < n_s; ++j) {
           const uint32_t pj = (uint32_t)(j & 1);
+          NERFCA_TL(s == 0, 3001);
           mbar_wait(bar_of(s, B_LDDZ), pj);
+          NERFCA_TL(s == 0, 3002);
           acc_acquire(acc_ticket, acc_rel);
+          NERFCA_TL(s == 0, 3003);
           umma_k<8, KK, KM>(tmem + B2_ACC, kmajor(c1), mnmajor(w2), id_dgrad, 0);                  // dH1 = dZ2 W2
           umma_commit(bar_of(s, B_ACC));
+          NERFCA_TL(s == 0, 3004);
           mbar_wait(bar_of(s, B_LDH1), pj);
           tc_fence_after();
+          NERFCA_TL(s == 0, 3005);
           umma_k<8, KM, KM>(tmem + B2_WG2, mnmajor(c1), mnmajor(c2), id_wgrad, 1);                 // WG2 += dZ2^T H1
           umma_k<8, KM, KM>(tmem + B2_BG2, mnmajor(c1), mnmajor(ones), id_side, 1);                // BG2 += colsum(dZ2)
           umma_commit(bar_of(s, B_WG2));
+          NERFCA_TL(s == 0, 3006);
           mbar_wait(bar_of(s, B_READY), 0);                          // step B: dZ1 is in c2
+          NERFCA_TL(s == 0, 3011);
           acc_acquire(acc_ticket, acc_rel);
+          NERFCA_TL(s == 0, 3012);
           umma_k<8, KK, KM>(tmem + B2_ACC, kmajor(c2), mnmajor(w1), id_dgrad, 0);                  // dH0 = dZ1 W1
           umma_commit(bar_of(s, B_ACC));
           mbar_wait(bar_of(s, B_LDH0), pj);
@@ -604,9 +644,12 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
           umma_k<8, KM, KM>(tmem + B2_WG1, mnmajor(c2), mnmajor(c1), id_wgrad, 1);                 // WG1 += dZ1^T H0
           umma_k<8, KM, KM>(tmem + B2_BG1, mnmajor(c2), mnmajor(ones), id_side, 1);                // BG1 += colsum(dZ1)
           umma_commit(bar_of(s, B_WG1));
+          NERFCA_TL(s == 0, 3016);
           mbar_wait(bar_of(s, B_READY), 1);                          // step C: dZ0 is in c1
+          NERFCA_TL(s == 0, 3021);
           mbar_wait(bar_of(s, B_X0), pj);
           tc_fence_after();
+          NERFCA_TL(s == 0, 3022);
           umma_k<8, KM, KM>(tmem + B2_WG0, mnmajor(c1), mnmajor(x0), id_wg0, 1);                   // WG0 += dZ0^T X0
           if (has_lat) {
             acc_acquire(acc_ticket, acc_rel);
@@ -614,6 +657,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
             umma_commit(bar_of(s, B_ACC));
           }
           umma_commit(bar_of(s, B_WG0));
+          NERFCA_TL(s == 0, 3023);
         }
       }
       __syncwarp();
@@ -639,26 +683,37 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
       const long long tile = worker + (slot + 2 * j) * n_workers;
       const uint32_t pj = (uint32_t)(j & 1);
       uint32_t va[32], vb[32], w[32];
+      const bool tl_me = warp == 1 && lane == 0;
       // ---- step B: dZ1 = dH1 * 1[H1 > 0] -> c2, over H1 itself once weight gradient 2 has read it
+      NERFCA_TL(tl_me, 1001);
       mbar_wait(bar_of(slot, B_ACC), ph_acc); ph_acc ^= 1;
       tc_fence_after();
+      NERFCA_TL(tl_me, 1010);
       ld_acc64(k_acc, va, vb);
       acc_release(acc_rel, lane);
+      NERFCA_TL(tl_me, 1011);
       mbar_wait(bar_of(slot, B_LDH1), pj);
       masked_grad_pack64(va, vb, c2, w);
+      NERFCA_TL(tl_me, 1012);
       mbar_wait(bar_of(slot, B_WG2), pj);
+      NERFCA_TL(tl_me, 1013);
       sts_row64(c2, w);
       warp_publish_smem(bar_of(slot, B_READY), lane);
+      NERFCA_TL(tl_me, 1014);
       // ---- step C: dZ0 = dH0 * 1[H0 > 0] -> c1, over H0 itself once weight gradient 1 has read it
       mbar_wait(bar_of(slot, B_ACC), ph_acc); ph_acc ^= 1;
       tc_fence_after();
       ld_acc64(k_acc, va, vb);
       acc_release(acc_rel, lane);
+      NERFCA_TL(tl_me, 1021);
       mbar_wait(bar_of(slot, B_LDH0), pj);
       masked_grad_pack64(va, vb, c1, w);
+      NERFCA_TL(tl_me, 1022);
       mbar_wait(bar_of(slot, B_WG1), pj);
+      NERFCA_TL(tl_me, 1023);
       sts_row64(c1, w);
       warp_publish_smem(bar_of(slot, B_READY), lane);
+      NERFCA_TL(tl_me, 1024);
       // ---- latent gradient (fallback): columns [enc_dim, enc_dim + T) of dX0 sit at accumulator columns enc_dim - 8 * lat_c0 + t
       if (has_lat) {
         mbar_wait(bar_of(slot, B_ACC), ph_acc); ph_acc ^= 1;

@@ -118,6 +118,9 @@ _SIGNATURES = {
     "nerfca_graph_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nerfca_graph_destroy": (C.c_int, [_P]),
     "nerfca_debug_x0": (C.c_int, [C.POINTER(FieldStruct), C.POINTER(SamplesStruct), _I32, _P, C.POINTER(C.c_int32), _P]),
+    "nerfca_render_workspace_bytes": (C.c_size_t, [C.POINTER(FieldStruct), C.POINTER(FieldStruct), C.POINTER(SamplesStruct), _I32]),
+    "nerfca_render_rays": (C.c_int, [C.POINTER(FieldStruct), C.POINTER(FieldStruct), C.POINTER(SamplesStruct), _I32, _P, _I32, _P, _P, _P, _P, _P]),
+    "nerfca_normalize_image": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
     "nerfca_launch_count": (C.c_int64, []),
     "nerfca_profile_enable": (C.c_int, [_I32]),
     "nerfca_profile_read": (C.c_int, [_I32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

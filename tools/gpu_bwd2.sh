@@ -11,12 +11,12 @@ import json,sys
 d=json.load(open('$OUT/bench_v2.json'))
 print('v2', d['value'], d['ms_per_step'], {k:round(v['ms_per_step'],4) for k,v in d['roofline']['kernels'].items()}, 'e2e', d['e2e']['value'])"
 tail -3 $OUT/bench_v2.err
-NERFCA_BWD_V1=1 timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-eager-baseline --no-render > $OUT/bench_v1.json 2> $OUT/bench_v1.err; echo "bench v1 exit $?"
+NERFCA_GRAPH=0 NERFCA_BWD_V1=1 timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-eager-baseline --no-render > $OUT/bench_v1.json 2> $OUT/bench_v1.err; echo "bench v1 exit $?"
 python -c "
 import json,sys
 d=json.load(open('$OUT/bench_v1.json'))
 print('v1', d['value'], d['ms_per_step'], {k:round(v['ms_per_step'],4) for k,v in d['roofline']['kernels'].items()}, 'e2e', d['e2e']['value'])"
-for sp in "30,44" "36,38" "27,47"; do
+for sp in "25,49" "27,47" "29,45" "31,43" "33,41"; do
 NERFCA_BWD_SPLIT=$sp timeout 300 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-eager-baseline --no-render > $OUT/bench_s.json 2> $OUT/bench_s.err
 python -c "
 import json,sys
