@@ -261,6 +261,70 @@ def workload_config(extra=None):
     return c
 
 
+def dropin_loop_rate(dev, rays_host_tab, phases_host_tab, n_rays: int, steps: int, warmup: int):
+    """rays/s of the UNMODIFIED driver's iteration (train/run_composite.py:227-308) over the drop-in modules: the same sequence of calls
+    the stock script makes -- update_freq_mask_alpha, numpy ray-id draw + host fancy index + H2D, obtain_train_predictions_iter
+    (two FieldFunction launches + the line integral through autograd), weighted_MSELoss, compute_losses (eager torch on the returned
+    sigma tensors), loss.backward(), torch.optim.Adam.step(), LinearLR.step(), and the early-stop read of the loss (:310, a D2H
+    sync every iteration).  (The stock script itself cannot run on the GPU box: /root/reference is not there, and it must not be
+    copied; this restates its loop line by line against the same module surface.)"""
+    import types
+    import model_helpers as mh
+    from model.CPPN import CPPN
+    from model.Temporal import Temporal
+    import parity
+    torch.manual_seed(0)
+    static = CPPN(parity.static_definition(dev, HIDDEN, N_EARLY, N_FREQ, precision="bf16")).to(dev)
+    temp = Temporal(parity.temporal_definition(dev, HIDDEN, N_EARLY, N_FREQ, N_LATENT, precision="bf16"))
+    if N_PHASES != temp.time_latents.shape[0]:
+        temp.time_latents = torch.nn.Parameter(torch.rand((N_PHASES, N_LATENT)))
+    temp.to(dev)
+    opt = torch.optim.Adam(list(temp.parameters()) + list(static.parameters()), lr=LR)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=LR_END_FACTOR, total_iters=LR_DECAY_STEPS)
+    from nerfca import trainer as tr
+    hp = tr.COMPOSITE_HP
+    args = types.SimpleNamespace(favor_s_opt=None, skewness_val=1, entro_mask_thre=hp["entro_mask_thre"],
+                                 entro_use_weighting=hp["entro_use_weighting"], entro_weighted_thresh=hp["entro_weighted_thresh"], occl_reg_perc=0.2)
+    t = torch.linspace(0., 1., N_DEPTH)
+    depth_values = (NEAR * (1. - t) + FAR * t).to(dev)
+    rays_np, phases_np = rays_host_tab.numpy(), phases_host_tab.numpy()
+    mse = mh.weighted_MSELoss()
+    rng = np.random.RandomState(0)
+    i0 = torch.full((n_rays,), I0, dtype=torch.float32, device=dev)
+    t0 = None
+    for k in range(warmup + steps):
+        if k == warmup:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        it = ITER + k
+        static.update_freq_mask_alpha(it, hp["static_window_decay_steps"])
+        temp.update_freq_mask_alpha(it, hp["temp_window_decay_steps"])
+        ids = rng.randint(0, rays_np.shape[0], size=n_rays)
+        batch_rays = torch.from_numpy(rays_np[ids]).to(dev)
+        batch_phases = torch.from_numpy(phases_np[ids]).to(dev)
+        phases_samples = batch_phases[:, None].repeat(1, N_DEPTH)
+        d = hp["hyperparam_decay_steps"]
+        fw = mh.linear_param_decay(it, hp["favor_s_weight_start"], hp["favor_s_weight_end"], d, hp["favor_s_weight_delay_steps"])
+        ew = mh.linear_param_decay(it, hp["dynamic_entro_weight_start"], hp["dynamic_entro_weight_end"], d)
+        ow = mh.linear_param_decay(it, hp["occl_weight_start"], hp["occl_weight_end"], d, hp["favor_s_weight_delay_steps"])
+        lw = mh.linear_param_decay(it, hp["l1_weight_start"], hp["l1_weight_end"], d)
+        pix, ss, sd, dists, *_ = mh.obtain_train_predictions_iter(static, temp, None, None, batch_rays[:, 0, :], batch_rays[:, 1, :], phases_samples,
+                                                                 i0, depth_values, "softplus", 32768, 0, dev)
+        pixel = mse(pix, batch_rays[:, 2, 0], batch_rays[:, 3, 0]).mean()
+        terms = mh.compute_losses(ss, sd, dists, batch_rays[:, 3, 0], args)
+        loss = pixel + fw * terms[3] + ew * terms[6] + ow * terms[8] + lw * terms[10] + lw * terms[9]
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        sched.step()
+        stop = bool(loss < 1e-12)            # the early-stop test of :310 (a D2H sync per iteration)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": n_rays * steps / dt, "unit": "rays/s", "ms_per_step": dt / steps * 1e3, "loss_last_step": float(loss),
+            "api": "the stock driver's iteration (run_composite.py:227-308) restated over the drop-in modules: obtain_train_predictions_iter + "
+                   "compute_losses + loss.backward() + torch.optim.Adam + LinearLR, host ray-table gather + H2D + per-iteration loss read"}
+
+
 def gpu_eager_step_fn(dev, n_rays: int):
     """The reference's own eager-PyTorch step on the GPU (SURVEY 8(d) last row, "the practical beat-this number"): the oracle port
     -- which times identically to the unmodified reference -- with every tensor on `dev`, true-fp32 sgemm (allow_tf32 off, torch's
@@ -306,6 +370,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     select_config(args.config)
@@ -428,6 +493,9 @@ def main():
         barrier()
         e2e_value = n_global * args.steps / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
         d2h = trainer.d2h_bytes_per_step
+        dropin = None
+        if world == 1 and args.config == 2 and not args.no_dropin:
+            dropin = dropin_loop_rate(dev, rays_host_tab, phases_host_tab, N_RAYS, min(args.steps, 30), 5)
         del rays_host_tab, phases_host_tab
 
         # ---------------- e2e, N1 path: ray table resident in HBM, only the step's ray ids + the jitter draw cross PCIe ----------------
@@ -561,6 +629,7 @@ def main():
                     "loss_last_step": losses[-1] if losses else None,
                     "api": "per step: rays_train[ids] / phases_train[ids] gathered on the HOST from the host ray table (as run_composite.py:250-265 does), "
                            "CompositeTrainer.step_host_async(rays[B,4,3] f64, phases[B], t_rand[N]), loss read one step late",
+                    "dropin_modules": dropin,
                     "device_ray_table": {"value": e2e_ids_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_ids, "d2h_bytes_per_step": d2h,
                                          "api": "CompositeTrainer.step_ids_async(ids[B] i64, t_rand[N]) -- ray table resident in HBM, "
                                                 "batch rows gathered by nerfca_gather_batch inside the step's graph"}},

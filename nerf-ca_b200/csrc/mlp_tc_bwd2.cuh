@@ -21,14 +21,18 @@
 // Roles, tile order, the dZ2 hand-off ring through L2 and its flags are those of tc_bwd_kernel.
 //
 // TMEM   top:    ACC [0,128) | WG4 [128,272) | WG3 [272,416)                 (N = 144: column 128 = bias gradient)
-//        bottom: ACC [0,128) | WG2 [128,256) | WG1 [256,384) | WG0 [384,480) | BG2 [480,496) | BG1 [496,512)
+//        bottom: ACC [0,128) | WG2 [128,272) | WG1 [272,416) | WG0 [416,512)        (WG2 / WG1: N = 144 as in the top role)
 // smem   top:    W3 | W4' | slot s: b1[s] (H3 -> dZ3, + constant-1 block), b2[s] (R -> H2, + constant-1 block) | H4 patterns | d_raw | ...
-//        bottom: W1 | W2  | slot s: c1[s] (dZ2 -> H0 -> dZ0), c2[s] (H1 -> dZ1) | X0 | ones | W0 latent chunks | ...
+//        bottom: W1 | W2  | slot s: c1[s] (dZ2 -> H0 -> dZ0, + constant-1 block), c2[s] (H1 -> dZ1 -> X0, + constant-1 block) | W0 latent chunks | ...
+//   * bottom role: the rebuilt first-layer input X0 of a tile goes into the tile's OWN c2 buffer once weight gradient 1 has read dZ1
+//     from it (there used to be one X0 buffer per CTA, refilled only after the previous tile's weight gradient 0: measured, it paced
+//     the whole role, ISS 21->22 = 4 000-5 000 cycles of waiting per tile); the 24 KB this frees hold the constant-1 blocks behind the
+//     buffers, so the bias gradients ride in N = 144 weight-gradient GEMMs instead of separate N = 16 GEMMs that re-read dZ.
 #pragma once
 
 constexpr int BWD2_THREADS = 24 * 32;   // warps 0-15: epilogue (slot = warp / 8); 16, 17: issuers; 18, 19: loaders; 20-23: X0 producers / publisher
 constexpr uint32_t T2_ACC = 0, T2_WG4 = 128, T2_WG3 = 272;
-constexpr uint32_t B2_ACC = 0, B2_WG2 = 128, B2_WG1 = 256, B2_WG0 = 384, B2_BG2 = 480, B2_BG1 = 496;
+constexpr uint32_t B2_ACC = 0, B2_WG2 = 128, B2_WG1 = 272, B2_WG0 = 416;     // WG2 / WG1 are 144 wide: column 128 = bias gradient
 
 // ---- the shared accumulator's ticket lock ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t atom_add_shared(uint32_t addr, uint32_t v) {
@@ -217,7 +221,7 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
       tc_fence_after();
       for (long long j = 0; j < n_s; ++j) {
         const uint32_t pj = (uint32_t)(j & 1);
-        const int tb = s ? 100 : 3000;
+        [[maybe_unused]] const int tb = s ? 100 : 3000;
         mbar_wait(bar_of(s, B_READY), 0);                          // step A: R is in b2
         NERFCA_TL(true, tb + 1);
         acc_acquire(acc_ticket, acc_rel);
@@ -333,8 +337,8 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
     for (long long j = 0; j < n_s; ++j) {
       const uint32_t pj = (uint32_t)(j & 1);
       uint32_t va[32], vb[32], w[32];
-      const bool tl_me = (warp & 7) == 1 && lane == 0;
-      const int te = 1000 + 1000 * slot;
+      [[maybe_unused]] const bool tl_me = (warp & 7) == 1 && lane == 0;
+      [[maybe_unused]] const int te = 1000 + 1000 * slot;
       // ---- step A: R = d_raw 1[H4 > 0] -> b2 (A operand of dgrad 4 and of wgrad 4)
       NERFCA_TL(tl_me, te + 0);
       mbar_wait(bar_of(slot, B_LDM), pj);
@@ -456,9 +460,7 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
 // bottom role: layers 2, 1, 0 (+ latent gradients)
 // =====================================================================================================================
 constexpr size_t B2_OFF_W1 = 0, B2_OFF_W2 = TILE_BYTES, B2_OFF_BUF = 2 * (size_t)TILE_BYTES;
-constexpr size_t B2_OFF_X0 = B2_OFF_BUF + 4 * (size_t)TILE_BYTES;           // 96 * 256
-constexpr size_t B2_OFF_ONES = B2_OFF_X0 + 96 * 256;
-constexpr size_t B2_OFF_W0LAT = B2_OFF_ONES + 4096;
+constexpr size_t B2_OFF_W0LAT = B2_OFF_BUF + 4 * (size_t)TOP_BUF_STRIDE;       // (buffers: 32 KB + a 4 KB constant-1 block each, as in the top role)
 constexpr size_t B2_OFF_LAT = B2_OFF_W0LAT + 4096;                          // 256 f32
 constexpr size_t B2_OFF_TAB = B2_OFF_LAT + 256 * 4;                         // band weights (32 f32) + latent table (256 f32) for the X0 warps
 constexpr size_t B2_OFF_MISC = B2_OFF_TAB + (32 + 256) * 4;                 // acc_rel, acc_ticket, pad
@@ -479,8 +481,6 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
   uint8_t* s_w1 = smem + B2_OFF_W1;
   uint8_t* s_w2 = smem + B2_OFF_W2;
   uint8_t* s_buf = smem + B2_OFF_BUF;
-  uint8_t* s_x0 = smem + B2_OFF_X0;
-  uint8_t* s_ones = smem + B2_OFF_ONES;
   uint8_t* s_w0lat = smem + B2_OFF_W0LAT;
   float* s_lat = reinterpret_cast<float*>(smem + B2_OFF_LAT);
   const int n_lat_acc = has_lat ? nt.n_phases * nt.n_latent : 0;            // <= 256 checked on the host
@@ -517,9 +517,9 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
     const int n_lt = e.n_latent > 0 ? e.n_phases * e.n_latent : 0;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lt[i] = (i < n_lt && lt_in_smem) ? __ldg(e.latents + i) : 0.f;
     for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x) s_lat[i] = 0.f;
-    // ones tile: column 0 == 1 in every row (bias gradients = column sums of dZ)
-    for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
-      reinterpret_cast<uint4*>(s_ones)[i] = (i < 128) ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x)      // the constant-1 block behind each tile buffer (column 0 == 1 in every row)
+      reinterpret_cast<uint4*>(s_buf + (size_t)(i >> 8) * TOP_BUF_STRIDE + TILE_BYTES)[i & 255] =
+          ((i & 255) < 128) ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
     if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(smem + B2_OFF_MISC)[threadIdx.x] = 0u;
   }
   tc_fence_before();
@@ -531,7 +531,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
   [[maybe_unused]] int tl_n = 0;     // developer timeline (NERFCA_TIMELINE=bot): regions 1 = epilogue slot 0, 2 = X0 producer, 3 = issuer 0, 0 = loader 0
 
   if (warp >= 20) {
-    // ================= 4 X0 warps: thread = tile row; ONE X0 buffer serves both slots, tiles in the CTA's order =================
+    // ================= 4 X0 warps: thread = tile row; tiles in the CTA's order, each into its own slot's c2 buffer =================
     reg_dealloc<64>();       // (register budget: see the top role)
     const int row = (warp - 20) * 32 + lane;
     const float* band_w = nt.x0.enc.band_weight ? s_bw : nullptr;
@@ -546,10 +546,11 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
       const long long pn = (worker + (i + 1) * n_workers) * TILE_M + row;
       rin = fetch_row(nt.x0, a.src, pn, i + 1 < n_my && pn < a.src.n_points);
       NERFCA_TL(warp == 20 && lane == 0, 2001);
-      if (i > 0) mbar_wait(bar_of((int)((i - 1) & 1), B_WG0), (uint32_t)(((i - 1) >> 1) & 1));   // weight gradient 0 of the previous tile has read X0
+      uint8_t* x0_dst = s_buf + (size_t)(2 * (int)(i & 1) + 1) * TOP_BUF_STRIDE;                 // c2 of the tile's slot
+      mbar_wait(bar_of((int)(i & 1), B_WG1), (uint32_t)((i >> 1) & 1));                          // weight gradient 1 of THIS tile has read dZ1 from it
       NERFCA_TL(warp == 20 && lane == 0, 2002);
-      emit_x0_row(nt.x0, cur, band_w, lat_tab, SmemSink{s_x0, row}, 0);
-      emit_x0_row(nt.x0, cur, band_w, lat_tab, SmemSink{s_x0, row}, 1);
+      emit_x0_row(nt.x0, cur, band_w, lat_tab, SmemSink{x0_dst, row}, 0);
+      emit_x0_row(nt.x0, cur, band_w, lat_tab, SmemSink{x0_dst, row}, 1);
       warp_publish_smem(bar_of((int)(i & 1), B_X0), lane);
       NERFCA_TL(warp == 20 && lane == 0, 2003);
     }
@@ -559,7 +560,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
       // ================= load warp of slot s =================
       const int s = warp - 18;
       const long long n_s = (n_my + 1 - s) / 2;
-      const uint32_t c1 = smem_u32(s_buf) + (uint32_t)(2 * s) * TILE_BYTES, c2 = c1 + TILE_BYTES;
+      const uint32_t c1 = smem_u32(s_buf) + (uint32_t)(2 * s) * TOP_BUF_STRIDE, c2 = c1 + TOP_BUF_STRIDE;
       if (lane == 0) {
         if (s == 0) {
           const uint32_t lat_bytes = has_lat ? (uint32_t)(lat_n / 8) * CHUNK_BYTES : 0u;
@@ -576,7 +577,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
           const uint32_t pj = (uint32_t)(j & 1);
           const uint32_t seen = ld_acquire_gpu(nt.produced + tile);   // requested now, looked at once the buffer is free
           NERFCA_TL(s == 0, 101);
-          if (j > 0) mbar_wait(bar_of(s, B_WG0), pj ^ 1);             // weight gradient 0 of the previous tile no longer reads dZ0 in c1
+          if (j > 0) mbar_wait(bar_of(s, B_WG0), pj ^ 1);             // weight gradient 0 of the previous tile no longer reads dZ0 (c1) / X0 (c2)
           NERFCA_TL(s == 0, 102);
           if (seen < 8u) wait_flag_ge(nt.produced + tile, 8u);        // all 8 epilogue warps of the top role have written the tile
           NERFCA_TL(s == 0, 103);
@@ -585,7 +586,6 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
           bulk_g2s(c1, nt.handoff + (size_t)ring_slot * TILE_BYTES, TILE_BYTES, bar_of(s, B_LDDZ));
           ring_slot += ring_step;
           if (ring_slot >= (uint32_t)a.ring) ring_slot -= (uint32_t)a.ring;
-          if (j > 0) mbar_wait(bar_of(s, B_WG1), pj ^ 1);             // weight gradient 1 of the previous tile no longer reads dZ1 in c2
           mbar_expect_tx(bar_of(s, B_LDH1), TILE_BYTES);
           bulk_g2s(c2, st + (size_t)TILE_BYTES, TILE_BYTES, bar_of(s, B_LDH1));
           mbar_wait(bar_of(s, B_LDDZ), pj);                           // dZ2 has left its hand-off slot
@@ -607,10 +607,10 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
       // ================= MMA-issuing warp of slot s =================
       const int s = warp - 16;
       const long long n_s = (n_my + 1 - s) / 2;
-      const uint32_t w1 = smem_u32(s_w1), w2 = smem_u32(s_w2), ones = smem_u32(s_ones), x0 = smem_u32(s_x0), w0lat = smem_u32(s_w0lat);
-      const uint32_t c1 = smem_u32(s_buf) + (uint32_t)(2 * s) * TILE_BYTES, c2 = c1 + TILE_BYTES;
+      const uint32_t w1 = smem_u32(s_w1), w2 = smem_u32(s_w2), w0lat = smem_u32(s_w0lat);
+      const uint32_t c1 = smem_u32(s_buf) + (uint32_t)(2 * s) * TOP_BUF_STRIDE, c2 = c1 + TOP_BUF_STRIDE;
       constexpr uint32_t KK = KSTEP_KMAJOR, KM = KSTEP_MNMAJOR;
-      constexpr uint32_t id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 128, 1, 1), id_side = instr_desc(128, 16, 1, 1);
+      constexpr uint32_t id_dgrad = instr_desc(128, 128, 0, 1), id_wgrad = instr_desc(128, 144, 1, 1);
       const uint32_t id_wg0 = instr_desc(128, kpad0, 1, 1), id_lat = instr_desc(128, lat_n > 0 ? lat_n : 16, 0, 1);
       if (lane == 0) {
         mbar_wait(bar_setup, 0);
@@ -629,8 +629,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
           mbar_wait(bar_of(s, B_LDH1), pj);
           tc_fence_after();
           NERFCA_TL(s == 0, 3005);
-          umma_k<8, KM, KM>(tmem + B2_WG2, mnmajor(c1), mnmajor(c2), id_wgrad, 1);                 // WG2 += dZ2^T H1
-          umma_k<8, KM, KM>(tmem + B2_BG2, mnmajor(c1), mnmajor(ones), id_side, 1);                // BG2 += colsum(dZ2)
+          umma_k<8, KM, KM>(tmem + B2_WG2, mnmajor(c1), mnmajor(c2), id_wgrad, 1);                 // WG2 += dZ2^T [H1 | 1]
           umma_commit(bar_of(s, B_WG2));
           NERFCA_TL(s == 0, 3006);
           mbar_wait(bar_of(s, B_READY), 0);                          // step B: dZ1 is in c2
@@ -641,8 +640,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
           umma_commit(bar_of(s, B_ACC));
           mbar_wait(bar_of(s, B_LDH0), pj);
           tc_fence_after();
-          umma_k<8, KM, KM>(tmem + B2_WG1, mnmajor(c2), mnmajor(c1), id_wgrad, 1);                 // WG1 += dZ1^T H0
-          umma_k<8, KM, KM>(tmem + B2_BG1, mnmajor(c2), mnmajor(ones), id_side, 1);                // BG1 += colsum(dZ1)
+          umma_k<8, KM, KM>(tmem + B2_WG1, mnmajor(c2), mnmajor(c1), id_wgrad, 1);                 // WG1 += dZ1^T [H0 | 1]
           umma_commit(bar_of(s, B_WG1));
           NERFCA_TL(s == 0, 3016);
           mbar_wait(bar_of(s, B_READY), 1);                          // step C: dZ0 is in c1
@@ -650,7 +648,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
           mbar_wait(bar_of(s, B_X0), pj);
           tc_fence_after();
           NERFCA_TL(s == 0, 3022);
-          umma_k<8, KM, KM>(tmem + B2_WG0, mnmajor(c1), mnmajor(x0), id_wg0, 1);                   // WG0 += dZ0^T X0
+          umma_k<8, KM, KM>(tmem + B2_WG0, mnmajor(c1), mnmajor(c2), id_wg0, 1);                   // WG0 += dZ0^T X0   (X0 sits in c2)
           if (has_lat) {
             acc_acquire(acc_ticket, acc_rel);
             umma_k<8, KK, KM>(tmem + B2_ACC, kmajor(c1), mnmajor(w0lat), id_lat, 0);               // latent columns of dX0
@@ -671,7 +669,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t k_acc = t_lane + B2_ACC + ch * 64;
     uint32_t k_rowoff = (uint32_t)(ch * 8) * CHUNK_BYTES + (uint32_t)row * 16u;
-    uint32_t c1 = smem_u32(s_buf) + (uint32_t)(2 * slot) * TILE_BYTES + k_rowoff, c2 = c1 + TILE_BYTES;
+    uint32_t c1 = smem_u32(s_buf) + (uint32_t)(2 * slot) * TOP_BUF_STRIDE + k_rowoff, c2 = c1 + TOP_BUF_STRIDE;
     pin(k_acc); pin(k_rowoff); pin(c1); pin(c2);
     // ---- set-up: zero the weight / bias gradient accumulators (384 columns over the 4 (slot, ch) warp groups)
     tmem_zero(t_lane + B2_WG2 + (uint32_t)(slot * 2 + ch) * 96u, 96);
@@ -683,7 +681,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
       const long long tile = worker + (slot + 2 * j) * n_workers;
       const uint32_t pj = (uint32_t)(j & 1);
       uint32_t va[32], vb[32], w[32];
-      const bool tl_me = warp == 1 && lane == 0;
+      [[maybe_unused]] const bool tl_me = warp == 1 && lane == 0;
       // ---- step B: dZ1 = dH1 * 1[H1 > 0] -> c2, over H1 itself once weight gradient 2 has read it
       NERFCA_TL(tl_me, 1001);
       mbar_wait(bar_of(slot, B_ACC), ph_acc); ph_acc ^= 1;
@@ -759,10 +757,10 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
         flush_wgrad(t_lane, B2_WG1, nt.g_w[1], row, ch, 128, 128);
         if (ch == 0) {
           uint32_t v[16];
-          tmem_ld16(t_lane + B2_BG2, v);
+          tmem_ld16(t_lane + B2_WG2 + 128, v);
           tmem_ld_wait();
           if (nt.g_b[2]) atomicAdd(nt.g_b[2] + row, __uint_as_float(v[0]));
-          tmem_ld16(t_lane + B2_BG1, v);
+          tmem_ld16(t_lane + B2_WG1 + 128, v);
           tmem_ld_wait();
           if (nt.g_b[1]) atomicAdd(nt.g_b[1] + row, __uint_as_float(v[0]));
         }
@@ -783,7 +781,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
           // S[n][ph] = sum over the samples of phase ph of dZ0[.][n] sits in columns in_dim + 1 + ph of wgrad 0 (all inside the
           // last 16-column group); d latents[ph][t] = sum_n S[n][ph] * W0[n][enc_dim + t].  S goes through shared memory (slot 1's
           // tile buffers are idle now) so that one thread per (ph, t) can run the 128-term dot product.
-          float* s_S = reinterpret_cast<float*>(s_buf + 2 * (size_t)TILE_BYTES);
+          float* s_S = reinterpret_cast<float*>(s_buf + 2 * (size_t)TOP_BUF_STRIDE);
           const int cg = kpad0 - 16;
           if (ch == (cg >> 6)) {
             uint32_t v[16];

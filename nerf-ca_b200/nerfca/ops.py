@@ -550,12 +550,14 @@ def train_step_static(static_model, rays: torch.Tensor, i0: torch.Tensor, depth:
 
 
 def render_frame(static_model, temp_model, origins: torch.Tensor, dirs: torch.Tensor, depth: torch.Tensor, phase,
-                 i0_value: float, output_activation: str = "softplus", rays_per_pass: int = 1 << 16):
+                 i0_value: float, output_activation: str = "softplus", rays_per_pass: int = 1 << 18):
     """No-grad full-frame render (train/run_composite.py:346-361, 407-413): float32 rays -> (pix, pix_static, pix_dynamic)
-    [n_rays] float32.  Rays are processed in passes so no [W*H*N,3] point tensor or per-sample field output of the
-    whole frame ever exists."""
-    o = origins.reshape(-1, 3).to(torch.float32)
-    d = dirs.reshape(-1, 3).to(torch.float32)
+    [n_rays] float32.  Rays are processed in passes so no [W*H*N,3] point tensor of the whole frame ever exists.
+    tcgen05 path (bf16): nerfca_render_rays -- the line integral is fused into the output layer's epilogue, so neither the
+    per-sample field outputs nor the sigma arrays reach HBM (one forward launch + a tiny finalize per pass).
+    fp32 path: nerfca_fields_forward + three nerfca_integrate launches per pass (reference arithmetic)."""
+    o = origins.reshape(-1, 3).to(torch.float32).contiguous()
+    d = dirs.reshape(-1, 3).to(torch.float32).contiguous()
     n = o.shape[0]
     dev = o.device
     act = activation_code(output_activation)
@@ -566,18 +568,30 @@ def render_frame(static_model, temp_model, origins: torch.Tensor, dirs: torch.Te
     dyn = temp_model is not None
     if dyn:
         spec_d, par_d, prec_d = temp_model._spec(), [p.detach() for p in temp_model._param_list()], temp_model._precision_code()
+        if prec_d != prec_s:
+            raise ValueError("both fields must use the same precision")
     lib = L.load()
+    fs_s = spec_s.struct(_check_params(spec_s, par_s))
+    fs_d = spec_d.struct(_check_params(spec_d, par_d)) if dyn else None
     for r0 in range(0, n, rays_per_pass):
         r1 = min(n, r0 + rays_per_pass)
+        B = r1 - r0
         ph = None
         if dyn:
-            ph = phase[r0:r1] if torch.is_tensor(phase) and phase.numel() > 1 else torch.full((r1 - r0,), int(phase), device=dev)
+            ph = phase[r0:r1] if torch.is_tensor(phase) and phase.numel() > 1 else torch.full((B,), int(phase), device=dev)
         smp = Samples.from_rays(o[r0:r1], d[r0:r1], z, ph)
-        B = r1 - r0
-        fs_s = spec_s.struct(_check_params(spec_s, par_s))
-        fs_d = spec_d.struct(_check_params(spec_d, par_d)) if dyn else None
-        if dyn and prec_d != prec_s:
-            raise ValueError("both fields must use the same precision")
+        i0 = _Scratch.get(("render_i0", B, float(i0_value)), (B,), torch.float32, dev)
+        i0.fill_(i0_value)
+        st = L.stream_ptr()
+        if prec_s == L.PREC_BF16:
+            need = lib.nerfca_render_workspace_bytes(C.byref(fs_s), C.byref(fs_d) if dyn else None, C.byref(smp.struct()), prec_s)
+            ws = _Scratch.get(("render_ws", B * N, prec_s, dyn), need, torch.uint8, dev)
+            L.check(lib.nerfca_render_rays(C.byref(fs_s), C.byref(fs_d) if dyn else None, C.byref(smp.struct()), prec_s, L.ptr(i0), act,
+                                           L.ptr(outs[0][r0:r1]), L.ptr(outs[1][r0:r1]) if dyn else None,
+                                           L.ptr(outs[2][r0:r1]) if dyn else None, L.ptr(ws), st), "nerfca_render_rays")
+            if not dyn:
+                outs[1][r0:r1] = outs[0][r0:r1]
+            continue
         raws = _Scratch.get(("render_raw", B * N), (2, B * N), torch.float32, dev)
         raw_s, raw_d = raws[0], (raws[1] if dyn else None)
         stp = L.StepStruct()
@@ -588,11 +602,9 @@ def render_frame(static_model, temp_model, origins: torch.Tensor, dirs: torch.Te
         stp.precision = prec_s
         ws = _Scratch.get(("render_ws", B * N, prec_s, dyn), lib.nerfca_step_workspace_bytes(C.byref(stp)), torch.uint8, dev)
         L.check(lib.nerfca_fields_forward(C.byref(fs_s), C.byref(fs_d) if dyn else None, C.byref(smp.struct()), prec_s, L.ptr(raw_s),
-                                          L.ptr(raw_d), L.ptr(ws), L.stream_ptr()), "nerfca_fields_forward")
-        i0 = torch.full((B,), i0_value, dtype=torch.float32, device=dev)
-        sig_a = torch.empty((B, N), dtype=torch.float32, device=dev)
-        sig_b = torch.empty((B, N), dtype=torch.float32, device=dev)
-        st = L.stream_ptr()
+                                          L.ptr(raw_d), L.ptr(ws), st), "nerfca_fields_forward")
+        sig = _Scratch.get(("render_sig", B * N), (2, B, N), torch.float32, dev)
+        sig_a, sig_b = sig[0], sig[1]
         if dyn:
             L.check(lib.nerfca_integrate(L.ptr(raw_s), L.ptr(raw_d), L.ptr(z), L.ptr(i0), B, N, act, L.F32, L.ptr(outs[0][r0:r1]),
                                          L.ptr(sig_a), L.ptr(sig_b), None, st), "nerfca_integrate")
@@ -603,3 +615,30 @@ def render_frame(static_model, temp_model, origins: torch.Tensor, dirs: torch.Te
         if not dyn:
             outs[0][r0:r1] = outs[1][r0:r1]
     return outs[0], outs[1], outs[2]
+
+
+def normalize_image(img: torch.Tensor):
+    """N4 (train/run_composite.py:394-413): (img - min) / (max - min) on the device -> (normalised image, float32 [2] = (min, max))."""
+    x = img.detach().to(torch.float32).contiguous()
+    out = torch.empty_like(x)
+    mm = torch.empty((2,), dtype=torch.float32, device=x.device)
+    scratch = torch.empty((2,), dtype=torch.int32, device=x.device)
+    L.check(L.load().nerfca_normalize_image(L.ptr(x), x.numel(), L.ptr(out), L.ptr(mm), L.ptr(scratch), L.stream_ptr()), "nerfca_normalize_image")
+    return out, mm
+
+
+def eval_frame(static_model, temp_model, origins, dirs, depth, phase, i0_value, gt_img=None, weights=None,
+               output_activation: str = "softplus"):
+    """The display block of train/run_composite.py:346-444 for one test frame: the composite / static / dynamic projections, their
+    min-max normalised display versions, and -- when the ground-truth frame is given -- the weighted pixel loss (:363) and its PSNR
+    -10 log10(loss).  Everything stays on the device; returns a dict of tensors."""
+    pix, pix_s, pix_d = render_frame(static_model, temp_model, origins, dirs, depth, phase, i0_value, output_activation)
+    out = {"pix": pix, "pix_static": pix_s, "pix_dynamic": pix_d}
+    for k in ("pix", "pix_static", "pix_dynamic"):
+        out[k + "_norm"], out[k + "_minmax"] = normalize_image(out[k])
+    if gt_img is not None:
+        gt = gt_img.reshape(-1).to(pix.device, torch.float32)
+        w = torch.ones_like(gt) if weights is None else weights.reshape(-1).to(pix.device, torch.float32)
+        out["pixel_loss"] = (((pix - gt) ** 2) * w).mean()
+        out["psnr"] = -10.0 * torch.log10(out["pixel_loss"])
+    return out
