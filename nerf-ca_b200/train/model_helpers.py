@@ -8,7 +8,8 @@ Differences that are deliberate and invisible to the drivers:
     fl32(fl64(o + d z)) in registers from the float64 ray rows (bit-identical positions);
   * the python chunk loop (get_minibatches*, `chunksize`) is replaced by the kernels' tile loop, so
     `chunksize` / `batch_size` is accepted and ignored;
-  * the hierarchical fine pass (depth_samples_per_ray_fine > 0) is not built yet.
+  * the hierarchical fine pass (depth_samples_per_ray_fine > 0) treats the fine sample positions as constants:
+    the CUDA fields do not differentiate with respect to positions (see obtain_train_predictions_iter).
 """
 import torch
 
@@ -95,24 +96,65 @@ def obtain_train_predictions_static(static_model, batch_origins, batch_direction
 def obtain_train_predictions_iter(static_model_coarse, temp_model_coarse, static_model_fine, temp_model_fine, batch_origins,
                                   batch_directions, batch_phases, batch_initial_intensities, depth_values, output_activation,
                                   batch_size, depth_samples_per_ray_fine, device):
-    if depth_samples_per_ray_fine > 0:
-        raise NotImplementedError("hierarchical fine pass (depth_samples_per_ray_fine > 0) is not built; "
-                                  "the shipped composite.txt sets it to 0")
     z = randomize_depth(depth_values, device)
     n_rays, n_depth = batch_origins.shape[0], z.shape[0]
     # upstream repeats the per-ray phase over the samples (run_composite.py:265); all entries of a row are equal
     phase_ray = batch_phases.reshape(n_rays, -1)[:, 0]
-    samples = ops.Samples.from_rays(batch_origins.to(device), batch_directions.to(device), z, phase_ray.to(device))
+    origins, dirs = batch_origins.to(device), batch_directions.to(device)
+    samples = ops.Samples.from_rays(origins, dirs, z, phase_ray.to(device))
     shape = (n_rays, n_depth, temp_model_coarse.num_output_channels)
     raw_s = static_model_coarse.forward_rays(samples).reshape(shape)
     raw_d = temp_model_coarse.forward_rays(samples).reshape(shape)
     pix, sig_s, sig_d, dists = render_volume_density_composite(raw_s, raw_d, batch_initial_intensities, batch_directions, z,
                                                                output_activation)
-    return pix, sig_s, sig_d, dists, None, None, None, None
+    if depth_samples_per_ray_fine <= 0:
+        return pix, sig_s, sig_d, dists, None, None, None, None
+
+    # ---- hierarchical fine pass (upstream :131-158): importance weights from |delta (sigma_s + sigma_d)| of the coarse pass,
+    # extra depths by inverse-transform sampling, merged + sorted per ray with the coarse depths, the fine pair of fields on the
+    # per-ray points (explicit points: the depths differ per ray), the line integral with RAY 0's depths for every ray (:150).
+    # One deliberate difference: the fine sample POSITIONS are constants here (as in the original NeRF); upstream does not detach
+    # them, so there d loss_fine / d position also flows through sample_pdf into the coarse fields.  The CUDA fields do not
+    # differentiate with respect to positions (no caller of the shipped configs needs it: composite.txt:26 sets n_fine = 0).
+    total = n_depth + depth_samples_per_ray_fine
+    with torch.no_grad():
+        eps = torch.ones_like(sig_s[:, :1]) * 1e-10
+        weights = torch.cat([eps, torch.abs((sig_s[:, 1:] + sig_d[:, 1:]) - (sig_s[:, :-1] + sig_d[:, :-1]))], dim=-1)
+        weights = weights / torch.max(weights)
+        zb = z[None, :].repeat(n_rays, 1)
+        mid = .5 * (zb[..., 1:] + zb[..., :-1])
+        pdf_z = sample_pdf(mid, weights[..., 1:-1], depth_samples_per_ray_fine, device)
+        z_fine, _ = torch.sort(torch.cat([pdf_z, zb], -1), -1)
+        pts = (origins[..., None, :] + dirs[..., None, :] * z_fine[..., :, None]).reshape((-1, 3)).float()
+        z_fine0 = z_fine[0, :].contiguous()
+        fine_phases = phase_ray.to(device)[:, None].repeat(1, total).flatten()
+    raw_s_f, raw_d_f = get_predictions_composite(static_model_fine, temp_model_fine, pts, fine_phases, batch_size)
+    shape_f = (n_rays, total, temp_model_coarse.num_output_channels)
+    pix_f, sig_s_f, sig_d_f, dists_f = render_volume_density_composite(raw_s_f.reshape(shape_f), raw_d_f.reshape(shape_f),
+                                                                       batch_initial_intensities, batch_directions, z_fine0,
+                                                                       output_activation)
+    return pix, sig_s, sig_d, dists, pix_f, sig_s_f, sig_d_f, dists_f
 
 
 def sample_pdf(bins, weights, N_samples, device):
-    raise NotImplementedError("sample_pdf belongs to the hierarchical fine pass, which is not built (SURVEY 8(f) N3)")
+    """Inverse-transform sampling of N_samples depths per ray from the piecewise-constant pdf `weights` over `bins`
+    (upstream :162-187).  The uniform draw comes from the CPU generator like upstream (:170), the rest runs on `weights`' device."""
+    weights = weights + 1e-5
+    pdf = weights / torch.sum(weights, dim=-1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
+    u = torch.rand(list(cdf.shape[:-1]) + [N_samples]).to(weights)
+    inds = torch.searchsorted(cdf, u, right=True)
+    below = torch.clamp(inds - 1, min=0)
+    above = torch.clamp(inds, max=cdf.shape[-1] - 1)
+    inds_g = torch.stack([below, above], -1)
+    shape = [inds_g.shape[0], inds_g.shape[1], cdf.shape[-1]]
+    cdf_g = torch.gather(cdf.unsqueeze(1).expand(shape), 2, inds_g)
+    bins_g = torch.gather(bins.unsqueeze(1).expand(shape), 2, inds_g)
+    denom = cdf_g[..., 1] - cdf_g[..., 0]
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    t = (u - cdf_g[..., 0]) / denom
+    return bins_g[..., 0] + t * (bins_g[..., 1] - bins_g[..., 0])
 
 
 # ---- A10: regularisers on the per-sample attenuations -------------------------------------------------------

@@ -401,6 +401,49 @@ def composite_step_loss(sd_static, sd_dyn, cfg_s, cfg_d, origins, dirs, phases_r
     return loss, out
 
 
+def sample_pdf(bins, weights, u):
+    """Inverse-transform sampling of the fine depths (train/model_helpers.py:162-187) with the U[0,1) draw `u` [B, n_fine]
+    passed in (the reference draws it from the CPU generator, :170)."""
+    weights = weights + 1e-5
+    pdf = weights / torch.sum(weights, dim=-1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
+    u = u.to(weights)
+    inds = torch.searchsorted(cdf, u, right=True)
+    below = torch.max(torch.zeros_like(inds - 1), inds - 1)
+    above = torch.min((cdf.shape[-1] - 1) * torch.ones_like(inds), inds)
+    inds_g = torch.stack([below, above], -1)
+    shape = [inds_g.shape[0], inds_g.shape[1], cdf.shape[-1]]
+    cdf_g = torch.gather(cdf.unsqueeze(1).expand(shape), 2, inds_g)
+    bins_g = torch.gather(bins.unsqueeze(1).expand(shape), 2, inds_g)
+    denom = cdf_g[..., 1] - cdf_g[..., 0]
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    t = (u - cdf_g[..., 0]) / denom
+    return bins_g[..., 0] + t * (bins_g[..., 1] - bins_g[..., 0])
+
+
+def fine_pass(sd_static_f, sd_dyn_f, cfg_s, cfg_d, origins, dirs, phases_ray, i0, z, ss_c, sd_c, u, act="softplus", chunk=32768):
+    """The hierarchical fine pass of obtain_train_predictions_iter (train/model_helpers.py:131-158): importance weights from
+    |delta (sigma_s + sigma_d)| of the coarse pass, n_fine extra depths per ray by sample_pdf, merged and sorted PER RAY with the
+    coarse depths, both fine nets on the per-ray points, and the line integral with RAY 0's depths for every ray (:150, a quirk of
+    the reference).  Returns pix_f, sigma_s_f, sigma_d_f, dists_f, z_fine [B, N + n_fine]."""
+    b, n = origins.shape[0], z.shape[0]
+    eps = torch.ones_like(ss_c[:, :1]) * 1e-10
+    w = torch.cat([eps, torch.abs((ss_c[:, 1:] + sd_c[:, 1:]) - (ss_c[:, :-1] + sd_c[:, :-1]))], dim=-1)
+    w = w / torch.max(w)
+    zb = z[None, :].repeat(b, 1)
+    mid = .5 * (zb[..., 1:] + zb[..., :-1])
+    pdf_z = sample_pdf(mid, w[..., 1:-1], u)
+    z_fine, _ = torch.sort(torch.cat([pdf_z, zb.detach()], -1), -1)
+    total = z_fine.shape[-1]
+    pts = (origins[..., None, :] + dirs[..., None, :] * z_fine[..., :, None]).reshape((-1, 3)).float()
+    ph = phases_ray[:, None].repeat(1, total).flatten()
+    raw_s = chunked(lambda p: static_field(p, sd_static_f, cfg_s), chunk, pts).reshape(b, total, 1)
+    raw_d = chunked(lambda p, t: dynamic_field(p, t, sd_dyn_f, cfg_d), chunk, pts, ph).reshape(b, total, 1)
+    pix, ss, sd_, d = integrate_composite(raw_s, raw_d, i0, dirs.dtype, z_fine[0, :], act)
+    return pix, ss, sd_, d, z_fine
+
+
 def static_step_loss(sd_static, cfg_s, origins, dirs, i0, z, gt, wpix, occl_weight, act="softplus", chunk=32768):
     """run_nerf.py training-step loss: obtain_train_predictions_static (model_helpers.py:99-113)
     + weighted MSE + occl_weight_start * compute_occl_loss (run_nerf.py:227-230)."""

@@ -291,6 +291,44 @@ def gen_activations():
     save("activations", **out)
 
 
+def gen_fine_pass():
+    """obtain_train_predictions_iter with the hierarchical fine pass on (model_helpers.py:131-158, sample_pdf :162-187):
+    20 rays x 24 coarse + 16 fine samples, two pairs of small nets; the sample_pdf draw comes from the CPU generator right
+    after randomize_depth's draw, so one torch.manual_seed reproduces both."""
+    geo = GEOS[0]
+    B, N, NF = 20, 24, 16
+    rng = np.random.default_rng(17)
+    o, d = ph.get_ray_values_tigre(60.0, 30.0, 0, geo, DEV)
+    ids = rng.integers(0, o.shape[0] * o.shape[1], size=B)
+    rays = np.zeros((B, 2, 3))
+    rays[:, 0] = o.reshape(-1, 3)[ids]; rays[:, 1] = d.reshape(-1, 3)[ids]
+    phases = rng.integers(0, 10, size=B).astype(np.int64)
+    torch.manual_seed(21)
+    nets = [CPPN(static_params(h=64, n_early=2, L=6)), Temporal(temp_params(h=64, n_early=2, L=6)),
+            CPPN(static_params(h=64, n_early=2, L=6)), Temporal(temp_params(h=64, n_early=2, L=6))]
+    for m in nets:
+        m.update_freq_mask_alpha(150000, 150000)
+    with torch.no_grad():
+        nets[1].output_linear[0].bias += 0.5; nets[3].output_linear[0].bias += 0.5
+    import data_helpers as dh
+    z0 = dh.create_depth_values(3.2, 8.8, N, DEV)
+    batch_rays = torch.from_numpy(rays)
+    bps = torch.from_numpy(phases)[:, None].repeat(1, N)
+    i0 = torch.Tensor([np.log(8.670397)] * B)
+    torch.manual_seed(99)
+    outs = mh.obtain_train_predictions_iter(nets[0], nets[1], nets[2], nets[3], batch_rays[:, 0, :], batch_rays[:, 1, :], bps, i0, z0,
+                                            "softplus", 32768, NF, DEV)
+    torch.manual_seed(99)
+    t_rand = torch.rand(z0.shape)
+    u = torch.rand([B, NF])
+    out = {"rays": rays, "phases": phases, "z0": z0, "i0": i0, "t_rand": t_rand, "u": u, "n_fine": np.int64(NF)}
+    for k, v in zip(["pix_c", "ss_c", "sd_c", "dists_c", "pix_f", "ss_f", "sd_f", "dists_f"], outs):
+        out[k] = v
+    for tag, m in zip(["sc.", "dc.", "sf.", "df."], nets):
+        out.update(sd_arrays(tag, m))
+    save("fine_pass", **out)
+
+
 if __name__ == "__main__":
     gen_geometry(); gen_ray_table(); gen_depth(); gen_encoding(); gen_fields()
-    gen_composite_step(); gen_static_step(); gen_render(); gen_activations()
+    gen_composite_step(); gen_static_step(); gen_render(); gen_activations(); gen_fine_pass()

@@ -375,6 +375,33 @@ def test_fused_render_matches_oracle_and_normalisation():
     assert float(ev["pix_static_norm"].min()) == 0.0 and float(ev["pix_dynamic_norm"].max()) == 1.0
 
 
+def test_fine_pass_matches_reference_fixture(golden):
+    """N3: obtain_train_predictions_iter with depth_samples_per_ray_fine = 16 through the drop-in functions (fp32 fields) vs the
+    reference's outputs: coarse and fine pixels, both pairs of sigma arrays, the ray-0 dists; and gradients reach the fine nets."""
+    import model_helpers as mh
+    g = golden("fine_pass")
+    rays, phases = torch.from_numpy(g["rays"]).to(DEV), torch.from_numpy(g["phases"]).to(DEV)
+    sds = {t: {k[len(t):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(t)} for t in ("sc.", "dc.", "sf.", "df.")}
+    ones = np.ones(6, dtype=np.float32)
+    sc, dc = parity.build_models(sds["sc."], sds["dc."], DEV, "fp32", 64, 2, 6, mask=ones)
+    sf, df = parity.build_models(sds["sf."], sds["df."], DEV, "fp32", 64, 2, 6, mask=ones)
+    n, nf = g["z0"].shape[0], int(g["n_fine"])
+    torch.manual_seed(99)                                    # randomize_depth's draw, then sample_pdf's, as in the reference
+    out = mh.obtain_train_predictions_iter(sc, dc, sf, df, rays[:, 0, :], rays[:, 1, :], phases[:, None].repeat(1, n),
+                                           torch.from_numpy(g["i0"]).to(DEV), torch.from_numpy(g["z0"]).to(DEV), "softplus", 32768, nf, DEV)
+    pix_c, ss_c, sd_c, d_c, pix_f, ss_f, sd_f, d_f = out
+    np.testing.assert_allclose(pix_c.detach().cpu().numpy(), g["pix_c"], rtol=2e-5)
+    assert ss_f.shape == (20, n + nf) and pix_f.dtype == torch.float64
+    # the fine depths are an inverse-CDF of |delta sigma| of the coarse pass: fp32-level differences of the coarse sigmas (summation
+    # order of the GEMMs) move a sample by up to ~2e-5 in depth (measured), and the fine sigmas are then taken at those positions
+    np.testing.assert_allclose(d_f.cpu().numpy(), g["dists_f"], rtol=0, atol=1e-4)          # ray 0's merged depths
+    np.testing.assert_allclose(pix_f.detach().cpu().numpy(), g["pix_f"], rtol=1e-4)
+    np.testing.assert_allclose(ss_f.detach().cpu().numpy(), g["ss_f"], rtol=2e-2, atol=1e-6)
+    np.testing.assert_allclose(sd_f.detach().cpu().numpy(), g["sd_f"], rtol=2e-2, atol=1e-6)
+    (pix_f.sum() + pix_c.sum()).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0 for p in list(sf.parameters()) + list(df.parameters()))
+
+
 # ---- seeded oracle comparisons at larger sizes + size-independent properties ---------------------------------------
 
 @pytest.mark.parametrize("precision", PRECISIONS)

@@ -171,3 +171,23 @@ def test_render_path(golden):
     assert np.array_equal(dists.numpy(), g["dists"])
     for got, key in [(pix, "pix"), (ss, "sigma_s"), (sd, "sigma_d"), (pix_s, "pix_static"), (pix_d, "pix_dynamic")]:
         np.testing.assert_allclose(got.numpy(), g[key], rtol=2e-5, atol=1e-8, err_msg=key)
+
+
+def test_fine_pass_matches_reference(golden):
+    """N3: the oracle's restatement of the hierarchical fine pass (sample_pdf + per-ray sorted depths + the ray-0 dists quirk)
+    against the reference's own obtain_train_predictions_iter with depth_samples_per_ray_fine = 16."""
+    g = golden("fine_pass")
+    rays, phases = torch.from_numpy(g["rays"]), torch.from_numpy(g["phases"])
+    z = orc.jitter_depth(torch.from_numpy(g["z0"]), torch.from_numpy(g["t_rand"]))
+    cfg = {"n_freq": 6, "n_hidden": 2, "pos_enc": "free_windowed", "window": torch.ones(6)}
+    sd = {t: {k[len(t):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(t)} for t in ("sc.", "dc.", "sf.", "df.")}
+    i0 = torch.from_numpy(g["i0"])
+    pix_c, ss_c, sd_c, d_c = orc.composite_forward(sd["sc."], sd["dc."], cfg, cfg, rays[:, 0, :], rays[:, 1, :], phases, i0, z)
+    np.testing.assert_allclose(pix_c.numpy(), g["pix_c"], rtol=1e-6)
+    pix_f, ss_f, sd_f, d_f, z_fine = orc.fine_pass(sd["sf."], sd["df."], cfg, cfg, rays[:, 0, :], rays[:, 1, :], phases, i0, z, ss_c, sd_c,
+                                                   torch.from_numpy(g["u"]))
+    assert z_fine.shape == (20, 40) and bool((z_fine[:, 1:] >= z_fine[:, :-1]).all())
+    assert np.array_equal(d_f.numpy(), g["dists_f"])
+    np.testing.assert_allclose(pix_f.numpy(), g["pix_f"], rtol=1e-6)
+    np.testing.assert_allclose(ss_f.numpy(), g["ss_f"], rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(sd_f.numpy(), g["sd_f"], rtol=1e-5, atol=1e-12)
