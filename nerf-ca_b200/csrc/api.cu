@@ -79,7 +79,15 @@ int simt_field_forward(const nerfca_field_t& f, const nerfca_samples_t& s, float
                        cudaStream_t st);
 int simt_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, const float* d_raw, const void* stash,
                         void* workspace, const nerfca_field_grads_t& gr, cudaStream_t st);
-// bf16 tcgen05 path (mlp_tc.cu)
+// bf16 layer-wise tcgen05 path for shapes outside the fused kernels (mlp_wide.cu)
+int wide_supported(const nerfca_field_t& f);
+size_t wide_stash_bytes(const nerfca_field_t& f, long long P);
+size_t wide_workspace_bytes(const nerfca_field_t& f, long long P, int backward);
+int wide_field_forward(const nerfca_field_t& f, const nerfca_samples_t& s, float* raw_out, void* stash, void* workspace, cudaStream_t st);
+int wide_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, const float* d_raw, const void* stash, void* workspace,
+                        const nerfca_field_grads_t& gr, cudaStream_t st);
+// bf16 fused tcgen05 path (mlp_tc.cu)
+bool tc_shape_ok(const nerfca_field_t& f, bool training);
 int tc_supported(const nerfca_field_t& f);
 size_t tc_stash_bytes(const nerfca_field_t& f, long long P);
 size_t tc_workspace_bytes(const nerfca_field_t& f, long long P, int backward);
@@ -99,6 +107,12 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
 int tc_debug_x0(const nerfca_field_t& f, const nerfca_samples_t& s, int onehot, uint16_t* out, int* kpad0_out, cudaStream_t st);
 
 static size_t up256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+// Which kernels serve a bf16 request: the fused chain kernels when every field has their shape, else the layer-wise GEMM path for ALL
+// fields of the call (one stash / workspace format per call).  `training`: the call writes or reads an activation stash.
+static bool bf16_wide(const nerfca_field_t* a, const nerfca_field_t* b, bool training) {
+  return (a && !tc_shape_ok(*a, training)) || (b && !tc_shape_ok(*b, training));
+}
 
 }  // namespace nerfca
 
@@ -139,14 +153,25 @@ extern "C" int nerfca_profile_read(int32_t kind, double* ms_total, int64_t* laun
 
 extern "C" size_t nerfca_field_stash_bytes(const nerfca_field_t* field, int64_t n_points, int32_t precision) {
   if (!field || n_points <= 0) return 0;
-  return precision == NERFCA_PREC_BF16 ? tc_stash_bytes(*field, n_points) : simt_stash_bytes(*field, n_points);
+  if (precision == NERFCA_PREC_BF16) return bf16_wide(field, nullptr, true) ? wide_stash_bytes(*field, n_points) : tc_stash_bytes(*field, n_points);
+  return simt_stash_bytes(*field, n_points);
 }
 
 extern "C" size_t nerfca_field_workspace_bytes(const nerfca_field_t* field, int64_t n_points, int32_t precision,
                                                int32_t backward) {
   if (!field || n_points <= 0) return 0;
-  return precision == NERFCA_PREC_BF16 ? tc_workspace_bytes(*field, n_points, backward)
-                                       : simt_workspace_bytes(*field, n_points, backward);
+  if (precision == NERFCA_PREC_BF16) {
+    // (a forward's size covers both the stash-writing and the stash-less call: a field of the fused kernels' shape whose latent table
+    // is too large for their backward trains on the layer-wise path but is still evaluated by the fused forward)
+    size_t n = 0;
+    if (bf16_wide(field, nullptr, true)) n = wide_workspace_bytes(*field, n_points, backward);
+    if (!bf16_wide(field, nullptr, backward != 0)) {
+      const size_t m = tc_workspace_bytes(*field, n_points, backward);
+      n = m > n ? m : n;
+    }
+    return n;
+  }
+  return simt_workspace_bytes(*field, n_points, backward);
 }
 
 extern "C" int nerfca_field_forward(const nerfca_field_t* field, const nerfca_samples_t* samples, int32_t precision,
@@ -162,8 +187,12 @@ extern "C" int nerfca_field_forward(const nerfca_field_t* field, const nerfca_sa
                      (stash && precision == NERFCA_PREC_FP32),
                  NERFCA_E_WORKSPACE, "workspace is null");
   if (precision == NERFCA_PREC_BF16) {
-    rc = tc_supported(*field);
-    if (rc) return rc;
+    if (bf16_wide(field, nullptr, stash != nullptr)) {
+      rc = wide_supported(*field);
+      if (rc) return rc;
+      ProfScope prof(NERFCA_K_FIELD_FWD, (cudaStream_t)stream);
+      return wide_field_forward(*field, *samples, raw_out, stash, workspace, (cudaStream_t)stream);
+    }
     return tc_field_forward(*field, *samples, raw_out, stash, workspace, (cudaStream_t)stream);
   }
   ProfScope prof(NERFCA_K_FIELD_FWD, (cudaStream_t)stream);
@@ -185,8 +214,12 @@ extern "C" int nerfca_field_backward(const nerfca_field_t* field, const nerfca_s
     NERFCA_REQUIRE(!field->bias[l] || grads->bias[l], NERFCA_E_ARG, "bias gradient pointer missing");
   }
   if (precision == NERFCA_PREC_BF16) {
-    rc = tc_supported(*field);
-    if (rc) return rc;
+    if (bf16_wide(field, nullptr, true)) {
+      rc = wide_supported(*field);
+      if (rc) return rc;
+      ProfScope prof(NERFCA_K_FIELD_BWD, (cudaStream_t)stream);
+      return wide_field_backward(*field, *samples, d_raw, stash, workspace, *grads, (cudaStream_t)stream);
+    }
     return tc_field_backward(*field, *samples, d_raw, stash, workspace, *grads, (cudaStream_t)stream);
   }
   ProfScope prof(NERFCA_K_FIELD_BWD, (cudaStream_t)stream);
@@ -223,10 +256,10 @@ static int validate_step(const nerfca_step_t* s, bool training) {
     NERFCA_REQUIRE(!s->samples->points && s->samples->n_rays > 0, NERFCA_E_ARG, "a training step needs ray-generated samples");
     NERFCA_REQUIRE(s->static_grads && (!s->dynamic_field || s->dynamic_grads), NERFCA_E_ARG, "gradient descriptors missing");
   }
-  if (s->precision == NERFCA_PREC_BF16) {
-    rc = tc_supported(*s->static_field);
+  if (s->precision == NERFCA_PREC_BF16 && bf16_wide(s->static_field, s->dynamic_field, training)) {
+    rc = wide_supported(*s->static_field);
     if (rc) return rc;
-    if (s->dynamic_field) rc = tc_supported(*s->dynamic_field);
+    if (s->dynamic_field) rc = wide_supported(*s->dynamic_field);
   }
   return rc;
 }
@@ -234,7 +267,12 @@ static int validate_step(const nerfca_step_t* s, bool training) {
 extern "C" size_t nerfca_step_stash_bytes(const nerfca_step_t* s) {
   if (!s || !s->static_field || !s->samples || s->samples->n_points <= 0) return 0;
   const long long P = s->samples->n_points;
-  if (s->precision == NERFCA_PREC_BF16) return tc_stash_bytes_n(s->dynamic_field ? 2 : 1, P);
+  if (s->precision == NERFCA_PREC_BF16) {
+    if (!bf16_wide(s->static_field, s->dynamic_field, true)) return tc_stash_bytes_n(s->dynamic_field ? 2 : 1, P);
+    size_t n = up256(wide_stash_bytes(*s->static_field, P));
+    if (s->dynamic_field) n += up256(wide_stash_bytes(*s->dynamic_field, P));
+    return n;
+  }
   size_t n = up256(simt_stash_bytes(*s->static_field, P));
   if (s->dynamic_field) n += up256(simt_stash_bytes(*s->dynamic_field, P));
   return n;
@@ -243,10 +281,11 @@ extern "C" size_t nerfca_step_stash_bytes(const nerfca_step_t* s) {
 extern "C" size_t nerfca_step_workspace_bytes(const nerfca_step_t* s) {
   if (!s || !s->static_field || !s->samples || s->samples->n_points <= 0) return 0;
   const long long P = s->samples->n_points;
-  if (s->precision == NERFCA_PREC_BF16) {
+  if (s->precision == NERFCA_PREC_BF16 && !bf16_wide(s->static_field, s->dynamic_field, true)) {
     const nerfca_field_t* f[2] = {s->static_field, s->dynamic_field};
     return tc_workspace_bytes_n(f, s->dynamic_field ? 2 : 1, P, 1);
   }
+  const bool wide = s->precision == NERFCA_PREC_BF16;
   // one buffer serves every fp32 call made with this descriptor: the stash-less forward of nerfca_fields_forward lays out
   // enc | ping | pong (in_dim + 2 hidden floats per sample of a chunk), the backward two hidden-wide gradient tiles
   size_t n = 0;
@@ -254,7 +293,7 @@ extern "C" size_t nerfca_step_workspace_bytes(const nerfca_step_t* s) {
   for (int i = 0; i < 2; ++i) {
     if (!fs[i]) continue;
     for (int backward = 0; backward < 2; ++backward) {
-      const size_t m = simt_workspace_bytes(*fs[i], P, backward);
+      const size_t m = wide ? wide_workspace_bytes(*fs[i], P, backward) : simt_workspace_bytes(*fs[i], P, backward);
       n = m > n ? m : n;
     }
   }
@@ -271,12 +310,17 @@ extern "C" int nerfca_fields_forward(const nerfca_field_t* fs, const nerfca_fiel
   NERFCA_REQUIRE(raw_s && (!fd || raw_d), NERFCA_E_ARG, "output pointer is null");
   NERFCA_REQUIRE(workspace || nerfca_step_workspace_bytes(&st) == 0, NERFCA_E_WORKSPACE, "workspace is null");
   cudaStream_t cs = (cudaStream_t)stream;
-  if (precision == NERFCA_PREC_BF16) {
+  if (precision == NERFCA_PREC_BF16 && !bf16_wide(fs, fd, true)) {
     const nerfca_field_t* f[2] = {fs, fd};
     float* outs[2] = {raw_s, raw_d};
     return tc_fields_forward(f, fd ? 2 : 1, *samples, outs, nullptr, workspace, 1, nullptr, cs);
   }
   ProfScope prof(NERFCA_K_FIELD_FWD, cs);
+  if (precision == NERFCA_PREC_BF16) {      // (the step descriptor sizes its workspace with the training criterion: same here)
+    rc = wide_field_forward(*fs, *samples, raw_s, nullptr, workspace, cs);
+    if (rc || !fd) return rc;
+    return wide_field_forward(*fd, *samples, raw_d, nullptr, workspace, cs);
+  }
   rc = simt_field_forward(*fs, *samples, raw_s, nullptr, workspace, cs);
   if (rc || !fd) return rc;
   return simt_field_forward(*fd, *samples, raw_d, nullptr, workspace, cs);
@@ -285,7 +329,7 @@ extern "C" int nerfca_fields_forward(const nerfca_field_t* fs, const nerfca_fiel
 // ---- render: no-grad rays -> pixels with the line integral fused into the output-layer epilogue (tcgen05 path) --------------------
 extern "C" size_t nerfca_render_workspace_bytes(const nerfca_field_t* fs, const nerfca_field_t* fd, const nerfca_samples_t* samples,
                                                 int32_t precision) {
-  if (!fs || !samples || samples->n_points <= 0 || precision != NERFCA_PREC_BF16) return 0;
+  if (!fs || !samples || samples->n_points <= 0 || precision != NERFCA_PREC_BF16 || bf16_wide(fs, fd, true)) return 0;
   const nerfca_field_t* f[2] = {fs, fd};
   return up256(tc_workspace_bytes_n(f, fd ? 2 : 1, samples->n_points, 0)) + 2 * up256((size_t)samples->n_rays * sizeof(float));
 }
@@ -297,8 +341,8 @@ extern "C" int nerfca_render_rays(const nerfca_field_t* fs, const nerfca_field_t
   st.static_field = fs; st.dynamic_field = fd; st.samples = samples; st.precision = precision;
   int rc = validate_step(&st, false);
   if (rc) return rc;
-  NERFCA_REQUIRE(precision == NERFCA_PREC_BF16, NERFCA_E_UNSUPPORTED,
-                 "nerfca_render_rays is the tcgen05 path (fp32: nerfca_fields_forward + nerfca_integrate)");
+  NERFCA_REQUIRE(precision == NERFCA_PREC_BF16 && !bf16_wide(fs, fd, true), NERFCA_E_UNSUPPORTED,
+                 "nerfca_render_rays is the fused tcgen05 path (other precisions / shapes: nerfca_fields_forward + nerfca_integrate)");
   NERFCA_REQUIRE(!samples->points && samples->n_rays > 0, NERFCA_E_ARG, "rendering needs ray-generated samples");
   NERFCA_REQUIRE(i0 && pix && workspace, NERFCA_E_ARG, "null pointer");
   NERFCA_REQUIRE(!fd || (pix_static && pix_dynamic) || (!pix_static && !pix_dynamic), NERFCA_E_ARG, "give both component images or neither");
@@ -331,23 +375,35 @@ extern "C" int nerfca_train_step(const nerfca_step_t* s, void* stream) {
   const float* draws[2] = {s->d_raw_s, s->d_raw_d};
   const int n = dyn ? 2 : 1;
   const long long P = smp.n_points;
-  uint8_t* stash_d = (uint8_t*)s->stash + (s->precision == NERFCA_PREC_BF16 ? 0 : up256(simt_stash_bytes(*s->static_field, P)));
+  const bool fused = s->precision == NERFCA_PREC_BF16 && !bf16_wide(s->static_field, s->dynamic_field, true);
+  const bool wide = s->precision == NERFCA_PREC_BF16 && !fused;
+  uint8_t* stash_d = (uint8_t*)s->stash + (fused ? 0 : up256(wide ? wide_stash_bytes(*s->static_field, P) : simt_stash_bytes(*s->static_field, P)));
   const bool zero_terms = (s->flags & NERFCA_STEP_ZERO_TERMS) != 0;
-  if (s->precision == NERFCA_PREC_BF16) {
+  if (fused) {
     // (the forward launch also clears the loss sums when asked to: no separate memset node in the step's graph)
     rc = tc_fields_forward(f, n, smp, raws, s->stash, s->workspace, (s->flags & NERFCA_STEP_PACKED) ? 0 : 1, zero_terms ? s->terms_out : nullptr, cs);
   } else {
     if (zero_terms) NERFCA_CUDA_OK(cudaMemsetAsync(s->terms_out, 0, NERFCA_N_LOSS_TERMS * sizeof(double), cs));
     ProfScope prof(NERFCA_K_FIELD_FWD, cs);
-    rc = simt_field_forward(*f[0], smp, raws[0], s->stash, s->workspace, cs);
-    if (!rc && dyn) rc = simt_field_forward(*f[1], smp, raws[1], stash_d, s->workspace, cs);
+    if (wide) {
+      rc = wide_field_forward(*f[0], smp, raws[0], s->stash, s->workspace, cs);
+      if (!rc && dyn) rc = wide_field_forward(*f[1], smp, raws[1], stash_d, s->workspace, cs);
+    } else {
+      rc = simt_field_forward(*f[0], smp, raws[0], s->stash, s->workspace, cs);
+      if (!rc && dyn) rc = simt_field_forward(*f[1], smp, raws[1], stash_d, s->workspace, cs);
+    }
   }
   if (rc) return rc;
   rc = nerfca_composite_loss(s->raw_s, dyn ? s->raw_d : nullptr, smp.depth, s->i0, s->gt, s->wpix, s->gw_stride, smp.n_rays, smp.n_depth,
                              s->activation, s->loss, s->pix_out, s->terms_out, s->d_raw_s, dyn ? s->d_raw_d : nullptr, stream);
   if (rc) return rc;
-  if (s->precision == NERFCA_PREC_BF16) return tc_fields_backward(f, n, smp, draws, s->stash, s->workspace, 0, g, cs);
+  if (fused) return tc_fields_backward(f, n, smp, draws, s->stash, s->workspace, 0, g, cs);
   ProfScope prof(NERFCA_K_FIELD_BWD, cs);
+  if (wide) {
+    rc = wide_field_backward(*f[0], smp, draws[0], s->stash, s->workspace, *g[0], cs);
+    if (!rc && dyn) rc = wide_field_backward(*f[1], smp, draws[1], stash_d, s->workspace, *g[1], cs);
+    return rc;
+  }
   rc = simt_field_backward(*f[0], smp, draws[0], s->stash, s->workspace, *g[0], cs);
   if (!rc && dyn) rc = simt_field_backward(*f[1], smp, draws[1], stash_d, s->workspace, *g[1], cs);
   return rc;

@@ -56,6 +56,12 @@ constexpr size_t STASH_PATTERN4_OFF = (size_t)STASH_TILES * 32768;          // t
 constexpr int FWD_THREADS = 20 * 32;             // 16 epilogue / issue warps + 4 X0 producer warps
 constexpr int FAST_FREQ = 12;                    // band count the register-resident encoder is specialised for
 
+// shapes the fused kernels are built for (the layer-wise tcgen05 path of mlp_wide.cu serves every other bf16 request)
+bool tc_shape_ok(const nerfca_field_t& f, bool training) {
+  if (!(f.hidden == TC_H && f.n_hidden == TC_N_RELU - 1 && in_dim_of(f) + 1 <= 96 && f.n_latent <= 16)) return false;
+  // the backward keeps the [phase][t] latent-gradient table in shared memory (forward-only calls, e.g. query_time's per-point latents, do not)
+  return !training || f.n_latent == 0 || (size_t)f.n_phases * f.n_latent <= 256;
+}
 int tc_supported(const nerfca_field_t& f) {
   NERFCA_REQUIRE(f.hidden == TC_H, NERFCA_E_UNSUPPORTED, "the tcgen05 path is built for hidden == 128 (use precision fp32)");
   NERFCA_REQUIRE(f.n_hidden == TC_N_RELU - 1, NERFCA_E_UNSUPPORTED, "the tcgen05 path is built for 4 hidden layers (use precision fp32)");
@@ -141,8 +147,7 @@ int make_repack_table(const nerfca_field_t* const* fields, int n_nets, void* wor
   int ns = 0;
   for (int i = 0; i < n_nets; ++i) {
     const nerfca_field_t& f = *fields[i];
-    int rc = tc_supported(f);
-    if (rc) return rc;
+    if (!tc_shape_ok(f, true)) { out->n_segs = 0; return NERFCA_OK; }    // layer-wise path: converts its weights itself, nothing to re-pack
     const NetDims d = net_dims(f);
     RepackNet& rn = out->net[i];
     rn.out = (uint8_t*)workspace + off;

@@ -461,8 +461,8 @@ __device__ __forceinline__ void bwd2_top_role(const BwdArgs& a, const BwdNet& nt
 // =====================================================================================================================
 constexpr size_t B2_OFF_W1 = 0, B2_OFF_W2 = TILE_BYTES, B2_OFF_BUF = 2 * (size_t)TILE_BYTES;
 constexpr size_t B2_OFF_W0LAT = B2_OFF_BUF + 4 * (size_t)TOP_BUF_STRIDE;       // (buffers: 32 KB + a 4 KB constant-1 block each, as in the top role)
-constexpr size_t B2_OFF_LAT = B2_OFF_W0LAT + 4096;                          // 256 f32
-constexpr size_t B2_OFF_TAB = B2_OFF_LAT + 256 * 4;                         // band weights (32 f32) + latent table (256 f32) for the X0 warps
+constexpr size_t B2_OFF_LAT = B2_OFF_W0LAT + 4096;                          // 8 x 256 f32: one [phase][t] latent-gradient table per (slot, quadrant)
+constexpr size_t B2_OFF_TAB = B2_OFF_LAT + 8 * 256 * 4;                         // band weights (32 f32) + latent table (256 f32) for the X0 warps
 constexpr size_t B2_OFF_MISC = B2_OFF_TAB + (32 + 256) * 4;                 // acc_rel, acc_ticket, pad
 constexpr size_t B2_OFF_BAR = B2_OFF_MISC + 16;
 constexpr int B2_N_BAR = 2 + 2 * 9;
@@ -516,7 +516,7 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
     for (int i = threadIdx.x; i < 32; i += blockDim.x) s_bw[i] = (e.band_weight && i < e.n_freq) ? __ldg(e.band_weight + i) : 1.f;
     const int n_lt = e.n_latent > 0 ? e.n_phases * e.n_latent : 0;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lt[i] = (i < n_lt && lt_in_smem) ? __ldg(e.latents + i) : 0.f;
-    for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x) s_lat[i] = 0.f;
+    if (has_lat) for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) s_lat[i] = 0.f;
     for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x)      // the constant-1 block behind each tile buffer (column 0 == 1 in every row)
       reinterpret_cast<uint4*>(s_buf + (size_t)(i >> 8) * TOP_BUF_STRIDE + TILE_BYTES)[i & 255] =
           ((i & 255) < 128) ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
@@ -645,16 +645,18 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
           NERFCA_TL(s == 0, 3016);
           mbar_wait(bar_of(s, B_READY), 1);                          // step C: dZ0 is in c1
           NERFCA_TL(s == 0, 3021);
-          mbar_wait(bar_of(s, B_X0), pj);
-          tc_fence_after();
-          NERFCA_TL(s == 0, 3022);
-          umma_k<8, KM, KM>(tmem + B2_WG0, mnmajor(c1), mnmajor(c2), id_wg0, 1);                   // WG0 += dZ0^T X0   (X0 sits in c2)
           if (has_lat) {
+            // latent fallback: issued BEFORE the wait for X0 (it only needs dZ0), so the GEMM and its epilogue run while the X0 warps
+            // are still building the tile, and the commit that hands c1 / c2 back to the loader is not held up by the accumulator lock
             acc_acquire(acc_ticket, acc_rel);
             umma_k<8, KK, KM>(tmem + B2_ACC, kmajor(c1), mnmajor(w0lat), id_lat, 0);               // latent columns of dX0
             umma_commit(bar_of(s, B_ACC));
           }
-          umma_commit(bar_of(s, B_WG0));
+          mbar_wait(bar_of(s, B_X0), pj);
+          tc_fence_after();
+          NERFCA_TL(s == 0, 3022);
+          umma_k<8, KM, KM>(tmem + B2_WG0, mnmajor(c1), mnmajor(c2), id_wg0, 1);                   // WG0 += dZ0^T X0   (X0 sits in c2)
+          umma_commit(bar_of(s, B_WG0));                                                           // (covers the latent GEMM's read of c1 too)
           NERFCA_TL(s == 0, 3023);
         }
       }
@@ -699,6 +701,11 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
       warp_publish_smem(bar_of(slot, B_READY), lane);
       NERFCA_TL(tl_me, 1014);
       // ---- step C: dZ0 = dH0 * 1[H0 > 0] -> c1, over H0 itself once weight gradient 1 has read it
+      int phase = -1;        // latent fallback: the row's phase, requested a whole chain step before it is used (an L2 round trip here:
+      if (has_lat) {         // the loaders' flag polls keep invalidating L1)
+        const long long p = tile * TILE_M + row;
+        if (p < a.src.n_points) phase = load_phase(a.src, p);
+      }
       mbar_wait(bar_of(slot, B_ACC), ph_acc); ph_acc ^= 1;
       tc_fence_after();
       ld_acc64(k_acc, va, vb);
@@ -714,36 +721,48 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
       NERFCA_TL(tl_me, 1024);
       // ---- latent gradient (fallback): columns [enc_dim, enc_dim + T) of dX0 sit at accumulator columns enc_dim - 8 * lat_c0 + t
       if (has_lat) {
+        // The accumulator lock is held only until the latent columns are in registers (the other slot's dgrad is waiting for it);
+        // the reduction by phase runs from registers.  Column group ch (16 columns).
         mbar_wait(bar_of(slot, B_ACC), ph_acc); ph_acc ^= 1;
         tc_fence_after();
-        if (ch == 0) {
-          // a warp's 32 rows are consecutive samples, almost always of one ray (one phase): reduce over the warp
-          // first and add once; rows of a warp that straddles two rays fall back to per-lane atomics
-          const long long p = tile * TILE_M + row;
-          const int phase = (p < a.src.n_points) ? load_phase(a.src, p) : -1;
-          const int ph0 = __shfl_sync(0xffffffffu, phase, 0);
-          const bool uniform = __all_sync(0xffffffffu, phase == ph0 || phase < 0);
-          const bool ok = phase >= 0 && phase < nt.n_phases;
-          uint32_t v[16];
-          for (int c0 = 0; c0 < lat_n; c0 += 16) {
-            tmem_ld16(t_lane + B2_ACC + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int t = c0 + e - (nt.enc_dim - 8 * lat_c0);
-              if (t < 0 || t >= nt.n_latent) continue;      // warp-uniform
-              float val = ok ? __uint_as_float(v[e]) : 0.f;
-              if (uniform) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-                if (lane == 0 && ph0 >= 0 && ph0 < nt.n_phases) atomicAdd(&s_lat[ph0 * nt.n_latent + t], val);
-              } else if (ok) {
-                atomicAdd(&s_lat[phase * nt.n_latent + t], val);
-              }
-            }
-          }
+        uint32_t v[16];
+        const int c0 = ch * 16;
+        if (c0 < lat_n) {
+          tmem_ld16(t_lane + B2_ACC + c0, v);
+          tmem_ld_wait();
         }
         acc_release(acc_rel, lane);
+        if (c0 < lat_n) {
+          // A warp's 32 rows are consecutive samples of one ray, sometimes two (one phase each): for every distinct phase in the warp,
+          // sum each latent column over the lanes of that phase by shuffles; lane e keeps column e and adds it to THIS warp's private
+          // copy of the [phase][t] table with a plain read-modify-write (the two column groups of a (slot, quadrant) pair own different
+          // t).  No atomics: shared-memory float atomics are compare-and-swap loops, and the 32 lanes of a straddling warp contending
+          // for two addresses took ~10 000 cycles per tile that the whole slot then waited for (30-phase backward 0.58 -> 0.40 ms, r4g/r4h).
+          // The copies are summed once at the end of the launch.
+          float* my_lat = s_lat + (slot * 4 + q) * 256;
+          const int toff = nt.enc_dim - 8 * lat_c0;
+          const bool ok = phase >= 0 && phase < nt.n_phases;
+          const int t_me = c0 + lane - toff;
+          const bool t_ok = lane < 16 && t_me >= 0 && t_me < nt.n_latent;
+          unsigned remaining = __ballot_sync(0xffffffffu, ok);
+          while (remaining) {                               // warp-uniform loop: one pass per distinct phase
+            const int ph = __shfl_sync(0xffffffffu, phase, __ffs(remaining) - 1);
+            const bool in_seg = ok && phase == ph;
+            float mine = 0.f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int t = c0 + e - toff;
+              if (t < 0 || t >= nt.n_latent) continue;      // warp-uniform
+              float val = in_seg ? __uint_as_float(v[e]) : 0.f;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+              if (lane == e) mine = val;
+            }
+            if (t_ok) my_lat[ph * nt.n_latent + t_me] += mine;
+            remaining &= ~__ballot_sync(0xffffffffu, in_seg);
+          }
+          __syncwarp();
+        }
       }
     }
     // ---- every MMA of both slots has completed: flush the TMEM-resident accumulators
@@ -810,8 +829,12 @@ __device__ __forceinline__ void bwd2_bot_role(const BwdArgs& a, const BwdNet& nt
   tc_fence_before();
   __syncthreads();
   if (nt.g_lat && has_lat)
-    for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x)
-      if (s_lat[i] != 0.f) atomicAdd(nt.g_lat + i, s_lat[i]);
+    for (int i = threadIdx.x; i < n_lat_acc; i += blockDim.x) {
+      float g = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) g += s_lat[w8 * 256 + i];
+      if (g != 0.f) atomicAdd(nt.g_lat + i, g);
+    }
   if (warp == 16) tmem_dealloc(tmem, 512);
 }
 

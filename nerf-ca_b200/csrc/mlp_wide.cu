@@ -1,0 +1,428 @@
+// bf16 tensor-core path for field shapes OUTSIDE the fused tcgen05 kernels of mlp_tc.cu (hidden != 128, first layers wider than 95
+// features, other layer counts: BASELINE config 5, hidden 256 / 16 bands): the layer stack as individual tcgen05 GEMMs.
+//
+// Same orchestration as the fp32 SIMT path (mlp_simt.cu: forward = bias + ReLU GEMM per layer, backward = split-K weight-gradient
+// GEMM + masked dgrad GEMM per layer), but
+//   * activations and gradients live in HBM as bf16 ROW-MAJOR matrices [samples, features] (half the traffic of the fp32 path),
+//     the weights are converted to bf16 row-major copies once per call,
+//   * every GEMM is one kernel template, wide_gemm_kernel<MODE>: 128 x 128 output tile per CTA, fp32 accumulator in tensor memory
+//     (128 columns), operands staged through a 3-stage ring of 32 KB shared-memory stages by 16-byte cp.async copies straight into the
+//     UMMA no-swizzle canonical layout (tc_common.cuh) -- a [128 rows x 64 cols] block of a row-major matrix is copied chunk by
+//     chunk, and depending on which matrix dimension is the reduction the SAME bytes are described K-major (rows = M/N index) or
+//     MN-major (rows = reduction index), so no operand is ever transposed:
+//         forward   C = relu(A W^T + b)   A K-major,  W K-major     (reduction along the contiguous dimension of both)
+//         dgrad     C = (A W) * 1[h > 0]  A K-major,  W MN-major
+//         wgrad     C += A^T H            A MN-major, H MN-major    (reduction = samples, split over blockIdx.z, fp32 atomics)
+//   * one elected thread issues tcgen05.mma (M128 N128 K16, kind::f16) per stage and commits to the stage's mbarrier; the epilogue
+//     reads the accumulator with tcgen05.ld (thread = row x column half) and writes bf16 rows / fp32 atomics.
+// Two CTAs fit per SM (98 KB shared memory, 128 TMEM columns each), which is what hides the copy latency.
+//
+// Reference: model/CPPN.py:88-110, model/Temporal.py:113-151 and their autograd.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace nerfca {
+
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+constexpr int W_STAGES = 3;
+constexpr uint32_t W_OPER_BYTES = 16384;               // one operand block: 128 x 64 (K-major) or 64 x 128 (MN-major) bf16
+constexpr uint32_t W_STAGE_BYTES = 2 * W_OPER_BYTES;
+constexpr size_t W_SMEM = (size_t)W_STAGES * W_STAGE_BYTES + (W_STAGES + 1) * 8 + 16;
+enum { W_FWD = 0, W_DGRAD = 1, W_WGRAD = 2 };
+
+struct WideGemm {
+  const bf16* A; long long lda, a_rows, a_cols;       // row-major matrices as stored (cols are multiples of 8, zero padded)
+  const bf16* B; long long ldb, b_rows, b_cols;
+  long long M; int N; long long K;                    // C is [M, N], reduction length K
+  bf16* C; long long ldc;                             // W_FWD / W_DGRAD output (bf16 rows)
+  const float* bias;                                  // W_FWD: [N] or null
+  const bf16* mask; long long ldm;                    // W_DGRAD: gradient passes where mask > 0 (same shape as C)
+  float* C32; long long ldc32;                        // W_WGRAD output (fp32, atomically accumulated)
+  long long k_split;                                  // W_WGRAD: reduction elements per blockIdx.z (multiple of 64)
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Copies the [RB rows x 8 * CB cols] block at (r0, c0) of a row-major bf16 matrix into the canonical layout
+// byte(row, col) = (col / 8) * (RB * 16) + row * 16 + (col % 8) * 2; everything outside the matrix is zero-filled.  A warp's 32 pieces
+// are 16 consecutive rows x 2 adjacent chunks: full 32-byte sectors on the global side, conflict-free quarter-warps on the shared side.
+template <int RB, int CB>
+__device__ __forceinline__ void load_block(const bf16* mat, long long ld, long long n_rows, long long n_cols, long long r0, long long c0,
+                                           uint32_t smem_base) {
+  constexpr int PIECES = RB * CB;
+  for (int p = threadIdx.x; p < PIECES; p += blockDim.x) {
+    const int sub = p & 31, grp = p >> 5;
+    const int row = (grp % (RB / 16)) * 16 + (sub & 15);
+    const int chunk = (grp / (RB / 16)) * 2 + (sub >> 4);
+    const long long r = r0 + row, c = c0 + chunk * 8;
+    const bool ok = r < n_rows && c < n_cols;
+    cp_async16(smem_base + (uint32_t)chunk * (RB * 16) + (uint32_t)row * 16, ok ? (const void*)(mat + r * ld + c) : (const void*)mat, ok ? 16u : 0u);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) wide_gemm_kernel(WideGemm g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + (size_t)W_STAGES * W_STAGE_BYTES);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + W_STAGES + 1);
+  const uint32_t bar0 = smem_u32(s_bar), bar_done = bar0 + 8 * W_STAGES;   // bar0 + 8 s: the MMAs that read stage s have completed
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s <= W_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+      mbar_init_fence();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(s_tmem), 128);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const long long m0 = (long long)blockIdx.x * 128;
+  const int n0 = blockIdx.y * 128;
+  const long long kbeg = (MODE == W_WGRAD) ? (long long)blockIdx.z * g.k_split : 0;
+  const long long kend = (MODE == W_WGRAD && kbeg + g.k_split < g.K) ? kbeg + g.k_split : g.K;
+  const int nkb = (int)((kend - kbeg + 63) / 64);
+  constexpr uint32_t idesc = (MODE == W_FWD) ? instr_desc(128, 128, 0, 0) : (MODE == W_DGRAD) ? instr_desc(128, 128, 0, 1) : instr_desc(128, 128, 1, 1);
+  const uint32_t s_base = smem_u32(smem);
+
+  auto issue_load = [&](int kb) {
+    const int s = kb % W_STAGES;
+    if (kb >= W_STAGES) mbar_wait(bar0 + 8 * s, (uint32_t)((kb / W_STAGES - 1) & 1));   // the MMAs of block kb - W_STAGES have left the stage
+    const long long k0 = kbeg + (long long)kb * 64;
+    const uint32_t sa = s_base + (uint32_t)s * W_STAGE_BYTES, sb = sa + W_OPER_BYTES;
+    if (MODE == W_WGRAD) load_block<64, 16>(g.A, g.lda, (kend < g.a_rows ? kend : g.a_rows), g.a_cols, k0, m0, sa);   // rows = samples (reduction), cols = M
+    else load_block<128, 8>(g.A, g.lda, g.a_rows, g.a_cols, m0, k0, sa);                                             // rows = M, cols = reduction
+    if (MODE == W_FWD) load_block<128, 8>(g.B, g.ldb, g.b_rows, g.b_cols, n0, k0, sb);                               // rows = N, cols = reduction
+    else load_block<64, 16>(g.B, g.ldb, (MODE == W_WGRAD && kend < g.b_rows) ? kend : g.b_rows, g.b_cols, k0, n0, sb);   // rows = reduction, cols = N
+  };
+  for (int kb = 0; kb < W_STAGES - 1; ++kb) {
+    if (kb < nkb) issue_load(kb);
+    cp_async_commit();
+  }
+  for (int kb = 0; kb < nkb; ++kb) {
+    cp_async_wait<W_STAGES - 2>();        // this thread's pieces of block kb have landed
+    fence_proxy_async();                   // ... and are visible to the tensor core's shared-memory reads
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const int s = kb % W_STAGES;
+      const uint32_t sa = s_base + (uint32_t)s * W_STAGE_BYTES, sb = sa + W_OPER_BYTES;
+      const long long kvalid = (kend - (kbeg + (long long)kb * 64) < 64) ? kend - (kbeg + (long long)kb * 64) : 64;
+      const int ksteps = (int)((kvalid + 15) / 16);
+      for (int kk = 0; kk < ksteps; ++kk) {
+        // K-major [128 x 64] block: reduction step = 2 chunks of 2048 B; MN-major [64 x 128] block: reduction step = 16 rows of 16 B, chunks 1024 B apart
+        const uint64_t da = (MODE == W_WGRAD) ? smem_desc(sa + kk * 256, 128, 1024) : smem_desc(sa + kk * 4096, 2048, 128);
+        const uint64_t db = (MODE == W_FWD) ? smem_desc(sb + kk * 4096, 2048, 128) : smem_desc(sb + kk * 256, 128, 1024);
+        umma_ss(tmem, da, db, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+      }
+      umma_commit(bar0 + 8 * s);
+      if (kb == nkb - 1) umma_commit(bar_done);
+    }
+    if (kb + W_STAGES - 1 < nkb) issue_load(kb + W_STAGES - 1);
+    cp_async_commit();                     // (an empty group keeps the group count uniform)
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue: thread = (accumulator row, column half) ----
+  if (nkb > 0) {
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const int q = warp & 3, ch = warp >> 2;
+    const int row = q * 32 + lane;
+    const long long m = m0 + row;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ch * 64 + half * 32, v);
+      tmem_ld_wait();
+      if (m >= g.M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + ch * 64 + half * 32 + 8 * j;
+        if (n >= g.N) continue;
+        if (MODE == W_WGRAD) {
+          float* dst = g.C32 + m * g.ldc32 + n;
+          if (n + 8 <= g.N && (g.ldc32 & 3) == 0 && (reinterpret_cast<uintptr_t>(g.C32) & 15) == 0) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(v[8 * j])), "f"(__uint_as_float(v[8 * j + 1])),
+                         "f"(__uint_as_float(v[8 * j + 2])), "f"(__uint_as_float(v[8 * j + 3])) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(__uint_as_float(v[8 * j + 4])), "f"(__uint_as_float(v[8 * j + 5])),
+                         "f"(__uint_as_float(v[8 * j + 6])), "f"(__uint_as_float(v[8 * j + 7])) : "memory");
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (n + e < g.N) atomicAdd(dst + e, __uint_as_float(v[8 * j + e]));
+          }
+        } else {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+          uint4 o;
+          if (MODE == W_FWD) {
+            if (g.bias) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += __ldg(g.bias + n + e);
+            }
+            o = make_uint4(pack_relu_bf16x2(f[0], f[1]), pack_relu_bf16x2(f[2], f[3]), pack_relu_bf16x2(f[4], f[5]), pack_relu_bf16x2(f[6], f[7]));
+          } else {
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(g.mask + m * g.ldm + n));
+            o = make_uint4(mul_bf16x2(pack_bf16x2(f[0], f[1]), relu_mask_bf16x2(h.x)), mul_bf16x2(pack_bf16x2(f[2], f[3]), relu_mask_bf16x2(h.y)),
+                           mul_bf16x2(pack_bf16x2(f[4], f[5]), relu_mask_bf16x2(h.z)), mul_bf16x2(pack_bf16x2(f[6], f[7]), relu_mask_bf16x2(h.w)));
+          }
+          *reinterpret_cast<uint4*>(g.C + m * g.ldc + n) = o;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+template <int MODE>
+static int run_wide_gemm(const WideGemm& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return NERFCA_OK;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NERFCA_CUDA_OK(cudaFuncSetAttribute(wide_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_SMEM));
+    attr_done = true;
+  }
+  const long long splits = (MODE == W_WGRAD) ? (g.K + g.k_split - 1) / g.k_split : 1;
+  dim3 grid((unsigned)((g.M + 127) / 128), (unsigned)((g.N + 127) / 128), (unsigned)splits);
+  wide_gemm_kernel<MODE><<<grid, 256, W_SMEM, st>>>(g);
+  NERFCA_LAUNCH_OK();
+  return NERFCA_OK;
+}
+
+// ---- small kernels around the GEMMs (bf16 row-major activations) --------------------------------------------------------------------
+// first-layer input [np, Dp] bf16 (A4 + A5 in registers, zero padded to Dp = roundup8(in_dim)): one thread per (sample, feature)
+__global__ void wide_encode_kernel(SampleSrc src, EncDesc enc, int Dp, bf16* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = src.n_points * Dp;
+  if (idx >= total) return;
+  const long long p = idx / Dp;
+  const int f = (int)(idx - p * Dp);
+  float v = 0.f;
+  if (f < enc.in_dim) {
+    float x, y, z;
+    load_point(src, p, x, y, z);
+    const int phase = (f >= enc.enc_dim) ? load_phase(src, p) : 0;
+    v = enc_feature(enc, f, x, y, z, phase);
+  }
+  out[idx] = __float2bfloat16_rn(v);
+}
+// W fp32 [rows, K] -> bf16 [rows, Kp] (zero padded)
+__global__ void wide_cvt_weight_kernel(const float* __restrict__ w, int rows, int K, int Kp, bf16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Kp) return;
+  const int r = idx / Kp, k = idx - r * Kp;
+  out[idx] = __float2bfloat16_rn(k < K ? __ldg(w + (size_t)r * K + k) : 0.f);
+}
+// output layer (hidden -> 1): one warp per sample
+__global__ void wide_out_forward_kernel(const bf16* __restrict__ h, const float* __restrict__ w, const float* __restrict__ b, long long np, int H,
+                                        float* __restrict__ raw) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= np) return;
+  float acc = 0.f;
+  for (int k = lane; k < H; k += 32) acc = fmaf(__bfloat162float(h[row * H + k]), __ldg(w + k), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) raw[row] = acc + (b ? __ldg(b) : 0.f);
+}
+// backward of the output layer: dZ[p,k] = d_raw[p] w[k] 1[h>0];  dW[k] += sum_p d_raw[p] h[p,k];  db += sum_p d_raw[p]
+constexpr int W_ROWS_PER_BLOCK = 128;
+__global__ void wide_out_backward_kernel(const float* __restrict__ d_raw, const bf16* __restrict__ h, const float* __restrict__ w, long long np, int H,
+                                         bf16* __restrict__ dz, float* __restrict__ dw, float* __restrict__ db) {
+  const long long r0 = (long long)blockIdx.x * W_ROWS_PER_BLOCK;
+  const long long r1 = (r0 + W_ROWS_PER_BLOCK < np) ? r0 + W_ROWS_PER_BLOCK : np;
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    const float wk = __ldg(w + k);
+    float aw = 0.f, ab = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+      const float g = __ldg(d_raw + r), hv = __bfloat162float(h[r * H + k]);
+      dz[r * H + k] = __float2bfloat16_rn(hv > 0.f ? g * wk : 0.f);
+      aw = fmaf(g, hv, aw);
+      ab += g;
+    }
+    atomicAdd(dw + k, aw);
+    if (k == 0 && db) atomicAdd(db, ab);
+  }
+}
+// db[n] += sum_p dz[p,n]
+__global__ void wide_colsum_kernel(const bf16* __restrict__ dz, long long np, int H, float* __restrict__ db) {
+  const long long r0 = (long long)blockIdx.x * W_ROWS_PER_BLOCK;
+  const long long r1 = (r0 + W_ROWS_PER_BLOCK < np) ? r0 + W_ROWS_PER_BLOCK : np;
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    float a = 0.f;
+    for (long long r = r0; r < r1; ++r) a += __bfloat162float(dz[r * H + k]);
+    atomicAdd(db + k, a);
+  }
+}
+// d time_latents[phase[p], t] += sum_n dz0[p,n] W0[n, enc_dim + t]   (scatter-add of Temporal.py:144-147's gather)
+__global__ void wide_latent_grad_kernel(const bf16* __restrict__ dz0, const float* __restrict__ w0, SampleSrc src, int H, int D, int enc_dim, int T,
+                                        int n_phases, int use_smem, float* __restrict__ dlat) {
+  extern __shared__ float sacc[];  // [n_phases * T] when use_smem
+  if (use_smem) {
+    for (int i = threadIdx.x; i < n_phases * T; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+  }
+  const int per_block = blockDim.x / T;
+  const int local = threadIdx.x / T, tt = threadIdx.x - local * T;
+  const long long p = (long long)blockIdx.x * per_block + local;
+  if (local < per_block && p < src.n_points) {
+    float a = 0.f;
+    for (int n = 0; n < H; ++n) a = fmaf(__bfloat162float(dz0[p * H + n]), __ldg(w0 + (size_t)n * D + enc_dim + tt), a);
+    const int ph = load_phase(src, p);
+    if (ph >= 0 && ph < n_phases) atomicAdd(use_smem ? &sacc[ph * T + tt] : dlat + (size_t)ph * T + tt, a);
+  }
+  if (!use_smem) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_phases * T; i += blockDim.x)
+    if (sacc[i] != 0.f) atomicAdd(dlat + i, sacc[i]);
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------------------
+constexpr long long WIDE_CHUNK = 262144;   // samples per pass over the layer stack
+static int pad8(int n) { return (n + 7) & ~7; }
+static size_t up256w(size_t n) { return (n + 255) & ~(size_t)255; }
+
+int wide_supported(const nerfca_field_t& f) {
+  NERFCA_REQUIRE(f.hidden % 8 == 0, NERFCA_E_UNSUPPORTED, "bf16 path: hidden must be a multiple of 8 (use precision fp32)");
+  return NERFCA_OK;
+}
+// bf16 weight copies [layer][hidden, Kp_l] at the head of the workspace
+static size_t wide_weight_bytes(const nerfca_field_t& f) {
+  const int Dp = pad8(in_dim_of(f)), H = f.hidden, L = f.n_hidden + 1;
+  return up256w(((size_t)H * Dp + (size_t)(L - 1) * H * H) * sizeof(bf16));
+}
+size_t wide_stash_bytes(const nerfca_field_t& f, long long P) {
+  return (size_t)P * ((size_t)pad8(in_dim_of(f)) + (size_t)(f.n_hidden + 1) * f.hidden) * sizeof(bf16);
+}
+size_t wide_workspace_bytes(const nerfca_field_t& f, long long P, int backward) {
+  const long long ch = P < WIDE_CHUNK ? P : WIDE_CHUNK;
+  const size_t w = wide_weight_bytes(f);
+  if (backward) return w + (size_t)ch * f.hidden * 2 * sizeof(bf16);
+  return w + (size_t)ch * ((size_t)pad8(in_dim_of(f)) + 2 * (size_t)f.hidden) * sizeof(bf16);
+}
+
+static int wide_convert_weights(const nerfca_field_t& f, bf16* wb, cudaStream_t st) {
+  const int D = in_dim_of(f), Dp = pad8(D), H = f.hidden, L = f.n_hidden + 1;
+  size_t off = 0;
+  for (int l = 0; l < L; ++l) {
+    const int K = l ? H : D, Kp = l ? H : Dp;
+    wide_cvt_weight_kernel<<<div_up((long long)H * Kp, 256), 256, 0, st>>>(f.weight[l], H, K, Kp, wb + off);
+    NERFCA_LAUNCH_OK();
+    off += (size_t)H * Kp;
+  }
+  return NERFCA_OK;
+}
+static const bf16* wide_weight(const nerfca_field_t& f, const bf16* wb, int l) {
+  const int Dp = pad8(in_dim_of(f)), H = f.hidden;
+  return l == 0 ? wb : wb + (size_t)H * Dp + (size_t)(l - 1) * H * H;
+}
+
+int wide_field_forward(const nerfca_field_t& f, const nerfca_samples_t& s, float* raw_out, void* stash, void* workspace, cudaStream_t st) {
+  const long long P = s.n_points;
+  const int D = in_dim_of(f), Dp = pad8(D), H = f.hidden, L = f.n_hidden + 1;   // L layers with ReLU
+  bf16* wb = (bf16*)workspace;
+  int rc = wide_convert_weights(f, wb, st);
+  if (rc) return rc;
+  bf16* scratch = (bf16*)((uint8_t*)workspace + wide_weight_bytes(f));
+  bf16* st_x0 = (bf16*)stash;
+  bf16* st_h = stash ? st_x0 + (size_t)P * Dp : nullptr;
+  const EncDesc enc = make_enc(f);
+  for (long long c0 = 0; c0 < P; c0 += WIDE_CHUNK) {
+    const long long np = (P - c0 < WIDE_CHUNK) ? P - c0 : WIDE_CHUNK;
+    const long long ch = P < WIDE_CHUNK ? P : WIDE_CHUNK;
+    bf16* x0 = stash ? st_x0 + (size_t)c0 * Dp : scratch;
+    bf16* ping[2] = {scratch + (size_t)ch * Dp, scratch + (size_t)ch * Dp + (size_t)ch * H};
+    wide_encode_kernel<<<div_up(np * Dp, 256), 256, 0, st>>>(make_src(s, c0, np), enc, Dp, x0);
+    NERFCA_LAUNCH_OK();
+    const bf16* in = x0;
+    int Kp = Dp;
+    for (int l = 0; l < L; ++l) {
+      bf16* out = stash ? st_h + ((size_t)l * P + c0) * H : ping[l & 1];
+      WideGemm g{};
+      g.A = in; g.lda = Kp; g.a_rows = np; g.a_cols = Kp;
+      g.B = wide_weight(f, wb, l); g.ldb = Kp; g.b_rows = H; g.b_cols = Kp;
+      g.M = np; g.N = H; g.K = Kp;
+      g.C = out; g.ldc = H; g.bias = f.bias[l];
+      rc = run_wide_gemm<W_FWD>(g, st);
+      if (rc) return rc;
+      in = out; Kp = H;
+    }
+    wide_out_forward_kernel<<<div_up(np * 32, 256), 256, 0, st>>>(in, f.weight[L], f.bias[L], np, H, raw_out + c0);
+    NERFCA_LAUNCH_OK();
+  }
+  return NERFCA_OK;
+}
+
+int wide_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, const float* d_raw, const void* stash, void* workspace,
+                        const nerfca_field_grads_t& gr, cudaStream_t st) {
+  const long long P = s.n_points;
+  const int D = in_dim_of(f), Dp = pad8(D), H = f.hidden, L = f.n_hidden + 1;
+  bf16* wb = (bf16*)workspace;
+  int rc = wide_convert_weights(f, wb, st);     // (the forward's copies may live in a different workspace: the autograd path)
+  if (rc) return rc;
+  const bf16* st_x0 = (const bf16*)stash;
+  const bf16* st_h = st_x0 + (size_t)P * Dp;
+  const long long ch = P < WIDE_CHUNK ? P : WIDE_CHUNK;
+  bf16* X = (bf16*)((uint8_t*)workspace + wide_weight_bytes(f));
+  bf16* Y = X + (size_t)ch * H;
+  for (long long c0 = 0; c0 < P; c0 += WIDE_CHUNK) {
+    const long long np = (P - c0 < WIDE_CHUNK) ? P - c0 : WIDE_CHUNK;
+    const unsigned rb = div_up(np, W_ROWS_PER_BLOCK);
+    const bf16* h_last = st_h + ((size_t)(L - 1) * P + c0) * H;
+    wide_out_backward_kernel<<<rb, 128, 0, st>>>(d_raw + c0, h_last, f.weight[L], np, H, X, gr.weight[L], gr.bias[L]);
+    NERFCA_LAUNCH_OK();
+    for (int l = L - 1; l >= 0; --l) {
+      const bf16* h_prev = (l > 0) ? st_h + ((size_t)(l - 1) * P + c0) * H : st_x0 + (size_t)c0 * Dp;
+      const int Kin = (l > 0) ? H : D, Kinp = (l > 0) ? H : Dp;
+      {  // wgrad: dW_l[n, k] += sum_p X[p, n] h_prev[p, k]
+        WideGemm g{};
+        g.A = X; g.lda = H; g.a_rows = np; g.a_cols = H;
+        g.B = h_prev; g.ldb = Kinp; g.b_rows = np; g.b_cols = Kinp;
+        g.M = H; g.N = Kin; g.K = np; g.k_split = 2048;
+        g.C32 = gr.weight[l]; g.ldc32 = Kin;
+        rc = run_wide_gemm<W_WGRAD>(g, st);
+        if (rc) return rc;
+      }
+      if (gr.bias[l]) {
+        wide_colsum_kernel<<<rb, 128, 0, st>>>(X, np, H, gr.bias[l]);
+        NERFCA_LAUNCH_OK();
+      }
+      if (l > 0) {  // dgrad: Y[p, k] = (sum_n X[p, n] W_l[n, k]) * 1[h_prev[p,k] > 0]
+        WideGemm g{};
+        g.A = X; g.lda = H; g.a_rows = np; g.a_cols = H;
+        g.B = wide_weight(f, wb, l); g.ldb = H; g.b_rows = H; g.b_cols = H;
+        g.M = np; g.N = H; g.K = H;
+        g.C = Y; g.ldc = H; g.mask = h_prev; g.ldm = H;
+        rc = run_wide_gemm<W_DGRAD>(g, st);
+        if (rc) return rc;
+        bf16* tmp = X; X = Y; Y = tmp;
+      } else if (f.n_latent > 0 && gr.latents) {
+        const int T = f.n_latent;
+        const int threads = (256 / T) * T;
+        const int per_block = threads / T;
+        const int use_smem = (size_t)f.n_phases * T * sizeof(float) <= 32 * 1024;
+        const size_t smem = use_smem ? (size_t)f.n_phases * T * sizeof(float) : 0;
+        wide_latent_grad_kernel<<<div_up(np, per_block), threads, smem, st>>>(X, f.weight[0], make_src(s, c0, np), H, D, enc_dim_of(f), T,
+                                                                            f.n_phases, use_smem, gr.latents);
+        NERFCA_LAUNCH_OK();
+      }
+    }
+  }
+  return NERFCA_OK;
+}
+
+}  // namespace nerfca

@@ -553,9 +553,9 @@ def render_frame(static_model, temp_model, origins: torch.Tensor, dirs: torch.Te
                  i0_value: float, output_activation: str = "softplus", rays_per_pass: int = 1 << 18):
     """No-grad full-frame render (train/run_composite.py:346-361, 407-413): float32 rays -> (pix, pix_static, pix_dynamic)
     [n_rays] float32.  Rays are processed in passes so no [W*H*N,3] point tensor of the whole frame ever exists.
-    tcgen05 path (bf16): nerfca_render_rays -- the line integral is fused into the output layer's epilogue, so neither the
-    per-sample field outputs nor the sigma arrays reach HBM (one forward launch + a tiny finalize per pass).
-    fp32 path: nerfca_fields_forward + three nerfca_integrate launches per pass (reference arithmetic)."""
+    fused tcgen05 path (bf16, hidden 128): nerfca_render_rays -- the line integral is fused into the output layer's epilogue, so
+    neither the per-sample field outputs nor the sigma arrays reach HBM (one forward launch + a tiny finalize per pass).
+    fp32 path and bf16 shapes on the layer-wise GEMM path: nerfca_fields_forward + three nerfca_integrate launches per pass."""
     o = origins.reshape(-1, 3).to(torch.float32).contiguous()
     d = dirs.reshape(-1, 3).to(torch.float32).contiguous()
     n = o.shape[0]
@@ -583,8 +583,9 @@ def render_frame(static_model, temp_model, origins: torch.Tensor, dirs: torch.Te
         i0 = _Scratch.get(("render_i0", B, float(i0_value)), (B,), torch.float32, dev)
         i0.fill_(i0_value)
         st = L.stream_ptr()
-        if prec_s == L.PREC_BF16:
-            need = lib.nerfca_render_workspace_bytes(C.byref(fs_s), C.byref(fs_d) if dyn else None, C.byref(smp.struct()), prec_s)
+        # (0 = these fields are not served by the fused kernels -- fp32, or bf16 shapes on the layer-wise GEMM path)
+        need = lib.nerfca_render_workspace_bytes(C.byref(fs_s), C.byref(fs_d) if dyn else None, C.byref(smp.struct()), prec_s)
+        if need > 0:
             ws = _Scratch.get(("render_ws", B * N, prec_s, dyn), need, torch.uint8, dev)
             L.check(lib.nerfca_render_rays(C.byref(fs_s), C.byref(fs_d) if dyn else None, C.byref(smp.struct()), prec_s, L.ptr(i0), act,
                                            L.ptr(outs[0][r0:r1]), L.ptr(outs[1][r0:r1]) if dyn else None,

@@ -742,13 +742,25 @@ def test_trainer_step_from_ids_equals_step_from_host_rows():
 
 # ---- BASELINE config 5: widened stress shapes ------------------------------------------------------------------------------------
 
-def test_config5_widened_stress_shapes():
-    """hidden 256, 16 Fourier bands (D_s = 99, D_t = 107), 256 samples per ray: outside the tile shapes the tcgen05 kernels are built
-    for, so the bf16 path must refuse loudly (NotImplementedError, no silent fallback) and the fp32 SIMT path must match the oracle."""
-    res = parity.run_composite_step_parity(n_rays=24, n_depth=256, precision="fp32", seed=13, hidden=256, n_freq=16, fused=True)
-    assert res["grad_cos_min"] >= parity.TOL["fp32"]["grad_cos"]
-    with pytest.raises(NotImplementedError):
-        parity.run_composite_step_parity(n_rays=8, n_depth=256, precision="bf16", seed=13, hidden=256, n_freq=16, fused=True)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_config5_widened_stress_shapes(precision):
+    """hidden 256, 16 Fourier bands (D_s = 99, D_t = 107), 256 samples per ray: outside the tile shapes the fused tcgen05 kernels are
+    built for.  bf16 runs the layer-wise tcgen05 GEMM path (csrc/mlp_wide.cu), fp32 the SIMT path; both against the oracle, fused step
+    and autograd drop-in path, with a sample count that is not a multiple of the 128-row GEMM tile."""
+    res = parity.run_composite_step_parity(n_rays=24, n_depth=256, precision=precision, seed=13, hidden=256, n_freq=16, fused=True)
+    assert res["grad_cos_min"] >= parity.TOL[precision]["grad_cos"]
+    res = parity.run_composite_step_parity(n_rays=11, n_depth=77, precision=precision, seed=14, hidden=256, n_freq=16, fused=False)
+    assert res["grad_cos_min"] >= parity.TOL[precision]["grad_cos"]
+
+
+def test_layerwise_tensor_core_path_other_shapes():
+    """The layer-wise tcgen05 path also serves other widths / depths the fused kernels refuse: hidden 64 with 2 hidden layers, and
+    hidden 192 with 30 phases x 16 latent dims (a latent table too large for the fused backward)."""
+    res = parity.run_composite_step_parity(n_rays=40, n_depth=50, precision="bf16", seed=21, hidden=64, n_early=2, n_freq=10, fused=True)
+    assert res["grad_cos_min"] >= parity.TOL["bf16"]["grad_cos"]
+    res = parity.run_composite_step_parity(n_rays=40, n_depth=50, precision="bf16", seed=22, hidden=192, n_early=3, n_freq=12, n_latent=16,
+                                           n_phases=30, fused=True)
+    assert res["grad_cos_min"] >= parity.TOL["bf16"]["grad_cos"]
 
 
 # ---- (e) multi-GPU: gradient sum fused with the optimizer step over peer memory (needs >= 2 GPUs; skipped on a one-GPU box) -------
