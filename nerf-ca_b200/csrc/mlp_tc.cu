@@ -19,7 +19,7 @@
 //   tc_forward_kernel   X0 -> H0 .. H4 -> raw.   16 epilogue warps (2 tiles in flight x (row quadrant, column half)), each slot
 //                       issues its own MMAs, 4 X0 producer warps.  Hidden-layer biases are added in the epilogue, ReLU is fused
 //                       into the bf16 conversion, the 128 -> 1 layer is an N = 16 MMA against a (hi, lo) bf16 split of w_out.
-//   tc_bwd_kernel       ONE launch, two CTA roles per net (31 : 43 of the 74 CTAs):
+//   tc_bwd_kernel       ONE launch, two CTA roles per net (31 : 43 of the 74 CTAs); the default while the latent gradient comes through one-hot columns (tc_bwd2_kernel, mlp_tc_bwd2.cuh, otherwise):
 //     top role          layers 4, 3 (+ output layer): loads H2, H3, the H4 pattern, d_raw; dZ4' = d_raw 1[H4 > 0]; dgrad 4, 3;
 //                       wgrad 4, 3 with the bias gradient folded in (N = 144) accumulate in TMEM; dZ2 -> L2 ring.
 //     bottom role       layers 2, 1, 0: polls the ring, loads dZ2, H1, H0; dgrad 2, 1; wgrad 2, 1, 0; rebuilds X0; latent
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) tc_forward_kernel(FwdArgs a) {
           if (stash_on) {
             if (l < 4) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
+              for (int c = 0; c < 4; ++c)      // (issued after the barrier, in the shadow of the next MMA, they measured 6 % slower: r5a, 254 vs 240 us)
                 __stcs(reinterpret_cast<uint4*>(dst + (4 * g + c) * CHUNK_BYTES), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
             } else {
               // every half of w is a non-negative bf16: adding 0x7FFF carries into the half's top bit exactly when it is nonzero (and
@@ -1121,9 +1121,14 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
       tmem_st_wait();
       tc_fence_before();
       fence_proxy_async();
+      // The slot wait comes BEFORE the arrival on bar_mfree: the loader's next arrival on bar_slot follows its wait for bar_mfree of THIS
+      // tile (inside the loop additionally bar_half / bar_h3free, after the loop nothing else), so with the two statements the other
+      // way round a warp that was held up between them on the LAST tile could find bar_slot two phases on (arrival n_my - 2 consumed
+      // by nobody yet, arrival n_my - 1 already in): its parity wait then never returns and the bounded wait traps.  That is the
+      // "once per 10^4 steps" trap of round 1 and the r3l soak failure.
+      if (i > 0) mbar_wait(bar_slot, par ^ 1);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_mfree);        // the pattern and d_raw of this tile have been consumed
-      if (i > 0) mbar_wait(bar_slot, par ^ 1);      // (before the barrier, so that the loader's next arrival cannot overtake this phase)
       NERFCA_TL(warp == 1 && lane == 0, 1013);
       named_bar_sync(1, 288);       // 8 epilogue warps + the issuing warp
       NERFCA_TL(warp == 1 && lane == 0, 1014);
@@ -1761,12 +1766,15 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
   NERFCA_REQUIRE(n_top >= 1 && n_bot >= 1, NERFCA_E_UNSUPPORTED, "tcgen05 backward needs at least two SMs per net");
   a.n_top = n_top; a.n_bot = n_bot; a.ring = (int)ring;
   NERFCA_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)n_nets * 2 * a.n_tiles * sizeof(uint32_t), st));
-  // Default: the second-generation kernel (two tiles in flight per CTA on one shared accumulator, mlp_tc_bwd2.cuh).  NERFCA_BWD_V1=1
-  // selects tc_bwd_kernel: ~5 % faster in isolation (r3j: 390 vs 410 us) but it TRAPPED in a 4 000-step soak under CUDA-graph
-  // replay (r3l: a bounded wait of its hand-off protocol gave up; the same kernel launched eagerly ran clean) -- the protocol slip
-  // behind the round-1 "once per 10^4 steps" trap is still in there.  Every mbarrier of the v2 kernel has a written argument why it
-  // can never run more than one phase ahead of a waiter (mlp_tc_bwd2.cuh), and it ran the same soak clean.
-  if (merged && !env_flag("NERFCA_BWD_V1", 0)) {
+  // Two generations of the one-launch kernel.  tc_bwd_kernel (one tile in flight, prefetched loads, dgrad A operands in tensor memory)
+  // is the faster one while the latent gradient comes through the one-hot columns (<= 12 phases; r5b: 390 vs 402-418 us);
+  // tc_bwd2_kernel (two tiles in flight on one shared accumulator, mlp_tc_bwd2.cuh) has the atomic-free latent fallback and wins
+  // 2.6x when that is needed (config 3, 30 phases: 0.45 vs 1.19 ms).  NERFCA_BWD_V1=1 / 0 forces one or the other.
+  // (tc_bwd_kernel trapped once per ~10^4 steps in round 1 and once in a 4 000-step soak under graph replay: its top role waited
+  // for bar_slot AFTER arriving on bar_mfree, see the comment there; with the two swapped it ran 2 x 40 000 + 2 x 70 000 steps clean.)
+  bool fallback_lat = false;
+  for (int i = 0; i < n_nets; ++i) fallback_lat = fallback_lat || (f[i]->n_latent > 0 && a.net[i].x0.onehot == 0);
+  if (merged && !env_flag("NERFCA_BWD_V1", fallback_lat ? 0 : 1)) {
     if (!getenv("NERFCA_BWD_SPLIT")) {
       // per tile the top role moves ~460 KB and the bottom role ~630 KB through shared memory (what bounds both): 29 : 45 of 74
       // measured best (r3i), kept coprime (see below)
