@@ -138,6 +138,7 @@ __device__ __forceinline__ int load_phase(const SampleSrc& s, long long q) {
 __device__ __forceinline__ float enc_feature(const EncDesc& e, int f, float x, float y, float z, int phase) {
   if (f >= e.enc_dim) {  // latent concat, model/Temporal.py:124,144-147
     const int t = f - e.enc_dim;
+    if (phase < 0 || phase >= e.n_phases) phase = 0;       // same convention as the tensor-core kernels (emit_x0_row): never read outside the table
     return (t < e.n_latent) ? __ldg(e.latents + (size_t)phase * e.n_latent + t) : 0.f;
   }
   if (e.mode == NERFCA_ENC_NONE) return f == 0 ? x : (f == 1 ? y : z);
