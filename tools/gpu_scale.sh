@@ -16,6 +16,6 @@ import json
 d=json.load(open('$OUT/${name}_${N}gpu.json'))
 print('$name N=$N', d['scaling'], round(d['value']), round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']), 'ids', round(d['e2e']['device_ray_table']['value']), d['config']['collective'], d['config']['replicas_bit_identical'], 'render', d['render'] and round(d['render']['ms_per_frame'],2), {k:round(v['ms_per_step'],4) for k,v in d['roofline']['kernels'].items()})" || tail -3 $OUT/${name}_${N}gpu.err
 }
-run cfg3_weak --config 3
-run cfg3_strong8192 --config 3 --strong 8192
+run cfg3_weak --config 3 --no-render
+run cfg3_strong8192 --config 3 --strong 8192 --no-render
 run cfg2_weak

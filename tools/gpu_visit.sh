@@ -24,7 +24,7 @@ for rep in 1 2; do timeout 600 python tools/soak.py $SOAK 2>&1 | tail -1 | tee -
 NERFCA_CUPROF=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv \
     --log-file $OUT/launches.csv python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-render --no-dropin > $OUT/ncu_bench.log 2>&1
 python tools/launch_shares.py $OUT/launches.csv > $OUT/launch_shares.txt 2>&1; cat $OUT/launch_shares.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_(forward|bwd2?)_kernel|composite_loss|adam' -s 8 -c 4 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_(forward|bwd2?)_kernel|composite_loss' -s 3 -c 3 \
     -o $OUT/prof -f python tools/profile_step.py 1024 500 3 > $OUT/ncu_full.log 2>&1
 tail -3 $OUT/ncu_full.log
 ls -la $OUT
