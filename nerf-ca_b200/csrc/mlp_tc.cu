@@ -1788,7 +1788,8 @@ int tc_fields_backward(const nerfca_field_t* const* f, int n_nets, const nerfca_
       // per tile the top role moves ~460 KB and the bottom role ~630 KB through shared memory (what bounds both): 29 : 45 of 74
       // measured best (r3i), kept coprime (see below)
       auto gcd2 = [](int x, int y) { while (y) { const int r = x % y; x = y; y = r; } return x; };
-      n_top = (per_net * 2 + 2) / 5;
+      // (with the latent fallback the bottom role carries an extra GEMM + scatter per tile: 25 : 49 measured best at 30 phases, r5x)
+      n_top = fallback_lat ? (per_net + 1) / 3 : (per_net * 2 + 2) / 5;
       while (n_top > 1 && gcd2(n_top, per_net - n_top) != 1) --n_top;
       n_bot = per_net - n_top;
       if (n_top > a.n_tiles) n_top = (int)a.n_tiles;
