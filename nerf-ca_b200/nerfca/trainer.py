@@ -145,6 +145,21 @@ class PeerGradients:
                 "nerfca_allreduce_adam_step")
 
 
+class _InputSlot:
+    """Device copies of one step's host inputs (batch rows or ray ids, phases, the jitter draw).  A ring of four per batch size: the
+    H2D copies of step k run on the trainer's copy stream while the kernels of step k - 1 are still busy on the compute stream
+    (`ready`: copies landed, the compute stream waits for it; `done`: the step that read the slot has been enqueued behind it, the
+    copy stream waits for it before the slot is overwritten four steps later)."""
+
+    def __init__(self, B, n_depth, device):
+        self.rays = torch.empty((B, 4, 3), dtype=torch.float64, device=device)
+        self.phases = torch.empty((B,), dtype=torch.int32, device=device)
+        self.ids = torch.empty((B,), dtype=torch.int64, device=device)
+        self.t_rand = torch.empty((n_depth,), dtype=torch.float32, device=device)
+        self.ready, self.done = torch.cuda.Event(), torch.cuda.Event()
+        self.used = False
+
+
 class PendingLoss:
     """Loss sums of one enqueued step: a pinned host slot + the event recorded behind its D2H copy (a ring of 8 per trainer, so a
     handle must be read before 8 further steps are enqueued)."""
@@ -215,7 +230,6 @@ class CompositeTrainer:
         self._pending_next = 0
         self.rays_table = self.phases_table = None       # device-resident ray table (attach_ray_table)
         self._gather_err = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self._gather_out = {}
         self.iteration = 0
         self.loss_cfg = ops.LossConfig()
         # one CUDA-graph launch per step (NERFCA_GRAPH=0: the same calls launched one by one); capture needs a non-default stream
@@ -223,6 +237,8 @@ class CompositeTrainer:
             use_graph = os.environ.get("NERFCA_GRAPH", "1") != "0"
         self.use_graph = bool(use_graph) and self.device.type == "cuda"
         self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self._copy_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self._input_rings, self._input_next = {}, 0
         self._graph = C.c_void_p()
         if self.use_graph:
             L.check(L.load().nerfca_graph_create(C.byref(self._graph)), "nerfca_graph_create")
@@ -399,12 +415,29 @@ class CompositeTrainer:
         if phases_host.dtype != torch.int32:
             phases_host = phases_host.to(torch.int32)          # run_composite.py:265 `.int()`, on the host: 4 B per ray cross PCIe
         n_glob = self._global_rays(rays_host.shape[0], n_rays_global)
+        slot = self._stage(rays_host.shape[0], rays=rays_host, phases=phases_host, t_rand=t_rand_host)
         with self._on_stream():
-            rays = rays_host.to(self.device, non_blocking=True)
-            phases = phases_host.to(self.device, non_blocking=True)
-            t_rand = t_rand_host.to(self.device, non_blocking=True)
-            self._enqueue_step(rays, phases, self._depth_buf, n_glob, pre=lambda: self._jitter_into(t_rand))
+            torch.cuda.current_stream().wait_event(slot.ready)
+            self._enqueue_step(slot.rays, slot.phases, self._depth_buf, n_glob, pre=lambda: self._jitter_into(slot.t_rand))
+            slot.done.record(torch.cuda.current_stream())
             return self._finish_async(n_glob)
+
+    def _stage(self, B: int, **host) -> _InputSlot:
+        """H2D copies of one step's host inputs into the next input slot, on the copy stream (they overlap the previous step's kernels)."""
+        ring = self._input_rings.get(B)
+        if ring is None:
+            ring = self._input_rings[B] = [_InputSlot(B, self.n_depth, self.device) for _ in range(4)]
+        slot = ring[self._input_next % len(ring)]
+        self._input_next += 1
+        cs = self._copy_stream
+        if slot.used:
+            cs.wait_event(slot.done)
+        slot.used = True
+        with torch.cuda.stream(cs):
+            for name, src in host.items():
+                getattr(slot, name).copy_(src, non_blocking=True)
+            slot.ready.record(cs)
+        return slot
 
     def _jitter_into(self, t_rand_dev):
         L.check(L.load().nerfca_jitter_depth(L.ptr(self.depth_uniform), L.ptr(t_rand_dev), self.n_depth, L.ptr(self._depth_buf),
@@ -429,21 +462,19 @@ class CompositeTrainer:
         if B > 0 and (int(ids_host.min()) < 0 or int(ids_host.max()) >= R):
             raise IndexError(f"ray id outside the ray table of {R} rays")
         n_glob = self._global_rays(B, n_rays_global)
-        if B not in self._gather_out:
-            self._gather_out[B] = (torch.empty((B, 4, 3), dtype=torch.float64, device=self.device),
-                                   torch.empty((B,), dtype=torch.int32, device=self.device))
-        rays, phases = self._gather_out[B]
+        slot = self._stage(B, ids=ids_host, t_rand=t_rand_host)
+        rays, phases, ids = slot.rays, slot.phases, slot.ids          # the gathered rows land in the slot's own row buffers
         lib = L.load()
 
         def pre():
             if B > 0:
                 L.check(lib.nerfca_gather_batch(L.ptr(self.rays_table), L.ptr(self.phases_table), R, L.ptr(ids), B, L.ptr(rays), L.ptr(phases),
                                                 L.ptr(self._gather_err), L.stream_ptr()), "nerfca_gather_batch")
-            self._jitter_into(t_rand)
+            self._jitter_into(slot.t_rand)
         with self._on_stream():
-            ids = ids_host.to(self.device, non_blocking=True)
-            t_rand = t_rand_host.to(self.device, non_blocking=True)
+            torch.cuda.current_stream().wait_event(slot.ready)
             self._enqueue_step(rays, phases, self._depth_buf, n_glob, pre=pre)
+            slot.done.record(torch.cuda.current_stream())
             return self._finish_async(n_glob)
 
     def loss_from(self, terms: torch.Tensor, n_rays_global: Optional[int] = None) -> torch.Tensor:
