@@ -18,7 +18,9 @@
 // Two CTAs fit per SM (98 KB shared memory, 128 TMEM columns each), which is what hides the copy latency.
 //
 // Reference: model/CPPN.py:88-110, model/Temporal.py:113-151 and their autograd.
+#include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -188,6 +190,263 @@ __global__ void __launch_bounds__(256) wide_gemm_kernel(WideGemm g) {
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+// ---- persistent TMA-fed version of the same GEMM (the default; NERFCA_WIDE_TMA=0 or a driver without cuTensorMapEncodeTiled falls back
+// to wide_gemm_kernel above) --------------------------------------------------------------------------------------------------------
+// One CTA per SM walks the output tiles (n fastest, so the CTAs that share an A block run side by side and the second fetch is an L2
+// hit).  Warp 0: one lane issues the operand loads as 2-D tensor-map copies with the 128-byte swizzle: a box of 64 contiguous bf16 (one
+// 128-byte swizzle row) x 128 rows is a K-major operand block, two boxes of 64 x 64 are an MN-major one (UMMA canonical layouts
+// SWIZZLE_128B: K-major ((8,n),2):((8,SBO),1), MN-major ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units, SBO = 1024 B, LBO = 8192 B);
+// out-of-range rows / columns are zero-filled by the copy engine.  (A 3-D map [cols / 8][rows][8] that lands the bytes in the no-swizzle
+// chunk layout of wide_gemm_kernel works too but moves 16 bytes per request: 170 us per GEMM, r6b.)  Warp 1: one lane issues the MMAs of a tile into one of two 128-column accumulators and commits
+// the stage's "empty" and the accumulator's "full" mbarriers.  Warps 2-9: epilogue of the OTHER accumulator meanwhile.  Six 32 KB
+// stages keep ~190 KB of loads in flight per SM; the per-thread cp.async version above had 64 KB and a CTA-wide barrier + proxy
+// fence per K block (r5w: 250 us per 262144 x 256 x 256 GEMM, tensor pipe 6.5 %).
+constexpr int W2_STAGES = 5;
+constexpr int W2_THREADS = 10 * 32;
+constexpr uint32_t W2_ROW_BYTES = 272;                 // one staged output row: 128 bf16 + 16 B of padding (conflict-free 16-byte accesses by row AND by column)
+constexpr uint32_t W2_STAGING = 128 * W2_ROW_BYTES;
+constexpr size_t W2_SMEM = (size_t)W2_STAGES * W_STAGE_BYTES + W2_STAGING + (2 * W2_STAGES + 4) * 8 + 16;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int col, int row, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(col), "r"(row)
+               : "memory");
+}
+// operand block at (row0, col0) of a row-major matrix: K-major = [128 rows x 64 reduction cols] in one box, MN-major = [64 reduction rows x
+// 128 cols] as two 64-column boxes 8 KB apart
+__device__ __forceinline__ void load_kmajor(uint32_t dst, const CUtensorMap* tm, int row0, int col0, uint32_t bar) { tma_load_2d(dst, tm, col0, row0, bar); }
+__device__ __forceinline__ void load_mnmajor(uint32_t dst, const CUtensorMap* tm, int row0, int col0, uint32_t bar) {
+  tma_load_2d(dst, tm, col0, row0, bar);
+  tma_load_2d(dst + 8192u, tm, col0 + 64, row0, bar);
+}
+// UMMA descriptors of those blocks (SWIZZLE_128B = layout type 2), reduction step kk of 16
+__device__ __forceinline__ uint64_t desc_sw128_k(uint32_t base, int kk) { return smem_desc(base + kk * 32, 16, 1024) | (2ull << 61); }
+__device__ __forceinline__ uint64_t desc_sw128_mn(uint32_t base, int kk) { return smem_desc(base + kk * 2048, 8192, 1024) | (2ull << 61); }
+
+template <int MODE>
+__global__ void __launch_bounds__(W2_THREADS, 1) wide_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                                   WideGemm g, int n_mt, int n_nt, int n_sp) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + (size_t)W2_STAGES * W_STAGE_BYTES + W2_STAGING);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * W2_STAGES + 4);
+  [[maybe_unused]] const uint32_t s_out = smem_u32(smem) + W2_STAGES * W_STAGE_BYTES;   // staged output tile (and, W_DGRAD, the mask tile before it)
+  const uint32_t full0 = smem_u32(s_bar), empty0 = full0 + 8 * W2_STAGES, accf0 = empty0 + 8 * W2_STAGES, acce0 = accf0 + 16;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < W2_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 8); }
+      mbar_init_fence();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(s_tmem), 256);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t s_base = smem_u32(smem);
+  const long long total = (long long)n_mt * n_nt * n_sp;
+  // tile t -> (n tile, m tile, reduction split); the K range of a tile in 64-wide blocks
+  auto k_range = [&](long long t, long long& m0, int& n0, long long& kbeg, long long& kend) {
+    const int nt = (int)(t % n_nt);
+    const long long rest = t / n_nt;
+    const long long mt = rest % n_mt, sp = rest / n_mt;
+    m0 = mt * 128; n0 = nt * 128;
+    kbeg = (MODE == W_WGRAD) ? sp * g.k_split : 0;
+    kend = (MODE == W_WGRAD && kbeg + g.k_split < g.K) ? kbeg + g.k_split : g.K;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {   // ================= operand loads =================
+      uint32_t it = 0;
+      for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+        long long m0, kbeg, kend; int n0;
+        k_range(t, m0, n0, kbeg, kend);
+        const int nkb = (int)((kend - kbeg + 63) / 64);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % W2_STAGES;
+          if (it >= W2_STAGES) mbar_wait(empty0 + 8 * s, ((it / W2_STAGES) - 1) & 1);   // the MMAs that read the stage's previous block are done
+          const uint32_t sa = s_base + s * W_STAGE_BYTES, sb = sa + W_OPER_BYTES, bar = full0 + 8 * s;
+          const int k0 = (int)(kbeg + (long long)kb * 64);
+          mbar_expect_tx(bar, W_STAGE_BYTES);
+          if (MODE == W_WGRAD) load_mnmajor(sa, &tmA, k0, (int)m0, bar);               // rows = reduction (samples), cols = M
+          else load_kmajor(sa, &tmA, (int)m0, k0, bar);                                 // rows = M, cols = reduction
+          if (MODE == W_FWD) load_kmajor(sb, &tmB, n0, k0, bar);                        // rows = N, cols = reduction
+          else load_mnmajor(sb, &tmB, k0, n0, bar);                                     // rows = reduction, cols = N
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ================= MMA issue =================
+      constexpr uint32_t idesc = (MODE == W_FWD) ? instr_desc(128, 128, 0, 0) : (MODE == W_DGRAD) ? instr_desc(128, 128, 0, 1) : instr_desc(128, 128, 1, 1);
+      uint32_t it = 0, tl = 0;
+      for (long long t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
+        long long m0, kbeg, kend; int n0;
+        k_range(t, m0, n0, kbeg, kend);
+        const int nkb = (int)((kend - kbeg + 63) / 64);
+        const uint32_t b = tl & 1;
+        if (tl >= 2) mbar_wait(acce0 + 8 * b, ((tl >> 1) - 1) & 1);   // the epilogue has read the accumulator's previous tile
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % W2_STAGES;
+          mbar_wait(full0 + 8 * s, (it / W2_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = s_base + s * W_STAGE_BYTES, sb = sa + W_OPER_BYTES;
+          const long long left = kend - (kbeg + (long long)kb * 64);
+          const int ksteps = (int)(((left < 64 ? left : 64) + 15) / 16);
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint64_t da = (MODE == W_WGRAD) ? desc_sw128_mn(sa, kk) : desc_sw128_k(sa, kk);
+            const uint64_t db = (MODE == W_FWD) ? desc_sw128_k(sb, kk) : desc_sw128_mn(sb, kk);
+            umma_ss(tmem + b * 128, da, db, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(accf0 + 8 * b);
+      }
+    }
+  } else {
+    // ================= epilogue: thread = (accumulator row, column half); warps 2-9 cover the four TMEM lane quadrants twice.  A thread
+    // owns a ROW of the tile, so its global accesses would touch 32 different lines per warp instruction; rows are therefore exchanged
+    // through a padded shared-memory tile and the global side runs 16 threads per 256-byte row segment (full lines): the ReLU-mask tile
+    // on the way in (W_DGRAD), the bf16 output tile on the way out.  (The fp32 weight-gradient tiles -- 512 per GEMM instead of 4096 --
+    // go out as vector reductions straight from the registers.) =================
+    const int q = warp & 3, ch = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int te = (int)threadIdx.x - 64;                     // 0 .. 255 among the epilogue threads
+    const int c_row = te >> 4, c_col = te & 15;               // coalesced side: rows c_row + 16 k, 16-byte piece c_col
+    const uint32_t my_row = s_out + (uint32_t)row * W2_ROW_BYTES + (uint32_t)(ch * 8) * 16u;
+    uint32_t tl = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
+      long long m0, kbeg, kend; int n0;
+      k_range(t, m0, n0, kbeg, kend);
+      const uint32_t b = tl & 1;
+      const long long m = m0 + row;
+      uint4 hmask[8];
+      if (MODE == W_DGRAD) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const long long r = m0 + c_row + 16 * k;
+          const int n = n0 + c_col * 8;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (r < g.M && n < g.N) v = __ldg(reinterpret_cast<const uint4*>(g.mask + r * g.ldm + n));
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(s_out + (uint32_t)(c_row + 16 * k) * W2_ROW_BYTES + (uint32_t)c_col * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hmask[j].x), "=r"(hmask[j].y), "=r"(hmask[j].z), "=r"(hmask[j].w) : "r"(my_row + (uint32_t)j * 16u) : "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      mbar_wait(accf0 + 8 * b, (tl >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + b * 128 + ch * 64 + half * 32, v);
+        tmem_ld_wait();
+        if (MODE == W_WGRAD) {
+          if (m >= g.M) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = n0 + ch * 64 + half * 32 + 8 * j;
+            if (n >= g.N) continue;
+            float* dst = g.C32 + m * g.ldc32 + n;
+            if (n + 8 <= g.N && (g.ldc32 & 3) == 0 && (reinterpret_cast<uintptr_t>(g.C32) & 15) == 0) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(v[8 * j])), "f"(__uint_as_float(v[8 * j + 1])),
+                           "f"(__uint_as_float(v[8 * j + 2])), "f"(__uint_as_float(v[8 * j + 3])) : "memory");
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(__uint_as_float(v[8 * j + 4])), "f"(__uint_as_float(v[8 * j + 5])),
+                           "f"(__uint_as_float(v[8 * j + 6])), "f"(__uint_as_float(v[8 * j + 7])) : "memory");
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (n + e < g.N) atomicAdd(dst + e, __uint_as_float(v[8 * j + e]));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = n0 + ch * 64 + half * 32 + 8 * j;
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+            uint4 o;
+            if (MODE == W_FWD) {
+              if (g.bias && n < g.N) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              o = make_uint4(pack_relu_bf16x2(f[0], f[1]), pack_relu_bf16x2(f[2], f[3]), pack_relu_bf16x2(f[4], f[5]), pack_relu_bf16x2(f[6], f[7]));
+            } else {
+              const uint4 h = hmask[half * 4 + j];
+              o = make_uint4(mul_bf16x2(pack_bf16x2(f[0], f[1]), relu_mask_bf16x2(h.x)), mul_bf16x2(pack_bf16x2(f[2], f[3]), relu_mask_bf16x2(h.y)),
+                             mul_bf16x2(pack_bf16x2(f[4], f[5]), relu_mask_bf16x2(h.z)), mul_bf16x2(pack_bf16x2(f[6], f[7]), relu_mask_bf16x2(h.w)));
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (uint32_t)(half * 4 + j) * 16u), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce0 + 8 * b);             // the accumulator has been read: the MMA lane may start the tile after next
+      if (MODE != W_WGRAD) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const long long r = m0 + c_row + 16 * k;
+          const int n = n0 + c_col * 8;
+          uint4 v;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                       : "r"(s_out + (uint32_t)(c_row + 16 * k) * W2_ROW_BYTES + (uint32_t)c_col * 16u) : "memory");
+          if (r < g.M && n < g.N) *reinterpret_cast<uint4*>(g.C + r * g.ldc + n) = v;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");       // the staged tile has been read: the next tile may overwrite it
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* e = getenv("NERFCA_WIDE_TMA");
+    if (!(e && e[0] == '0')) {
+      void* p = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+      else cudaGetLastError();
+    }
+  }
+  return fn;
+}
+// row-major bf16 matrix [n_rows, n_cols] (ld a multiple of 8) as a 2-D tensor map, box = 64 columns (128 B, one swizzle row) x box_rows
+static bool make_operand_map(EncodeTiledFn fn, CUtensorMap* tm, const bf16* mat, long long ld, long long n_rows, long long n_cols, int box_rows) {
+  if ((ld & 7) || (reinterpret_cast<uintptr_t>(mat) & 15) || n_rows <= 0 || n_cols <= 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)n_cols, (cuuint64_t)n_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(bf16)};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(mat), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static int wide_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int MODE>
 static int run_wide_gemm(const WideGemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return NERFCA_OK;
@@ -197,6 +456,24 @@ static int run_wide_gemm(const WideGemm& g, cudaStream_t st) {
     attr_done = true;
   }
   const long long splits = (MODE == W_WGRAD) ? (g.K + g.k_split - 1) / g.k_split : 1;
+  if (EncodeTiledFn fn = encode_tiled_fn()) {
+    CUtensorMap tmA, tmB;
+    const bool a_ok = make_operand_map(fn, &tmA, g.A, g.lda, g.a_rows, g.a_cols, (MODE == W_WGRAD) ? 64 : 128);
+    const bool b_ok = make_operand_map(fn, &tmB, g.B, g.ldb, g.b_rows, g.b_cols, (MODE == W_FWD) ? 128 : 64);
+    if (a_ok && b_ok) {
+      static bool attr2_done = false;
+      if (!attr2_done) {
+        NERFCA_CUDA_OK(cudaFuncSetAttribute(wide_gemm2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
+        attr2_done = true;
+      }
+      const int n_mt = (int)((g.M + 127) / 128), n_nt = (g.N + 127) / 128;
+      const long long total = (long long)n_mt * n_nt * splits;
+      const unsigned grid2 = (unsigned)(total < wide_sm_count() ? total : wide_sm_count());
+      wide_gemm2_kernel<MODE><<<grid2, W2_THREADS, W2_SMEM, st>>>(tmA, tmB, g, n_mt, n_nt, (int)splits);
+      NERFCA_LAUNCH_OK();
+      return NERFCA_OK;
+    }
+  }
   dim3 grid((unsigned)((g.M + 127) / 128), (unsigned)((g.N + 127) / 128), (unsigned)splits);
   wide_gemm_kernel<MODE><<<grid, 256, W_SMEM, st>>>(g);
   NERFCA_LAUNCH_OK();
