@@ -5,17 +5,21 @@
 // GEMM + masked dgrad GEMM per layer), but
 //   * activations and gradients live in HBM as bf16 ROW-MAJOR matrices [samples, features] (half the traffic of the fp32 path),
 //     the weights are converted to bf16 row-major copies once per call,
-//   * every GEMM is one kernel template, wide_gemm_kernel<MODE>: 128 x 128 output tile per CTA, fp32 accumulator in tensor memory
-//     (128 columns), operands staged through a 3-stage ring of 32 KB shared-memory stages by 16-byte cp.async copies straight into the
-//     UMMA no-swizzle canonical layout (tc_common.cuh) -- a [128 rows x 64 cols] block of a row-major matrix is copied chunk by
-//     chunk, and depending on which matrix dimension is the reduction the SAME bytes are described K-major (rows = M/N index) or
-//     MN-major (rows = reduction index), so no operand is ever transposed:
+//   * every GEMM is one kernel template with three modes
 //         forward   C = relu(A W^T + b)   A K-major,  W K-major     (reduction along the contiguous dimension of both)
-//         dgrad     C = (A W) * 1[h > 0]  A K-major,  W MN-major
-//         wgrad     C += A^T H            A MN-major, H MN-major    (reduction = samples, split over blockIdx.z, fp32 atomics)
-//   * one elected thread issues tcgen05.mma (M128 N128 K16, kind::f16) per stage and commits to the stage's mbarrier; the epilogue
-//     reads the accumulator with tcgen05.ld (thread = row x column half) and writes bf16 rows / fp32 atomics.
-// Two CTAs fit per SM (98 KB shared memory, 128 TMEM columns each), which is what hides the copy latency.
+//         dgrad     C = (A W) * 1[h > 0]  A K-major,  W MN-major    (+ the column sums of C = the next bias gradient)
+//         wgrad     C += A^T H            A MN-major, H MN-major    (reduction = samples, split over tiles, fp32 vector reductions)
+//     wide_gemm2_kernel<MODE> (the default): persistent, one CTA per SM, 128 x 128 output tiles, warp-specialised -- one lane feeds a
+//     5-stage ring of 32 KB stages with 128-byte-swizzled tensor-map copies (TMA), one lane issues tcgen05.mma (M128 N128 K16,
+//     kind::f16) into one of two TMEM accumulators, 8 epilogue warps drain the other (tcgen05.ld -> bias / ReLU / mask -> padded
+//     shared-memory tile -> full-line global stores).  Depending on which matrix dimension is the reduction the same row-major bytes
+//     are loaded as a K-major block (one 64 x 128 box) or an MN-major block (two 64 x 64 boxes), so no operand is ever transposed.
+//     wide_gemm_kernel<MODE> (fallback when the driver has no cuTensorMapEncodeTiled, or NERFCA_WIDE_TMA=0): one tile per CTA,
+//     operands staged by 16-byte cp.async copies straight into the UMMA no-swizzle canonical layout (tc_common.cuh), 3-stage ring.
+//   * the small kernels around the GEMMs (encoder: one thread per sample; output layer forward / backward; latent-gradient scatter)
+//     are single passes over their bf16 matrix.
+// Config 5 (1024 rays x 256 samples, hidden 256, 16 bands): 2.6 ms per step = 19 % of the tensor roofline (the per-thread cp.async version
+// of round 2a: 7.7 ms); the GEMMs run at 60-105 us against an HBM bound of 41-62 us per 262144 x 256 x 256 layer.
 //
 // Reference: model/CPPN.py:88-110, model/Temporal.py:113-151 and their autograd.
 #include <cuda.h>
@@ -43,9 +47,13 @@ struct WideGemm {
   bf16* C; long long ldc;                             // W_FWD / W_DGRAD output (bf16 rows)
   const float* bias;                                  // W_FWD: [N] or null
   const bf16* mask; long long ldm;                    // W_DGRAD: gradient passes where mask > 0 (same shape as C)
+  float* colsum;                                      // W_DGRAD (persistent kernel only), optional: [N] += column sums of the bf16 output (the next bias gradient)
   float* C32; long long ldc32;                        // W_WGRAD output (fp32, atomically accumulated)
   long long k_split;                                  // W_WGRAD: reduction elements per blockIdx.z (multiple of 64)
 };
+
+constexpr int W_ROWS_PER_BLOCK = 128;
+__global__ void wide_colsum_kernel(const bf16* __restrict__ dz, long long np, int H, float* __restrict__ db);
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -205,7 +213,8 @@ constexpr int W2_STAGES = 5;
 constexpr int W2_THREADS = 10 * 32;
 constexpr uint32_t W2_ROW_BYTES = 272;                 // one staged output row: 128 bf16 + 16 B of padding (conflict-free 16-byte accesses by row AND by column)
 constexpr uint32_t W2_STAGING = 128 * W2_ROW_BYTES;
-constexpr size_t W2_SMEM = (size_t)W2_STAGES * W_STAGE_BYTES + W2_STAGING + (2 * W2_STAGES + 4) * 8 + 16;
+constexpr uint32_t W2_CS_BYTES = 8 * 128 * 4;          // column-sum exchange: [8 row parts][128 columns] fp32
+constexpr size_t W2_SMEM = (size_t)W2_STAGES * W_STAGE_BYTES + W2_STAGING + W2_CS_BYTES + (2 * W2_STAGES + 4) * 8 + 16;
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int col, int row, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -228,7 +237,8 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wide_gemm2_kernel(const __grid_
                                                                    WideGemm g, int n_mt, int n_nt, int n_sp) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + (size_t)W2_STAGES * W_STAGE_BYTES + W2_STAGING);
+  [[maybe_unused]] float* s_cs = reinterpret_cast<float*>(smem + (size_t)W2_STAGES * W_STAGE_BYTES + W2_STAGING);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + (size_t)W2_STAGES * W_STAGE_BYTES + W2_STAGING + W2_CS_BYTES);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * W2_STAGES + 4);
   [[maybe_unused]] const uint32_t s_out = smem_u32(smem) + W2_STAGES * W_STAGE_BYTES;   // staged output tile (and, W_DGRAD, the mask tile before it)
   const uint32_t full0 = smem_u32(s_bar), empty0 = full0 + 8 * W2_STAGES, accf0 = empty0 + 8 * W2_STAGES, acce0 = accf0 + 16;
@@ -316,6 +326,8 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wide_gemm2_kernel(const __grid_
     const int te = (int)threadIdx.x - 64;                     // 0 .. 255 among the epilogue threads
     const int c_row = te >> 4, c_col = te & 15;               // coalesced side: rows c_row + 16 k, 16-byte piece c_col
     const uint32_t my_row = s_out + (uint32_t)row * W2_ROW_BYTES + (uint32_t)(ch * 8) * 16u;
+    float cs_acc = 0.f;                                       // running column sum of column (cs_n0 + te), te < 128, over this CTA's tiles
+    int cs_n0 = -1;
     uint32_t tl = 0;
     for (long long t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
       long long m0, kbeg, kend; int n0;
@@ -391,6 +403,28 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wide_gemm2_kernel(const __grid_
       if (lane == 0) mbar_arrive(acce0 + 8 * b);             // the accumulator has been read: the MMA lane may start the tile after next
       if (MODE != W_WGRAD) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (MODE == W_DGRAD && g.colsum) {
+          // column sums of the staged tile (rows beyond M are zero): thread = (16-row part, 4 columns), then 128 threads add the 8 parts
+          const int rpart = te >> 5, col4 = te & 31;
+          float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            uint32_t lo, hi;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(s_out + (uint32_t)(rpart * 16 + k) * W2_ROW_BYTES + (uint32_t)col4 * 8u) : "memory");
+            p0 += __uint_as_float(lo << 16); p1 += __uint_as_float(lo & 0xFFFF0000u);
+            p2 += __uint_as_float(hi << 16); p3 += __uint_as_float(hi & 0xFFFF0000u);
+          }
+          *reinterpret_cast<float4*>(s_cs + rpart * 128 + col4 * 4) = make_float4(p0, p1, p2, p3);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (te < 128) {
+            if (n0 != cs_n0) {
+              if (cs_n0 >= 0 && cs_n0 + te < g.N) atomicAdd(g.colsum + cs_n0 + te, cs_acc);
+              cs_n0 = n0; cs_acc = 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cs_acc += s_cs[k * 128 + te];
+          }
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const long long r = m0 + c_row + 16 * k;
@@ -403,6 +437,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wide_gemm2_kernel(const __grid_
         asm volatile("bar.sync 1, 256;" ::: "memory");       // the staged tile has been read: the next tile may overwrite it
       }
     }
+    if (MODE == W_DGRAD && g.colsum && te < 128 && cs_n0 >= 0 && cs_n0 + te < g.N) atomicAdd(g.colsum + cs_n0 + te, cs_acc);
   }
   tc_fence_before();
   __syncthreads();
@@ -477,32 +512,48 @@ static int run_wide_gemm(const WideGemm& g, cudaStream_t st) {
   dim3 grid((unsigned)((g.M + 127) / 128), (unsigned)((g.N + 127) / 128), (unsigned)splits);
   wide_gemm_kernel<MODE><<<grid, 256, W_SMEM, st>>>(g);
   NERFCA_LAUNCH_OK();
+  if (MODE == W_DGRAD && g.colsum) {
+    wide_colsum_kernel<<<div_up(g.M, W_ROWS_PER_BLOCK), 128, 0, st>>>(g.C, g.M, g.N, g.colsum);
+    NERFCA_LAUNCH_OK();
+  }
   return NERFCA_OK;
 }
 
 // ---- small kernels around the GEMMs (bf16 row-major activations) --------------------------------------------------------------------
-// first-layer input [np, Dp] bf16 (A4 + A5 in registers, zero padded to Dp = roundup8(in_dim)): one thread per (sample, feature)
+// first-layer input [np, Dp] bf16 (A4 + A5 in registers, zero padded to Dp = roundup8(in_dim)): one thread per sample -- the point
+// (float64 ray algebra) and the phase are formed once, the row leaves in 16-byte pieces.  (One thread per (sample, feature) re-derived
+// the point for every feature: 194 us per field at config 5.)
 __global__ void wide_encode_kernel(SampleSrc src, EncDesc enc, int Dp, bf16* __restrict__ out) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = src.n_points * Dp;
-  if (idx >= total) return;
-  const long long p = idx / Dp;
-  const int f = (int)(idx - p * Dp);
-  float v = 0.f;
-  if (f < enc.in_dim) {
-    float x, y, z;
-    load_point(src, p, x, y, z);
-    const int phase = (f >= enc.enc_dim) ? load_phase(src, p) : 0;
-    v = enc_feature(enc, f, x, y, z, phase);
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= src.n_points) return;
+  float x, y, z;
+  load_point(src, p, x, y, z);
+  const int phase = (enc.n_latent > 0) ? load_phase(src, p) : 0;
+  uint4* dst = reinterpret_cast<uint4*>(out + p * Dp);
+  for (int c = 0; c < Dp / 8; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int f0 = c * 8 + 2 * j;
+      const float a = (f0 < enc.in_dim) ? enc_feature(enc, f0, x, y, z, phase) : 0.f;
+      const float b = (f0 + 1 < enc.in_dim) ? enc_feature(enc, f0 + 1, x, y, z, phase) : 0.f;
+      w[j] = pack_bf16x2(a, b);
+    }
+    dst[c] = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  out[idx] = __float2bfloat16_rn(v);
 }
-// W fp32 [rows, K] -> bf16 [rows, Kp] (zero padded)
-__global__ void wide_cvt_weight_kernel(const float* __restrict__ w, int rows, int K, int Kp, bf16* __restrict__ out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * Kp) return;
-  const int r = idx / Kp, k = idx - r * Kp;
-  out[idx] = __float2bfloat16_rn(k < K ? __ldg(w + (size_t)r * K + k) : 0.f);
+// every layer's W fp32 [H, K_l] -> bf16 [H, Kp_l] (zero padded), back to back: layer 0 is [H, Dp], the others [H, H]
+struct WideWeights { const float* w[NERFCA_MAX_LAYERS]; };
+__global__ void wide_cvt_weight_kernel(WideWeights ws, int H, int D, int Dp, int L, bf16* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n0 = (long long)H * Dp;
+  if (idx >= n0 + (long long)(L - 1) * H * H) return;
+  int l, K, Kp;
+  long long e;
+  if (idx < n0) { l = 0; K = D; Kp = Dp; e = idx; }
+  else { l = 1 + (int)((idx - n0) / ((long long)H * H)); K = Kp = H; e = (idx - n0) % ((long long)H * H); }
+  const int r = (int)(e / Kp), k = (int)(e - (long long)r * Kp);
+  out[idx] = __float2bfloat16_rn(k < K ? __ldg(ws.w[l] + (size_t)r * K + k) : 0.f);
 }
 // output layer (hidden -> 1): one warp per sample
 __global__ void wide_out_forward_kernel(const bf16* __restrict__ h, const float* __restrict__ w, const float* __restrict__ b, long long np, int H,
@@ -517,21 +568,23 @@ __global__ void wide_out_forward_kernel(const bf16* __restrict__ h, const float*
   if (lane == 0) raw[row] = acc + (b ? __ldg(b) : 0.f);
 }
 // backward of the output layer: dZ[p,k] = d_raw[p] w[k] 1[h>0];  dW[k] += sum_p d_raw[p] h[p,k];  db += sum_p d_raw[p]
-constexpr int W_ROWS_PER_BLOCK = 128;
 __global__ void wide_out_backward_kernel(const float* __restrict__ d_raw, const bf16* __restrict__ h, const float* __restrict__ w, long long np, int H,
-                                         bf16* __restrict__ dz, float* __restrict__ dw, float* __restrict__ db) {
+                                         bf16* __restrict__ dz, float* __restrict__ dw, float* __restrict__ db, float* __restrict__ db_prev) {
   const long long r0 = (long long)blockIdx.x * W_ROWS_PER_BLOCK;
   const long long r1 = (r0 + W_ROWS_PER_BLOCK < np) ? r0 + W_ROWS_PER_BLOCK : np;
   for (int k = threadIdx.x; k < H; k += blockDim.x) {
     const float wk = __ldg(w + k);
-    float aw = 0.f, ab = 0.f;
+    float aw = 0.f, ab = 0.f, az = 0.f;
     for (long long r = r0; r < r1; ++r) {
       const float g = __ldg(d_raw + r), hv = __bfloat162float(h[r * H + k]);
-      dz[r * H + k] = __float2bfloat16_rn(hv > 0.f ? g * wk : 0.f);
+      const bf16 z = __float2bfloat16_rn(hv > 0.f ? g * wk : 0.f);
+      dz[r * H + k] = z;
+      az += __bfloat162float(z);            // bias gradient of the last hidden layer = column sums of the (rounded) dZ
       aw = fmaf(g, hv, aw);
       ab += g;
     }
     atomicAdd(dw + k, aw);
+    if (db_prev) atomicAdd(db_prev + k, az);
     if (k == 0 && db) atomicAdd(db, ab);
   }
 }
@@ -546,22 +599,90 @@ __global__ void wide_colsum_kernel(const bf16* __restrict__ dz, long long np, in
   }
 }
 // d time_latents[phase[p], t] += sum_n dz0[p,n] W0[n, enc_dim + t]   (scatter-add of Temporal.py:144-147's gather)
-__global__ void wide_latent_grad_kernel(const bf16* __restrict__ dz0, const float* __restrict__ w0, SampleSrc src, int H, int D, int enc_dim, int T,
-                                        int n_phases, int use_smem, float* __restrict__ dlat) {
-  extern __shared__ float sacc[];  // [n_phases * T] when use_smem
-  if (use_smem) {
+// A skinny GEMM [np x H] x [H x T] followed by a scatter by phase, bound by the one pass over dz0: a warp walks 32 consecutive samples,
+// lane = 8 consecutive columns of the row (16-byte loads, 512 contiguous bytes per warp and row), the latent columns of W0 sit in shared
+// memory as [H][T] fp32.  Consecutive samples belong to the same ray and hence the same phase almost always, so the lanes keep private
+// partial sums while the phase does not change and only then reduce over the warp (shuffles) and add to the block's [phase][t] table.
+constexpr int WL_ROWS_PER_WARP = 32;
+constexpr int WL_MAX_T = 16;
+__global__ void __launch_bounds__(256) wide_latent_grad_kernel(const bf16* __restrict__ dz0, const float* __restrict__ w0, SampleSrc src, int H, int D,
+                                                               int enc_dim, int T, int n_phases, int use_smem, float* __restrict__ dlat) {
+  extern __shared__ float wl_smem[];        // [roundup256(H) * T] latent columns of W0, then (use_smem) [n_phases * T] accumulators
+  float* s_w = wl_smem;
+  float* sacc = wl_smem + ((H + 255) & ~255) * T;
+  // W0's latent columns, laid out so that the 32 lanes of a warp (lane = columns 8 lane .. 8 lane + 7 of a 256-column group) read 32
+  // consecutive words: word(n, t) = (n / 256) * 256 T + (8 t + n % 8) * 32 + (n / 8) % 32
+  for (int i = threadIdx.x; i < H * T; i += blockDim.x) {
+    const int n = i / T, t = i - n * T;
+    s_w[(n >> 8) * (T << 8) + (((t << 3) + (n & 7)) << 5) + ((n >> 3) & 31)] = __ldg(w0 + (size_t)n * D + enc_dim + t);
+  }
+  if (use_smem)
     for (int i = threadIdx.x; i < n_phases * T; i += blockDim.x) sacc[i] = 0.f;
-    __syncthreads();
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * WL_ROWS_PER_WARP;
+  float acc[WL_MAX_T];
+#pragma unroll
+  for (int t = 0; t < WL_MAX_T; ++t) acc[t] = 0.f;
+  int cur = -1;
+  auto flush = [&]() {
+    if (cur >= 0 && cur < n_phases) {
+#pragma unroll
+      for (int t = 0; t < WL_MAX_T; ++t) {
+        if (t < T) {
+          float v = acc[t];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) atomicAdd(use_smem ? &sacc[cur * T + t] : dlat + (size_t)cur * T + t, v);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < WL_MAX_T; ++t) acc[t] = 0.f;
+  };
+  if (H <= 256 && T <= 8) {
+    // common case (config 5: H = 256, T = 8): the lane's 8 x T slice of W0 lives in registers
+    float wreg[8][8];
+    const bool live = lane * 8 < H;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) wreg[e][t] = (live && t < T) ? s_w[(((t << 3) + e) << 5) + lane] : 0.f;
+    for (int k = 0; k < WL_ROWS_PER_WARP; ++k) {
+      const long long p = r0 + k;
+      if (p >= src.n_points) break;
+      const int ph = load_phase(src, p);           // warp-uniform
+      if (ph != cur) { flush(); cur = ph; }
+      if (!live) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(dz0 + p * H + lane * 8));
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = __uint_as_float((e & 1) ? (w4[e >> 1] & 0xFFFF0000u) : (w4[e >> 1] << 16));
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = fmaf(d, wreg[e][t], acc[t]);
+      }
+    }
+  } else
+  for (int k = 0; k < WL_ROWS_PER_WARP; ++k) {
+    const long long p = r0 + k;
+    if (p >= src.n_points) break;
+    const int ph = load_phase(src, p);           // warp-uniform
+    if (ph != cur) { flush(); cur = ph; }
+    for (int c = lane * 8; c < H; c += 256) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(dz0 + p * H + c));
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = __uint_as_float((e & 1) ? (w4[e >> 1] & 0xFFFF0000u) : (w4[e >> 1] << 16));
+        const float* wr = s_w + (c >> 8) * (T << 8) + (e << 5) + lane;
+#pragma unroll
+        for (int t = 0; t < WL_MAX_T; ++t)
+          if (t < T) acc[t] = fmaf(d, wr[t << 8], acc[t]);
+      }
+    }
   }
-  const int per_block = blockDim.x / T;
-  const int local = threadIdx.x / T, tt = threadIdx.x - local * T;
-  const long long p = (long long)blockIdx.x * per_block + local;
-  if (local < per_block && p < src.n_points) {
-    float a = 0.f;
-    for (int n = 0; n < H; ++n) a = fmaf(__bfloat162float(dz0[p * H + n]), __ldg(w0 + (size_t)n * D + enc_dim + tt), a);
-    const int ph = load_phase(src, p);
-    if (ph >= 0 && ph < n_phases) atomicAdd(use_smem ? &sacc[ph * T + tt] : dlat + (size_t)ph * T + tt, a);
-  }
+  flush();
   if (!use_smem) return;
   __syncthreads();
   for (int i = threadIdx.x; i < n_phases * T; i += blockDim.x)
@@ -594,13 +715,10 @@ size_t wide_workspace_bytes(const nerfca_field_t& f, long long P, int backward) 
 
 static int wide_convert_weights(const nerfca_field_t& f, bf16* wb, cudaStream_t st) {
   const int D = in_dim_of(f), Dp = pad8(D), H = f.hidden, L = f.n_hidden + 1;
-  size_t off = 0;
-  for (int l = 0; l < L; ++l) {
-    const int K = l ? H : D, Kp = l ? H : Dp;
-    wide_cvt_weight_kernel<<<div_up((long long)H * Kp, 256), 256, 0, st>>>(f.weight[l], H, K, Kp, wb + off);
-    NERFCA_LAUNCH_OK();
-    off += (size_t)H * Kp;
-  }
+  WideWeights ws;
+  for (int l = 0; l < NERFCA_MAX_LAYERS; ++l) ws.w[l] = f.weight[l];
+  wide_cvt_weight_kernel<<<div_up((long long)H * Dp + (long long)(L - 1) * H * H, 256), 256, 0, st>>>(ws, H, D, Dp, L, wb);
+  NERFCA_LAUNCH_OK();
   return NERFCA_OK;
 }
 static const bf16* wide_weight(const nerfca_field_t& f, const bf16* wb, int l) {
@@ -623,7 +741,7 @@ int wide_field_forward(const nerfca_field_t& f, const nerfca_samples_t& s, float
     const long long ch = P < WIDE_CHUNK ? P : WIDE_CHUNK;
     bf16* x0 = stash ? st_x0 + (size_t)c0 * Dp : scratch;
     bf16* ping[2] = {scratch + (size_t)ch * Dp, scratch + (size_t)ch * Dp + (size_t)ch * H};
-    wide_encode_kernel<<<div_up(np * Dp, 256), 256, 0, st>>>(make_src(s, c0, np), enc, Dp, x0);
+    wide_encode_kernel<<<div_up(np, 128), 128, 0, st>>>(make_src(s, c0, np), enc, Dp, x0);
     NERFCA_LAUNCH_OK();
     const bf16* in = x0;
     int Kp = Dp;
@@ -660,7 +778,8 @@ int wide_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, cons
     const long long np = (P - c0 < WIDE_CHUNK) ? P - c0 : WIDE_CHUNK;
     const unsigned rb = div_up(np, W_ROWS_PER_BLOCK);
     const bf16* h_last = st_h + ((size_t)(L - 1) * P + c0) * H;
-    wide_out_backward_kernel<<<rb, 128, 0, st>>>(d_raw + c0, h_last, f.weight[L], np, H, X, gr.weight[L], gr.bias[L]);
+    // (every kernel that produces a dZ also accumulates its column sums = the bias gradient of that layer)
+    wide_out_backward_kernel<<<rb, 128, 0, st>>>(d_raw + c0, h_last, f.weight[L], np, H, X, gr.weight[L], gr.bias[L], gr.bias[L - 1]);
     NERFCA_LAUNCH_OK();
     for (int l = L - 1; l >= 0; --l) {
       const bf16* h_prev = (l > 0) ? st_h + ((size_t)(l - 1) * P + c0) * H : st_x0 + (size_t)c0 * Dp;
@@ -674,27 +793,24 @@ int wide_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, cons
         rc = run_wide_gemm<W_WGRAD>(g, st);
         if (rc) return rc;
       }
-      if (gr.bias[l]) {
-        wide_colsum_kernel<<<rb, 128, 0, st>>>(X, np, H, gr.bias[l]);
-        NERFCA_LAUNCH_OK();
-      }
       if (l > 0) {  // dgrad: Y[p, k] = (sum_n X[p, n] W_l[n, k]) * 1[h_prev[p,k] > 0]
         WideGemm g{};
         g.A = X; g.lda = H; g.a_rows = np; g.a_cols = H;
         g.B = wide_weight(f, wb, l); g.ldb = H; g.b_rows = H; g.b_cols = H;
         g.M = np; g.N = H; g.K = H;
-        g.C = Y; g.ldc = H; g.mask = h_prev; g.ldm = H;
+        g.C = Y; g.ldc = H; g.mask = h_prev; g.ldm = H; g.colsum = gr.bias[l - 1];
         rc = run_wide_gemm<W_DGRAD>(g, st);
         if (rc) return rc;
         bf16* tmp = X; X = Y; Y = tmp;
       } else if (f.n_latent > 0 && gr.latents) {
         const int T = f.n_latent;
-        const int threads = (256 / T) * T;
-        const int per_block = threads / T;
-        const int use_smem = (size_t)f.n_phases * T * sizeof(float) <= 32 * 1024;
-        const size_t smem = use_smem ? (size_t)f.n_phases * T * sizeof(float) : 0;
-        wide_latent_grad_kernel<<<div_up(np, per_block), threads, smem, st>>>(X, f.weight[0], make_src(s, c0, np), H, D, enc_dim_of(f), T,
-                                                                            f.n_phases, use_smem, gr.latents);
+        NERFCA_REQUIRE(T <= WL_MAX_T, NERFCA_E_UNSUPPORTED, "bf16 layer-wise path: more than 16 latent dims (use precision fp32)");
+        const size_t w_bytes = (size_t)((H + 255) & ~255) * T * sizeof(float), acc_bytes = (size_t)f.n_phases * T * sizeof(float);
+        const int use_smem = w_bytes + acc_bytes <= 40 * 1024;
+        NERFCA_REQUIRE(w_bytes <= 40 * 1024, NERFCA_E_UNSUPPORTED, "bf16 layer-wise path: hidden x latent dims too large for the latent-gradient kernel");
+        const size_t smem = w_bytes + (use_smem ? acc_bytes : 0);
+        wide_latent_grad_kernel<<<div_up(np, 8 * WL_ROWS_PER_WARP), 256, smem, st>>>(X, f.weight[0], make_src(s, c0, np), H, D, enc_dim_of(f), T,
+                                                                                  f.n_phases, use_smem, gr.latents);
         NERFCA_LAUNCH_OK();
       }
     }
