@@ -763,6 +763,22 @@ def test_layerwise_tensor_core_path_other_shapes():
     assert res["grad_cos_min"] >= parity.TOL["bf16"]["grad_cos"]
 
 
+def test_layerwise_path_cp_async_fallback_kernel():
+    """The same two shape families through the fallback GEMM kernel of csrc/mlp_wide.cu (NERFCA_WIDE_TMA=0: per-thread cp.async copies
+    instead of tensor-map copies; what a driver without cuTensorMapEncodeTiled gets).  The switch is read once per process, so the
+    checks run in a child interpreter."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NERFCA_WIDE_TMA="0")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests"), "-m", "gpu", "-q", "-x", "-k",
+                          "config5_widened_stress_shapes and bf16 or layerwise_tensor_core_path_other_shapes"], capture_output=True, text=True,
+                         timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "2 passed" in out.stdout
+
+
 # ---- (e) multi-GPU: gradient sum fused with the optimizer step over peer memory (needs >= 2 GPUs; skipped on a one-GPU box) -------
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
