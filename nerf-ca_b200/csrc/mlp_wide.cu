@@ -209,12 +209,20 @@ __global__ void __launch_bounds__(256) wide_gemm_kernel(WideGemm g) {
 // the stage's "empty" and the accumulator's "full" mbarriers.  Warps 2-9: epilogue of the OTHER accumulator meanwhile.  Six 32 KB
 // stages keep ~190 KB of loads in flight per SM; the per-thread cp.async version above had 64 KB and a CTA-wide barrier + proxy
 // fence per K block (r5w: 250 us per 262144 x 256 x 256 GEMM, tensor pipe 6.5 %).
-constexpr int W2_STAGES = 5;
+// operand stages per mode: what the mask / output tiles leave of the shared memory (dgrad: 3 stages + 2 mask tiles + output tile,
+// forward: 5 stages + output tile, wgrad: 6 stages)
+__host__ __device__ constexpr int w2_stages(int mode) { return mode == W_DGRAD ? 3 : (mode == W_FWD ? 5 : 6); }
 constexpr int W2_THREADS = 10 * 32;
-constexpr uint32_t W2_ROW_BYTES = 272;                 // one staged output row: 128 bf16 + 16 B of padding (conflict-free 16-byte accesses by row AND by column)
-constexpr uint32_t W2_STAGING = 128 * W2_ROW_BYTES;
+// [128 x 128] bf16 tiles that enter or leave through the copy engine: two 64-column halves of [128 rows x 128 B], 128-byte swizzle (the
+// 16-byte chunk j of row r sits at r * 128 + ((j ^ (r & 7)) << 4)): conflict-free for a thread that owns a row, and what a box of the tensor map is
+constexpr uint32_t W2_IO_TILE = 32768;
+__host__ __device__ constexpr uint32_t w2_io_bytes(int mode) {   // ReLU-mask tiles of the next two tiles (W_DGRAD) + the staged output tile
+  return mode == W_DGRAD ? 3 * W2_IO_TILE : (mode == W_FWD ? W2_IO_TILE : 0);
+}
 constexpr uint32_t W2_CS_BYTES = 8 * 128 * 4;          // column-sum exchange: [8 row parts][128 columns] fp32
-constexpr size_t W2_SMEM = (size_t)W2_STAGES * W_STAGE_BYTES + W2_STAGING + W2_CS_BYTES + (2 * W2_STAGES + 4) * 8 + 16;
+__host__ __device__ constexpr size_t w2_smem(int mode) {
+  return (size_t)w2_stages(mode) * W_STAGE_BYTES + w2_io_bytes(mode) + W2_CS_BYTES + (2 * w2_stages(mode) + 8) * 8 + 16;
+}
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int col, int row, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -223,6 +231,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
 }
 // operand block at (row0, col0) of a row-major matrix: K-major = [128 rows x 64 reduction cols] in one box, MN-major = [64 reduction rows x
 // 128 cols] as two 64-column boxes 8 KB apart
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int col, int row) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(col), "r"(row)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t io_chunk(uint32_t tile, int row, int half, int j) {
+  return tile + (uint32_t)half * 16384u + (uint32_t)row * 128u + ((uint32_t)(j ^ (row & 7)) << 4);
+}
 __device__ __forceinline__ void load_kmajor(uint32_t dst, const CUtensorMap* tm, int row0, int col0, uint32_t bar) { tma_load_2d(dst, tm, col0, row0, bar); }
 __device__ __forceinline__ void load_mnmajor(uint32_t dst, const CUtensorMap* tm, int row0, int col0, uint32_t bar) {
   tma_load_2d(dst, tm, col0, row0, bar);
@@ -234,18 +250,23 @@ __device__ __forceinline__ uint64_t desc_sw128_mn(uint32_t base, int kk) { retur
 
 template <int MODE>
 __global__ void __launch_bounds__(W2_THREADS, 1) wide_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmM,
                                                                    WideGemm g, int n_mt, int n_nt, int n_sp) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int W2_STAGES = w2_stages(MODE);
+  constexpr uint32_t W2_IO_BYTES = w2_io_bytes(MODE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  [[maybe_unused]] float* s_cs = reinterpret_cast<float*>(smem + (size_t)W2_STAGES * W_STAGE_BYTES + W2_STAGING);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + (size_t)W2_STAGES * W_STAGE_BYTES + W2_STAGING + W2_CS_BYTES);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * W2_STAGES + 4);
-  [[maybe_unused]] const uint32_t s_out = smem_u32(smem) + W2_STAGES * W_STAGE_BYTES;   // staged output tile (and, W_DGRAD, the mask tile before it)
+  [[maybe_unused]] float* s_cs = reinterpret_cast<float*>(smem + (size_t)W2_STAGES * W_STAGE_BYTES + W2_IO_BYTES);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + (size_t)W2_STAGES * W_STAGE_BYTES + W2_IO_BYTES + W2_CS_BYTES);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * W2_STAGES + 8);
+  [[maybe_unused]] const uint32_t s_mask = smem_u32(smem) + W2_STAGES * W_STAGE_BYTES;  // two ReLU-mask tiles (W_DGRAD), filled by the loader lane
+  [[maybe_unused]] const uint32_t s_out = s_mask + (MODE == W_DGRAD ? 2 * W2_IO_TILE : 0);   // staged output tile, drained by a tensor-map store
   const uint32_t full0 = smem_u32(s_bar), empty0 = full0 + 8 * W2_STAGES, accf0 = empty0 + 8 * W2_STAGES, acce0 = accf0 + 16;
+  [[maybe_unused]] const uint32_t mfull0 = acce0 + 16, mempty0 = mfull0 + 16;
   if (warp == 0) {
     if (lane == 0) {
       for (int s = 0; s < W2_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 8); }
+      for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 8); mbar_init(mfull0 + 8 * b, 1); mbar_init(mempty0 + 8 * b, 8); }
       mbar_init_fence();
     }
     __syncwarp();
@@ -269,11 +290,18 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wide_gemm2_kernel(const __grid_
 
   if (warp == 0) {
     if (lane == 0) {   // ================= operand loads =================
-      uint32_t it = 0;
-      for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+      uint32_t it = 0, tl = 0;
+      for (long long t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
         long long m0, kbeg, kend; int n0;
         k_range(t, m0, n0, kbeg, kend);
         const int nkb = (int)((kend - kbeg + 63) / 64);
+        if (MODE == W_DGRAD) {      // the tile's ReLU-mask tile (two buffers: the epilogue released this one two tiles ago)
+          const uint32_t b = tl & 1;
+          if (tl >= 2) mbar_wait(mempty0 + 8 * b, ((tl >> 1) - 1) & 1);
+          mbar_expect_tx(mfull0 + 8 * b, W2_IO_TILE);
+          tma_load_2d(s_mask + b * W2_IO_TILE, &tmM, n0, (int)m0, mfull0 + 8 * b);
+          tma_load_2d(s_mask + b * W2_IO_TILE + 16384u, &tmM, n0 + 64, (int)m0, mfull0 + 8 * b);
+        }
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const uint32_t s = it % W2_STAGES;
           if (it >= W2_STAGES) mbar_wait(empty0 + 8 * s, ((it / W2_STAGES) - 1) & 1);   // the MMAs that read the stage's previous block are done
@@ -317,15 +345,13 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wide_gemm2_kernel(const __grid_
     }
   } else {
     // ================= epilogue: thread = (accumulator row, column half); warps 2-9 cover the four TMEM lane quadrants twice.  A thread
-    // owns a ROW of the tile, so its global accesses would touch 32 different lines per warp instruction; rows are therefore exchanged
-    // through a padded shared-memory tile and the global side runs 16 threads per 256-byte row segment (full lines): the ReLU-mask tile
-    // on the way in (W_DGRAD), the bf16 output tile on the way out.  (The fp32 weight-gradient tiles -- 512 per GEMM instead of 4096 --
+    // owns a ROW of the tile, so direct global accesses would touch 32 different lines per warp instruction: the ReLU-mask tile
+    // (W_DGRAD) therefore comes in, and the bf16 output tile goes out, through the copy engine and a 128-byte-swizzled shared-memory
+    // tile in which a row's eight 16-byte chunks are conflict-free.  (The fp32 weight-gradient tiles -- 512 per GEMM instead of 4096 --
     // go out as vector reductions straight from the registers.) =================
     const int q = warp & 3, ch = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int te = (int)threadIdx.x - 64;                     // 0 .. 255 among the epilogue threads
-    const int c_row = te >> 4, c_col = te & 15;               // coalesced side: rows c_row + 16 k, 16-byte piece c_col
-    const uint32_t my_row = s_out + (uint32_t)row * W2_ROW_BYTES + (uint32_t)(ch * 8) * 16u;
     float cs_acc = 0.f;                                       // running column sum of column (cs_n0 + te), te < 128, over this CTA's tiles
     int cs_n0 = -1;
     uint32_t tl = 0;
@@ -336,22 +362,20 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wide_gemm2_kernel(const __grid_
       const long long m = m0 + row;
       uint4 hmask[8];
       if (MODE == W_DGRAD) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const long long r = m0 + c_row + 16 * k;
-          const int n = n0 + c_col * 8;
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (r < g.M && n < g.N) v = __ldg(reinterpret_cast<const uint4*>(g.mask + r * g.ldm + n));
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(s_out + (uint32_t)(c_row + 16 * k) * W2_ROW_BYTES + (uint32_t)c_col * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_wait(mfull0 + 8 * b, (tl >> 1) & 1);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hmask[j].x), "=r"(hmask[j].y), "=r"(hmask[j].z), "=r"(hmask[j].w) : "r"(my_row + (uint32_t)j * 16u) : "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hmask[j].x), "=r"(hmask[j].y), "=r"(hmask[j].z), "=r"(hmask[j].w)
+                       : "r"(io_chunk(s_mask + b * W2_IO_TILE, row, ch, j)) : "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mempty0 + 8 * b);          // the loader lane may fetch the mask of the tile after next
       }
       mbar_wait(accf0 + 8 * b, (tl >> 1) & 1);
       tc_fence_after();
+      if (MODE != W_WGRAD) {
+        if (te == 0) bulk_wait_read_all();                     // the previous tile's store has drained the staged tile
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
@@ -394,7 +418,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wide_gemm2_kernel(const __grid_
               o = make_uint4(mul_bf16x2(pack_bf16x2(f[0], f[1]), relu_mask_bf16x2(h.x)), mul_bf16x2(pack_bf16x2(f[2], f[3]), relu_mask_bf16x2(h.y)),
                              mul_bf16x2(pack_bf16x2(f[4], f[5]), relu_mask_bf16x2(h.z)), mul_bf16x2(pack_bf16x2(f[6], f[7]), relu_mask_bf16x2(h.w)));
             }
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (uint32_t)(half * 4 + j) * 16u), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(io_chunk(s_out, row, ch, half * 4 + j)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
           }
         }
       }
@@ -402,15 +426,22 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wide_gemm2_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(acce0 + 8 * b);             // the accumulator has been read: the MMA lane may start the tile after next
       if (MODE != W_WGRAD) {
+        fence_proxy_async();                                   // the staged tile is read by the copy engine
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (te == 0) {                                         // rows / columns beyond the matrix are clipped by the store
+          tma_store_2d(&tmC, s_out, n0, (int)m0);
+          tma_store_2d(&tmC, s_out + 16384u, n0 + 64, (int)m0);
+          bulk_commit();
+        }
         if (MODE == W_DGRAD && g.colsum) {
           // column sums of the staged tile (rows beyond M are zero): thread = (16-row part, 4 columns), then 128 threads add the 8 parts
           const int rpart = te >> 5, col4 = te & 31;
           float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
+            const int r = rpart * 16 + k;
             uint32_t lo, hi;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(s_out + (uint32_t)(rpart * 16 + k) * W2_ROW_BYTES + (uint32_t)col4 * 8u) : "memory");
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(io_chunk(s_out, r, col4 >> 4, (col4 & 15) >> 1) + (uint32_t)(col4 & 1) * 8u) : "memory");
             p0 += __uint_as_float(lo << 16); p1 += __uint_as_float(lo & 0xFFFF0000u);
             p2 += __uint_as_float(hi << 16); p3 += __uint_as_float(hi & 0xFFFF0000u);
           }
@@ -425,19 +456,10 @@ __global__ void __launch_bounds__(W2_THREADS, 1) wide_gemm2_kernel(const __grid_
             for (int k = 0; k < 8; ++k) cs_acc += s_cs[k * 128 + te];
           }
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const long long r = m0 + c_row + 16 * k;
-          const int n = n0 + c_col * 8;
-          uint4 v;
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                       : "r"(s_out + (uint32_t)(c_row + 16 * k) * W2_ROW_BYTES + (uint32_t)c_col * 16u) : "memory");
-          if (r < g.M && n < g.N) *reinterpret_cast<uint4*>(g.C + r * g.ldc + n) = v;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");       // the staged tile has been read: the next tile may overwrite it
       }
     }
     if (MODE == W_DGRAD && g.colsum && te < 128 && cs_n0 >= 0 && cs_n0 + te < g.N) atomicAdd(g.colsum + cs_n0 + te, cs_acc);
+    if (MODE != W_WGRAD && te == 0) bulk_wait_all();           // the last store has left shared memory (and reached global memory)
   }
   tc_fence_before();
   __syncthreads();
@@ -493,18 +515,24 @@ static int run_wide_gemm(const WideGemm& g, cudaStream_t st) {
   const long long splits = (MODE == W_WGRAD) ? (g.K + g.k_split - 1) / g.k_split : 1;
   if (EncodeTiledFn fn = encode_tiled_fn()) {
     CUtensorMap tmA, tmB;
+    CUtensorMap tmC, tmM;
     const bool a_ok = make_operand_map(fn, &tmA, g.A, g.lda, g.a_rows, g.a_cols, (MODE == W_WGRAD) ? 64 : 128);
     const bool b_ok = make_operand_map(fn, &tmB, g.B, g.ldb, g.b_rows, g.b_cols, (MODE == W_FWD) ? 128 : 64);
-    if (a_ok && b_ok) {
+    bool io_ok = true;
+    if (MODE != W_WGRAD) io_ok = make_operand_map(fn, &tmC, g.C, g.ldc, g.M, g.N, 128);
+    else tmC = tmA;
+    if (MODE == W_DGRAD) io_ok = io_ok && make_operand_map(fn, &tmM, g.mask, g.ldm, g.M, g.N, 128);
+    else tmM = tmA;
+    if (a_ok && b_ok && io_ok) {
       static bool attr2_done = false;
       if (!attr2_done) {
-        NERFCA_CUDA_OK(cudaFuncSetAttribute(wide_gemm2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2_SMEM));
+        NERFCA_CUDA_OK(cudaFuncSetAttribute(wide_gemm2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w2_smem(MODE)));
         attr2_done = true;
       }
       const int n_mt = (int)((g.M + 127) / 128), n_nt = (g.N + 127) / 128;
       const long long total = (long long)n_mt * n_nt * splits;
       const unsigned grid2 = (unsigned)(total < wide_sm_count() ? total : wide_sm_count());
-      wide_gemm2_kernel<MODE><<<grid2, W2_THREADS, W2_SMEM, st>>>(tmA, tmB, g, n_mt, n_nt, (int)splits);
+      wide_gemm2_kernel<MODE><<<grid2, W2_THREADS, w2_smem(MODE), st>>>(tmA, tmB, tmC, tmM, g, n_mt, n_nt, (int)splits);
       NERFCA_LAUNCH_OK();
       return NERFCA_OK;
     }
