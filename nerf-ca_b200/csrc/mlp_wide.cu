@@ -590,30 +590,75 @@ __global__ void wide_out_forward_kernel(const bf16* __restrict__ h, const float*
   const int lane = threadIdx.x & 31;
   if (row >= np) return;
   float acc = 0.f;
-  for (int k = lane; k < H; k += 32) acc = fmaf(__bfloat162float(h[row * H + k]), __ldg(w + k), acc);
+  for (int c = lane * 8; c < H; c += 256) {      // 16-byte pieces: a warp reads 512 contiguous bytes of the row
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(h + row * H + c));
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c)), w1 = __ldg(reinterpret_cast<const float4*>(w + c + 4));
+    acc = fmaf(__uint_as_float(v.x << 16), w0.x, acc); acc = fmaf(__uint_as_float(v.x & 0xFFFF0000u), w0.y, acc);
+    acc = fmaf(__uint_as_float(v.y << 16), w0.z, acc); acc = fmaf(__uint_as_float(v.y & 0xFFFF0000u), w0.w, acc);
+    acc = fmaf(__uint_as_float(v.z << 16), w1.x, acc); acc = fmaf(__uint_as_float(v.z & 0xFFFF0000u), w1.y, acc);
+    acc = fmaf(__uint_as_float(v.w << 16), w1.z, acc); acc = fmaf(__uint_as_float(v.w & 0xFFFF0000u), w1.w, acc);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) raw[row] = acc + (b ? __ldg(b) : 0.f);
 }
-// backward of the output layer: dZ[p,k] = d_raw[p] w[k] 1[h>0];  dW[k] += sum_p d_raw[p] h[p,k];  db += sum_p d_raw[p]
-__global__ void wide_out_backward_kernel(const float* __restrict__ d_raw, const bf16* __restrict__ h, const float* __restrict__ w, long long np, int H,
-                                         bf16* __restrict__ dz, float* __restrict__ dw, float* __restrict__ db, float* __restrict__ db_prev) {
+// backward of the output layer: dZ[p,k] = d_raw[p] w[k] 1[h>0];  dW[k] += sum_p d_raw[p] h[p,k];  db += sum_p d_raw[p];
+// db_prev[k] += sum_p dZ[p,k] (the bias gradient of the last hidden layer).  Block = 128 rows; thread = (row lane 0..7, 8 columns): 16-byte
+// loads / stores, 512 contiguous bytes per warp and row; the eight row lanes meet in shared memory before the atomics.
+__global__ void __launch_bounds__(256) wide_out_backward_kernel(const float* __restrict__ d_raw, const bf16* __restrict__ h, const float* __restrict__ w,
+                                                                long long np, int H, bf16* __restrict__ dz, float* __restrict__ dw, float* __restrict__ db,
+                                                                float* __restrict__ db_prev) {
+  __shared__ float s_red[2][8][256];
   const long long r0 = (long long)blockIdx.x * W_ROWS_PER_BLOCK;
   const long long r1 = (r0 + W_ROWS_PER_BLOCK < np) ? r0 + W_ROWS_PER_BLOCK : np;
-  for (int k = threadIdx.x; k < H; k += blockDim.x) {
-    const float wk = __ldg(w + k);
-    float aw = 0.f, ab = 0.f, az = 0.f;
-    for (long long r = r0; r < r1; ++r) {
-      const float g = __ldg(d_raw + r), hv = __bfloat162float(h[r * H + k]);
-      const bf16 z = __float2bfloat16_rn(hv > 0.f ? g * wk : 0.f);
-      dz[r * H + k] = z;
-      az += __bfloat162float(z);            // bias gradient of the last hidden layer = column sums of the (rounded) dZ
-      aw = fmaf(g, hv, aw);
-      ab += g;
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  float ab = 0.f;
+  for (int c0 = 0; c0 < H; c0 += 256) {
+    const int c = c0 + cl * 8;
+    float aw[8], az[8], wk[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { aw[e] = az[e] = 0.f; wk[e] = (c + e < H) ? __ldg(w + c + e) : 0.f; }
+    if (c < H) {
+      for (long long r = r0 + rl; r < r1; r += 8) {
+        const float g = __ldg(d_raw + r);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(h + r * H + c));
+        const uint32_t hw[4] = {v.x, v.y, v.z, v.w};
+        uint32_t zo[4];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          const float h0 = __uint_as_float(hw[e2] << 16), h1 = __uint_as_float(hw[e2] & 0xFFFF0000u);
+          const bf16 z0 = __float2bfloat16_rn(h0 > 0.f ? g * wk[2 * e2] : 0.f), z1 = __float2bfloat16_rn(h1 > 0.f ? g * wk[2 * e2 + 1] : 0.f);
+          az[2 * e2] += __bfloat162float(z0); az[2 * e2 + 1] += __bfloat162float(z1);
+          aw[2 * e2] = fmaf(g, h0, aw[2 * e2]); aw[2 * e2 + 1] = fmaf(g, h1, aw[2 * e2 + 1]);
+          zo[e2] = (uint32_t)__bfloat16_as_ushort(z0) | ((uint32_t)__bfloat16_as_ushort(z1) << 16);
+        }
+        *reinterpret_cast<uint4*>(dz + r * H + c) = make_uint4(zo[0], zo[1], zo[2], zo[3]);
+        if (c0 == 0 && cl == 0) ab += g;
+      }
     }
-    atomicAdd(dw + k, aw);
-    if (db_prev) atomicAdd(db_prev + k, az);
-    if (k == 0 && db) atomicAdd(db, ab);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s_red[0][rl][cl * 8 + e] = aw[e]; s_red[1][rl][cl * 8 + e] = az[e]; }
+    __syncthreads();
+    {
+      const int k = c0 + (int)threadIdx.x;
+      if (k < H) {
+        float tw = 0.f, tz = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { tw += s_red[0][q][threadIdx.x]; tz += s_red[1][q][threadIdx.x]; }
+        atomicAdd(dw + k, tw);
+        if (db_prev) atomicAdd(db_prev + k, tz);
+      }
+    }
+    __syncthreads();
+  }
+  if (db) {                     // the eight row lanes' shares of sum_p d_raw[p]  (db is uniform over the block)
+    if (cl == 0) s_red[0][0][rl] = ab;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int q = 0; q < 8; ++q) t += s_red[0][0][q];
+      atomicAdd(db, t);
+    }
   }
 }
 // db[n] += sum_p dz[p,n]
@@ -676,19 +721,27 @@ __global__ void __launch_bounds__(256) wide_latent_grad_kernel(const bf16* __res
     for (int e = 0; e < 8; ++e)
 #pragma unroll
       for (int t = 0; t < 8; ++t) wreg[e][t] = (live && t < T) ? s_w[(((t << 3) + e) << 5) + lane] : 0.f;
-    for (int k = 0; k < WL_ROWS_PER_WARP; ++k) {
-      const long long p = r0 + k;
-      if (p >= src.n_points) break;
-      const int ph = load_phase(src, p);           // warp-uniform
-      if (ph != cur) { flush(); cur = ph; }
-      if (!live) continue;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(dz0 + p * H + lane * 8));
-      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    for (int k0 = 0; k0 < WL_ROWS_PER_WARP; k0 += 4) {      // four rows' loads in flight at a time
+      uint4 v4[4];
+      int ph4[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float d = __uint_as_float((e & 1) ? (w4[e >> 1] & 0xFFFF0000u) : (w4[e >> 1] << 16));
+      for (int u = 0; u < 4; ++u) {
+        const long long p = r0 + k0 + u;
+        const bool ok = p < src.n_points;
+        ph4[u] = ok ? load_phase(src, p) : -2;                 // warp-uniform; -2: past the end
+        v4[u] = (ok && live) ? __ldg(reinterpret_cast<const uint4*>(dz0 + p * H + lane * 8)) : make_uint4(0u, 0u, 0u, 0u);
+      }
 #pragma unroll
-        for (int t = 0; t < 8; ++t) acc[t] = fmaf(d, wreg[e][t], acc[t]);
+      for (int u = 0; u < 4; ++u) {
+        if (ph4[u] == -2) break;
+        if (ph4[u] != cur) { flush(); cur = ph4[u]; }
+        const uint32_t w4[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = __uint_as_float((e & 1) ? (w4[e >> 1] & 0xFFFF0000u) : (w4[e >> 1] << 16));
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc[t] = fmaf(d, wreg[e][t], acc[t]);
+        }
       }
     }
   } else
@@ -807,7 +860,7 @@ int wide_field_backward(const nerfca_field_t& f, const nerfca_samples_t& s, cons
     const unsigned rb = div_up(np, W_ROWS_PER_BLOCK);
     const bf16* h_last = st_h + ((size_t)(L - 1) * P + c0) * H;
     // (every kernel that produces a dZ also accumulates its column sums = the bias gradient of that layer)
-    wide_out_backward_kernel<<<rb, 128, 0, st>>>(d_raw + c0, h_last, f.weight[L], np, H, X, gr.weight[L], gr.bias[L], gr.bias[L - 1]);
+    wide_out_backward_kernel<<<rb, 256, 0, st>>>(d_raw + c0, h_last, f.weight[L], np, H, X, gr.weight[L], gr.bias[L], gr.bias[L - 1]);
     NERFCA_LAUNCH_OK();
     for (int l = L - 1; l >= 0; --l) {
       const bf16* h_prev = (l > 0) ? st_h + ((size_t)(l - 1) * P + c0) * H : st_x0 + (size_t)c0 * Dp;
