@@ -11,15 +11,15 @@
 //         wgrad     C += A^T H            A MN-major, H MN-major    (reduction = samples, split over tiles, fp32 vector reductions)
 //     wide_gemm2_kernel<MODE> (the default): persistent, one CTA per SM, 128 x 128 output tiles, warp-specialised -- one lane feeds a
 //     5-stage ring of 32 KB stages with 128-byte-swizzled tensor-map copies (TMA), one lane issues tcgen05.mma (M128 N128 K16,
-//     kind::f16) into one of two TMEM accumulators, 8 epilogue warps drain the other (tcgen05.ld -> bias / ReLU / mask -> padded
-//     shared-memory tile -> full-line global stores).  Depending on which matrix dimension is the reduction the same row-major bytes
+//     kind::f16) into one of two TMEM accumulators, 8 epilogue warps drain the other (tcgen05.ld -> bias / ReLU / mask -> 128-byte-swizzled
+//     shared-memory tile -> tensor-map store; the ReLU-mask tile of a dgrad comes in the same way).  Depending on which matrix dimension is the reduction the same row-major bytes
 //     are loaded as a K-major block (one 64 x 128 box) or an MN-major block (two 64 x 64 boxes), so no operand is ever transposed.
 //     wide_gemm_kernel<MODE> (fallback when the driver has no cuTensorMapEncodeTiled, or NERFCA_WIDE_TMA=0): one tile per CTA,
 //     operands staged by 16-byte cp.async copies straight into the UMMA no-swizzle canonical layout (tc_common.cuh), 3-stage ring.
 //   * the small kernels around the GEMMs (encoder: one thread per sample; output layer forward / backward; latent-gradient scatter)
 //     are single passes over their bf16 matrix.
-// Config 5 (1024 rays x 256 samples, hidden 256, 16 bands): 2.6 ms per step = 19 % of the tensor roofline (the per-thread cp.async version
-// of round 2a: 7.7 ms); the GEMMs run at 60-105 us against an HBM bound of 41-62 us per 262144 x 256 x 256 layer.
+// Config 5 (1024 rays x 256 samples, hidden 256, 16 bands): 2.3 ms per step = 22 % of the tensor roofline (the per-thread cp.async version
+// of round 2a: 7.7 ms); the GEMMs run at 57-78 us against an HBM bound of 41-62 us per 262144 x 256 x 256 layer.
 //
 // Reference: model/CPPN.py:88-110, model/Temporal.py:113-151 and their autograd.
 #include <cuda.h>
