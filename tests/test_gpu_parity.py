@@ -375,6 +375,36 @@ def test_fused_render_matches_oracle_and_normalisation():
     assert float(ev["pix_static_norm"].min()) == 0.0 and float(ev["pix_dynamic_norm"].max()) == 1.0
 
 
+def test_render_row_shards_equal_the_full_frame():
+    """SURVEY 8(e), rendering: the detector rows are sharded over the ranks with no collective (bench.py's `render` leg at every N).  Rays
+    are independent, so the rows rendered shard by shard must equal the frame rendered at once; the only difference allowed is the fp32
+    order in which a ray's tile segments reach its accumulator (atomics)."""
+    import proj_helpers as ph
+    from nerfca import ops
+    sd_s = orc.init_field_state(75, 128, 4, seed=1)
+    sd_d = orc.init_field_state(83, 128, 4, 10, 8, seed=2)
+    sd_d["output_linear.0.bias"] = sd_d["output_linear.0.bias"] + 0.5
+    mask, _ = orc.freq_mask(12, 120000, 150000, 1)
+    s, t = parity.build_models(sd_s, sd_d, DEV, "bf16", mask=mask)
+    s.eval(); t.eval()
+    o, d = ph.ray_values_tigre_device(60.0, 30.0, 0, GEOS[2], DEV)            # 64 x 64 detector
+    H, W = o.shape[0], o.shape[1]
+    z = orc.depth_values(3.2, 8.8, 500).to(DEV)
+    with torch.no_grad():
+        full = ops.render_frame(s, t, o.reshape(-1, 3), d.reshape(-1, 3), z, 4, parity.I0)
+        for world in (2, 3, 8):                                              # 3: uneven split of the 64 rows
+            parts = [[], [], []]
+            for rank in range(world):
+                r0, r1 = rank * H // world, (rank + 1) * H // world
+                out = ops.render_frame(s, t, o[r0:r1].reshape(-1, 3), d[r0:r1].reshape(-1, 3), z, 4, parity.I0)
+                for k in range(3):
+                    parts[k].append(out[k])
+            for k in range(3):
+                got = torch.cat(parts[k])
+                assert got.numel() == H * W
+                np.testing.assert_allclose(got.cpu().numpy(), full[k].cpu().numpy(), rtol=2e-6, atol=1e-7)
+
+
 def test_fine_pass_matches_reference_fixture(golden):
     """N3: obtain_train_predictions_iter with depth_samples_per_ray_fine = 16 through the drop-in functions (fp32 fields) vs the
     reference's outputs: coarse and fine pixels, both pairs of sigma arrays, the ray-0 dists; and gradients reach the fine nets."""
