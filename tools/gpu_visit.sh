@@ -1,6 +1,7 @@
 #!/bin/bash
 # One full GPU-box visit = what a profiles/<tag>/ directory holds: every GPU parity test, the bench line (both arms) of config 2 and
-# the config 3 / config 5 lines, a soak run, the ncu launch list of the bench command and one full ncu capture of the step's kernels.
+# the config 3 / config 5 lines, a soak run, the ncu launch list of the bench command, one full ncu capture of the step's kernels, the
+# same two for the layer-wise path, and a compute-sanitizer memcheck run.
 # Usage (from the repo root): gpurun --timeout 2400 -- 'bash tools/gpu_visit.sh tag [soak_steps]'
 # Afterwards here: python tools/ncu_summary.py / tools/make_traffic.py / tools/sass_summary.py, copy into profiles/<tag>/.
 TAG=${1:-run}; SOAK=${2:-70000}
@@ -27,4 +28,13 @@ python tools/launch_shares.py $OUT/launches.csv > $OUT/launch_shares.txt 2>&1; c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_(forward|bwd2?)_kernel|composite_loss' -s 3 -c 3 \
     -o $OUT/prof -f python tools/profile_step.py 1024 500 3 > $OUT/ncu_full.log 2>&1
 tail -3 $OUT/ncu_full.log
+# layer-wise path (config 5): launch list + full capture of the GEMM kernels, then compute-sanitizer memcheck of both paths
+NERFCA_CUPROF=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 200 --csv \
+    --log-file $OUT/launches_cfg5.csv python bench.py --config 5 --steps 1 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-render --no-dropin > $OUT/ncu_bench_cfg5.log 2>&1
+python tools/launch_list.py $OUT/launches_cfg5.csv > $OUT/launch_shares_cfg5.txt 2>&1; head -6 $OUT/launch_shares_cfg5.txt
+timeout 800 ncu --set full --clock-control none --import-source on -k regex:wide_gemm2 -s 8 -c 5 -o $OUT/wide -f \
+    python bench.py --config 5 --steps 1 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-render --no-dropin > $OUT/ncu_wide.log 2>&1
+timeout 900 compute-sanitizer --tool memcheck python -m pytest tests -m gpu -x -q \
+    -k "config5_widened_stress_shapes and bf16 or layerwise_tensor_core_path_other_shapes or composite_step_vs_oracle or trainer_step_from_ids or composite_step_30_phases or fused_render" > $OUT/memcheck.log 2>&1
+grep -E "ERROR SUMMARY|passed|failed" $OUT/memcheck.log
 ls -la $OUT
